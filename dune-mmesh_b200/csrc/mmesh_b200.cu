@@ -1,0 +1,723 @@
+// mmesh_b200.cu -- C-ABI implementation (include/mmesh_b200.h) on top of the sm_100a kernels in kernels.cuh.
+// Host side is plain C++/CUDA runtime: no torch, no CPU fallback.  Every entry point fails with
+// MMB_ERR_CUDA when no usable device / kernel image exists.
+#include "../../include/mmesh_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mmb;
+
+namespace {
+
+struct TimedLaunch { const char* name; cudaEvent_t a, b; };
+
+template <class T>
+struct DBuf {
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct mmb_context {
+  int device = 0, dim = 2;
+  cudaStream_t stream = nullptr; bool own_stream = false;
+  std::string err;
+  int64_t nv = 0, nc = 0, ne = 0, ns = 0, nc_pad = 0;
+  mmb_params prm{};
+  // mesh
+  DBuf<double> x, shift, dist;
+  DBuf<int32_t> cv[4], cells_aos, facets, facets_sorted;
+  DBuf<uint8_t> perm, valid_fp, edge_flag, longest;
+  DBuf<int8_t> orient, mark, imark;
+  DBuf<int4> edges;
+  DBuf<int32_t> wl, list_out;
+  DBuf<uint32_t> block_count;
+  DBuf<Counters> counters;
+  bool has_shift = false, dist_valid = false, mesh_ok = false;
+  // bvh
+  int L = 1;
+  DBuf<SegLeaf> seg_leaf; DBuf<double4> box2;
+  DBuf<TriLeaf> tri_leaf; DBuf<double> box3;
+  // projection
+  int64_t nnew = 0, npairs = 0, n_old = 0;
+  DBuf<long long> new_off; DBuf<int32_t> new_cell, old_idx; DBuf<double> old_xy, dofs_old, dofs_new, part_a, part_b, pair_vol;
+  int dofs_ncomp = 0;
+  // 3-D trace
+  DBuf<int32_t> tr_in, tr_out; DBuf<double> tr_u, tr_ug, tr_a, tr_b, tr_c;
+  // misc
+  DBuf<double> pred_pts; DBuf<int8_t> pred_sign;
+  Counters* h_counters = nullptr;   // pinned
+  bool timing = false;
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
+  int64_t launches = 0;
+  int num_sms = 148;
+};
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                     \
+      return MMB_ERR_CUDA;                                                                               \
+    }                                                                                                    \
+  } while (0)
+#define REQUIRE(cond, code, msg)                                                                         \
+  do { if (!(cond)) { ctx->err = msg; return code; } } while (0)
+
+static cudaEvent_t get_event(mmb_context* ctx) {
+  if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct LaunchScope {
+  mmb_context* ctx; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(mmb_context* c, const char* n) : ctx(c), name(n) {
+    ctx->launches++;
+    if (ctx->timing) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, ctx->stream); }
+  }
+  ~LaunchScope() { if (ctx->timing) { cudaEventRecord(b, ctx->stream); ctx->timed.push_back({ name, a, b }); } }
+};
+#define LAUNCH(name, kernel, grid, block, ...)                                                           \
+  do {                                                                                                   \
+    LaunchScope ls_(ctx, name);                                                                          \
+    kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                                            \
+  } while (0)
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
+static DevParams dev_params(const mmb_params& p) {
+  DevParams d; d.minH = p.minH; d.maxH = p.maxH; d.factor = p.factor; d.distProportion = p.distProportion;
+  d.edgeRatio = p.edgeRatio; d.radiusRatio = p.radiusRatio; d.clip_eps = p.clip_eps; d.drop_area = p.drop_area;
+  d.clip_translate = p.clip_translate; return d;
+}
+static int fetch_counters(mmb_context* ctx) {
+  CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MMB_OK;
+}
+#define TRY(expr) do { int rc_ = (expr); if (rc_ != MMB_OK) return rc_; } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mmb_create(int device, int dim, void* stream, mmb_context** out) {
+  if (!out || (dim != 2 && dim != 3)) return MMB_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MMB_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return MMB_ERR_CUDA;
+  // fail loudly when this build has no kernel image for the device (sm_100a only)
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, k_move) != cudaSuccess) { cudaGetLastError(); return MMB_ERR_CUDA; }
+  mmb_context* ctx = new mmb_context();
+  ctx->device = device; ctx->dim = dim;
+  if (stream) ctx->stream = (cudaStream_t)stream;
+  else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MMB_ERR_CUDA; } ctx->own_stream = true; }
+  cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (ctx->counters.ensure(1) != cudaSuccess || cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters)) != cudaSuccess) {
+    delete ctx; return MMB_ERR_CUDA;
+  }
+  cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), ctx->stream);
+  ctx->prm = mmb_params{ 0.0, 0.0, 1.0, 1.0, 4.0, 30.0, 1e-14, 1e-8, 0, 0 };
+  *out = ctx;
+  return MMB_OK;
+}
+
+int mmb_destroy(mmb_context* ctx) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  ctx->x.release(); ctx->shift.release(); ctx->dist.release();
+  for (auto& b : ctx->cv) b.release();
+  ctx->cells_aos.release(); ctx->facets.release(); ctx->facets_sorted.release();
+  ctx->perm.release(); ctx->valid_fp.release(); ctx->edge_flag.release(); ctx->longest.release();
+  ctx->orient.release(); ctx->mark.release(); ctx->imark.release(); ctx->edges.release();
+  ctx->wl.release(); ctx->list_out.release(); ctx->block_count.release(); ctx->counters.release();
+  ctx->seg_leaf.release(); ctx->box2.release(); ctx->tri_leaf.release(); ctx->box3.release();
+  ctx->new_off.release(); ctx->new_cell.release(); ctx->old_idx.release(); ctx->old_xy.release();
+  ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
+  ctx->tr_in.release(); ctx->tr_out.release(); ctx->tr_u.release(); ctx->tr_ug.release();
+  ctx->tr_a.release(); ctx->tr_b.release(); ctx->tr_c.release(); ctx->pred_pts.release(); ctx->pred_sign.release();
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return MMB_OK;
+}
+
+const char* mmb_last_error(const mmb_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* mmb_stream(const mmb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int mmb_synchronize(mmb_context* ctx) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MMB_OK;
+}
+int64_t mmb_launch_count(const mmb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int mmb_set_params(mmb_context* ctx, const mmb_params* p) {
+  if (!ctx || !p) return MMB_ERR_INVALID_ARG;
+  ctx->prm = *p; return MMB_OK;
+}
+int mmb_get_params(const mmb_context* ctx, mmb_params* p) {
+  if (!ctx || !p) return MMB_ERR_INVALID_ARG;
+  *p = ctx->prm; return MMB_OK;
+}
+
+// Morton key of a point inside a bounding box (host; upload time only)
+static uint64_t morton2(double x, double y, const double* lo, const double* inv) {
+  auto q = [](double t) { t = std::min(std::max(t, 0.0), 1.0); return (uint32_t)(t * 65535.0); };
+  auto spread = [](uint64_t v) {
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull; v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full; v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull; return v;
+  };
+  return spread(q((x - lo[0]) * inv[0])) | (spread(q((y - lo[1]) * inv[1])) << 1);
+}
+static uint64_t morton3(const double* c, const double* lo, const double* inv) {
+  auto q = [](double t) { t = std::min(std::max(t, 0.0), 1.0); return (uint64_t)(t * 1023.0); };
+  auto spread = [](uint64_t v) {
+    v = (v | (v << 16)) & 0x030000FFull; v = (v | (v << 8)) & 0x0300F00Full;
+    v = (v | (v << 4)) & 0x030C30C3ull; v = (v | (v << 2)) & 0x09249249ull; return v;
+  };
+  return spread(q((c[0] - lo[0]) * inv[0])) | (spread(q((c[1] - lo[1]) * inv[1])) << 1) | (spread(q((c[2] - lo[2]) * inv[2])) << 2);
+}
+
+int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t nc, const int32_t* cells_host,
+                    const uint8_t* perm_host, int64_t ne, const int32_t* edges_host, int64_t ns,
+                    const int32_t* facets_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(nv > 0 && nc >= 0 && ne >= 0 && ns >= 0 && x_host && (nc == 0 || (cells_host && perm_host)),
+          MMB_ERR_INVALID_ARG, "mmb_upload_mesh: bad sizes or null arrays");
+  REQUIRE(nv < (1ll << 31) && nc < (1ll << 31) && ne < (1ll << 31) && ns < (1ll << 24), MMB_ERR_CAPACITY,
+          "mmb_upload_mesh: int32 index space exceeded");
+  REQUIRE((ne == 0 || edges_host) && (ns == 0 || facets_host), MMB_ERR_INVALID_ARG, "mmb_upload_mesh: null edges/facets");
+  CK(cudaSetDevice(ctx->device));
+  const int dim = ctx->dim, k = dim + 1;
+  ctx->mesh_ok = false;
+  ctx->nv = nv; ctx->nc = nc; ctx->ne = ne; ctx->ns = ns;
+  ctx->nc_pad = (nc + 3) / 4 * 4;
+  const size_t nx = (size_t)nv * dim + 2;
+  CK(ctx->x.ensure(nx)); CK(ctx->shift.ensure(nx)); CK(ctx->dist.ensure(nv));
+  CK(cudaMemsetAsync(ctx->x.p, 0, nx * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(ctx->shift.p, 0, nx * sizeof(double), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->x.p, x_host, (size_t)nv * dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  for (int j = 0; j < k; ++j) CK(ctx->cv[j].ensure(ctx->nc_pad + 4));
+  CK(ctx->cells_aos.ensure((size_t)nc * k + 4));
+  CK(ctx->perm.ensure(ctx->nc_pad + 4)); CK(ctx->valid_fp.ensure(ctx->nc_pad + 4)); CK(ctx->orient.ensure(ctx->nc_pad + 4));
+  CK(ctx->mark.ensure(ctx->nc_pad + 4)); CK(ctx->longest.ensure(ctx->nc_pad + 4));
+  CK(ctx->wl.ensure(std::max(ctx->nc_pad, ne) + 4)); CK(ctx->list_out.ensure(std::max(ctx->nc_pad, ne) + 4));
+  CK(ctx->block_count.ensure((std::max(ctx->nc_pad, ne) + COMPACT_TILE - 1) / COMPACT_TILE + 1));
+  if (nc) {
+    CK(cudaMemcpyAsync(ctx->cells_aos.p, cells_host, (size_t)nc * k * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->perm.p, perm_host, (size_t)nc, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("cells_to_planes", k_cells_to_planes, grid_for(ctx->nc_pad, 256), 256, ctx->cells_aos.p, k, nc, ctx->nc_pad,
+           ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, k == 4 ? ctx->cv[3].p : nullptr);
+  }
+  if (dim == 2) {
+    CK(ctx->edges.ensure(ne + 1)); CK(ctx->edge_flag.ensure(ne + 4));
+    if (ne) CK(cudaMemcpyAsync(ctx->edges.p, edges_host, (size_t)ne * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // interface facets: original order (marks) + Morton order (BVH leaves)
+  CK(ctx->facets.ensure((size_t)ns * dim + 2)); CK(ctx->facets_sorted.ensure((size_t)ns * dim + 2)); CK(ctx->imark.ensure(ns + 4));
+  int L = 1; while (L < ns) L <<= 1;
+  ctx->L = L;
+  if (ns) {
+    CK(cudaMemcpyAsync(ctx->facets.p, facets_host, (size_t)ns * dim * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, inv[3];
+    std::vector<double> mid((size_t)ns * dim);
+    for (int64_t s = 0; s < ns; ++s)
+      for (int j = 0; j < dim; ++j) {
+        double m = 0;
+        for (int c = 0; c < dim; ++c) m += x_host[(size_t)facets_host[s * dim + c] * dim + j];
+        m /= dim; mid[s * dim + j] = m; lo[j] = std::min(lo[j], m); hi[j] = std::max(hi[j], m);
+      }
+    for (int j = 0; j < dim; ++j) inv[j] = hi[j] > lo[j] ? 1.0 / (hi[j] - lo[j]) : 0.0;
+    std::vector<std::pair<uint64_t, int32_t>> keyed(ns);
+    for (int64_t s = 0; s < ns; ++s)
+      keyed[s] = { dim == 2 ? morton2(mid[2 * s], mid[2 * s + 1], lo, inv) : morton3(&mid[3 * s], lo, inv), (int32_t)s };
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<int32_t> sorted((size_t)ns * dim);
+    for (int64_t s = 0; s < ns; ++s)
+      for (int c = 0; c < dim; ++c) sorted[s * dim + c] = facets_host[(size_t)keyed[s].second * dim + c];
+    CK(cudaMemcpyAsync(ctx->facets_sorted.p, sorted.data(), sorted.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // `sorted` is a stack-owned staging buffer
+  }
+  if (dim == 2) { CK(ctx->seg_leaf.ensure(L)); CK(ctx->box2.ensure(2 * (size_t)L)); }
+  else { CK(ctx->tri_leaf.ensure(L)); CK(ctx->box3.ensure(12 * (size_t)L)); }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  ctx->has_shift = false; ctx->dist_valid = false; ctx->mesh_ok = true;
+  ctx->nnew = ctx->npairs = 0;
+  return MMB_OK;
+}
+
+int mmb_upload_coords(mmb_context* ctx, const double* x_host) {
+  if (!ctx || !x_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  CK(cudaMemcpyAsync(ctx->x.p, x_host, (size_t)ctx->nv * ctx->dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->dist_valid = false;
+  return MMB_OK;
+}
+int mmb_download_coords(mmb_context* ctx, double* x_host) {
+  if (!ctx || !x_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  CK(cudaMemcpyAsync(x_host, ctx->x.p, (size_t)ctx->nv * ctx->dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MMB_OK;
+}
+int mmb_upload_shifts(mmb_context* ctx, const double* shifts_host) {
+  if (!ctx || !shifts_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  CK(cudaMemcpyAsync(ctx->shift.p, shifts_host, (size_t)ctx->nv * ctx->dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->has_shift = true;
+  return MMB_OK;
+}
+static int stage_shifts(mmb_context* ctx, const double* shifts_host) {
+  if (shifts_host) return mmb_upload_shifts(ctx, shifts_host);
+  REQUIRE(ctx->has_shift, MMB_ERR_STATE, "shifts == NULL but no resident shifts (mmb_upload_shifts)");
+  return MMB_OK;
+}
+
+// ---- move ---------------------------------------------------------------------------------------------
+static int do_move(mmb_context* ctx) {
+  const int64_t n2 = ((int64_t)ctx->nv * ctx->dim + 1) / 2;
+  LAUNCH("move", k_move, std::min<unsigned>(grid_for(n2, 256), ctx->num_sms * 16), 256, (double2*)ctx->x.p,
+         (const double2*)ctx->shift.p, n2);
+  ctx->dist_valid = false;
+  return MMB_OK;
+}
+int mmb_move_vertices(mmb_context* ctx, const double* shifts_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  TRY(stage_shifts(ctx, shifts_host));
+  TRY(do_move(ctx));
+  CK(cudaGetLastError());
+  return MMB_OK;
+}
+
+// ---- trial move + validity ------------------------------------------------------------------------------
+static int do_validate(mmb_context* ctx, bool with_shift) {
+  Counters* c = ctx->counters.p;
+  const unsigned fb = ctx->num_sms * 4;
+  if (ctx->dim == 2) {
+    const int64_t nc4 = ctx->nc_pad / 4;
+    if (with_shift)
+      LAUNCH("validate2d", k_validate2d<true>, grid_for(nc4, 256), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
+             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, nc4, ctx->nc,
+             (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
+    else
+      LAUNCH("validate2d", k_validate2d<false>, grid_for(nc4, 256), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
+             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, nc4, ctx->nc,
+             (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
+    if (with_shift)
+      LAUNCH("exact_orient2d", k_exact_orient2d<true>, fb, 128, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
+             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->orient.p, c);
+    else
+      LAUNCH("exact_orient2d", k_exact_orient2d<false>, fb, 128, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
+             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->orient.p, c);
+  } else {
+    if (with_shift)
+      LAUNCH("validate3d", k_validate3d<true>, grid_for(ctx->nc, 256), 256, ctx->x.p, ctx->shift.p, ctx->cv[0].p, ctx->cv[1].p,
+             ctx->cv[2].p, ctx->cv[3].p, ctx->nc, ctx->valid_fp.p, ctx->orient.p, ctx->wl.p, c);
+    else
+      LAUNCH("validate3d", k_validate3d<false>, grid_for(ctx->nc, 256), 256, ctx->x.p, ctx->shift.p, ctx->cv[0].p, ctx->cv[1].p,
+             ctx->cv[2].p, ctx->cv[3].p, ctx->nc, ctx->valid_fp.p, ctx->orient.p, ctx->wl.p, c);
+    if (with_shift)
+      LAUNCH("exact_orient3d", k_exact_orient3d<true>, fb, 128, ctx->x.p, ctx->shift.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p,
+             ctx->cv[3].p, ctx->wl.p, ctx->orient.p, c);
+    else
+      LAUNCH("exact_orient3d", k_exact_orient3d<false>, fb, 128, ctx->x.p, ctx->shift.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p,
+             ctx->cv[3].p, ctx->wl.p, ctx->orient.p, c);
+  }
+  return MMB_OK;
+}
+static int zero_counters(mmb_context* ctx) {
+  CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), ctx->stream));
+  return MMB_OK;
+}
+int mmb_trial_move_validate(mmb_context* ctx, const double* shifts_host, uint8_t* valid_fp_host, int8_t* orient_sign_host,
+                            int64_t* n_invalid) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  TRY(stage_shifts(ctx, shifts_host));
+  // keep max_dist across calls: only the validity counters are reset
+  CK(cudaMemsetAsync(&ctx->counters.p->n_invalid, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->wl_orient, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->n_exact_orient, 0, sizeof(unsigned long long), ctx->stream));
+  TRY(do_validate(ctx, true));
+  if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, (size_t)ctx->nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, (size_t)ctx->nc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaGetLastError());
+  if (n_invalid || valid_fp_host || orient_sign_host || ctx->dim == 3) {
+    TRY(fetch_counters(ctx));
+    if (n_invalid) *n_invalid = (int64_t)ctx->h_counters->n_invalid;
+    if (ctx->dim == 3 && ctx->h_counters->n_invalid > 0) {
+      ctx->err = "Vertices could not be moved, because the removal of vertices is not supported in 3D!";
+      return MMB_ERR_INVALID_CELL_3D;
+    }
+  }
+  return MMB_OK;
+}
+
+// ordered compaction helper -> ctx->list_out; total in *n_total
+static int compact_flags(mmb_context* ctx, const uint8_t* flags, int64_t n, uint8_t match, int32_t* out_host, int64_t cap,
+                         int64_t* n_total) {
+  const int nb = (int)((n + COMPACT_TILE - 1) / COMPACT_TILE);
+  if (nb == 0) { if (n_total) *n_total = 0; return MMB_OK; }
+  LAUNCH("compact_count", k_compact_count, nb, 256, flags, n, match, ctx->block_count.p);
+  LAUNCH("compact_scan", k_compact_scan, 1, 1024, ctx->block_count.p, nb, &ctx->counters.p->pad_[0]);
+  LAUNCH("compact_scatter", k_compact_scatter, nb, 256, flags, n, match, ctx->block_count.p, ctx->list_out.p,
+         (int64_t)ctx->list_out.cap);
+  CK(cudaGetLastError());
+  TRY(fetch_counters(ctx));
+  const int64_t tot = (int64_t)ctx->h_counters->pad_[0];
+  if (n_total) *n_total = tot;
+  if (out_host && cap > 0 && tot > 0) {
+    CK(cudaMemcpyAsync(out_host, ctx->list_out.p, (size_t)std::min(cap, tot) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return MMB_OK;
+}
+int mmb_invalid_cells(mmb_context* ctx, int32_t* cells_host, int64_t cap, int64_t* n_total) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  return compact_flags(ctx, ctx->valid_fp.p, ctx->nc, 0, cells_host, cap, n_total);
+}
+int mmb_marked_cells(mmb_context* ctx, int which, int32_t* cells_host, int64_t cap, int64_t* n_total) {
+  if (!ctx || (which != 1 && which != -1)) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  return compact_flags(ctx, (const uint8_t*)ctx->mark.p, ctx->nc, which == 1 ? 1 : 0xFF, cells_host, cap, n_total);
+}
+
+// ---- legality -------------------------------------------------------------------------------------------
+static int do_legality(mmb_context* ctx) {
+  if (ctx->ne == 0) return MMB_OK;
+  LAUNCH("legality", k_legality<false>, grid_for(ctx->ne, 256), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
+         (const int4*)ctx->edges.p, ctx->ne, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p);
+  LAUNCH("exact_incircle", k_exact_incircle<false>, ctx->num_sms * 4, 128, (const double2*)ctx->x.p,
+         (const double2*)ctx->shift.p, (const int4*)ctx->edges.p, ctx->wl.p, ctx->edge_flag.p, ctx->counters.p);
+  return MMB_OK;
+}
+int mmb_legality(mmb_context* ctx, uint8_t* flags_host, int64_t* n_illegal) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "legality needs an uploaded 2-D mesh");
+  CK(cudaMemsetAsync(&ctx->counters.p->n_illegal, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->wl_incircle, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->n_exact_incircle, 0, sizeof(unsigned long long), ctx->stream));
+  TRY(do_legality(ctx));
+  if (flags_host && ctx->ne) CK(cudaMemcpyAsync(flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaGetLastError());
+  if (flags_host || n_illegal) { TRY(fetch_counters(ctx)); if (n_illegal) *n_illegal = (int64_t)ctx->h_counters->n_illegal; }
+  return MMB_OK;
+}
+
+// ---- distance -------------------------------------------------------------------------------------------
+static int do_distance(mmb_context* ctx) {
+  CK(cudaMemsetAsync(&ctx->counters.p->max_dist_bits, 0, sizeof(unsigned long long), ctx->stream));
+  const int ns = (int)ctx->ns, L = ctx->L;
+  if (ctx->dim == 2) {
+    if (ns) {
+      LAUNCH("seg_prepare", k_seg_prepare, grid_for(L, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets_sorted.p, ns, L,
+             ctx->seg_leaf.p, ctx->box2.p);
+      LAUNCH("bvh_upper", k_bvh_upper, 1, 1024, L, ctx->box2.p);
+    }
+    LAUNCH("distance2d", k_distance2d, grid_for(ctx->nv, 256), 256, (const double2*)ctx->x.p, ctx->nv, ctx->seg_leaf.p,
+           ctx->box2.p, ns, L, ctx->dist.p, ctx->counters.p);
+  } else {
+    if (ns) {
+      LAUNCH("tri_prepare", k_tri_prepare, grid_for(L, 256), 256, ctx->x.p, ctx->facets_sorted.p, ns, L, ctx->tri_leaf.p, ctx->box3.p);
+      LAUNCH("bvh_upper3", k_bvh_upper3, 1, 1024, L, ctx->box3.p);
+    }
+    LAUNCH("distance3d", k_distance3d, grid_for(ctx->nv, 256), 256, ctx->x.p, ctx->nv, ctx->tri_leaf.p, ctx->box3.p, ns, L,
+           ctx->dist.p, ctx->counters.p);
+  }
+  ctx->dist_valid = true;
+  return MMB_OK;
+}
+int mmb_distance_update(mmb_context* ctx, double* dist_host, double* max_out) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  TRY(do_distance(ctx));
+  if (dist_host) CK(cudaMemcpyAsync(dist_host, ctx->dist.p, (size_t)ctx->nv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaGetLastError());
+  if (dist_host || max_out) {
+    TRY(fetch_counters(ctx));
+    if (max_out) { double m; memcpy(&m, &ctx->h_counters->max_dist_bits, 8); *max_out = m; }
+  }
+  return MMB_OK;
+}
+int mmb_distance_set(mmb_context* ctx, const double* dist_host) {
+  if (!ctx || !dist_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  CK(cudaMemcpyAsync(ctx->dist.p, dist_host, (size_t)ctx->nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  double m = 0.0;
+  for (int64_t i = 0; i < ctx->nv; ++i) m = std::max(dist_host[i], m);
+  CK(cudaMemcpyAsync(&ctx->counters.p->max_dist_bits, &m, 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->dist_valid = true;
+  return MMB_OK;
+}
+
+// ---- indicator ------------------------------------------------------------------------------------------
+int mmb_indicator_init(mmb_context* ctx) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "indicator_init needs an uploaded 2-D mesh");
+  Counters* c = ctx->counters.p;
+  const unsigned long long init[4] = { ~0ull, 0ull, ~0ull, 0ull };
+  CK(cudaMemcpyAsync(c->minmax_bits, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->ns)
+    LAUNCH("edge_minmax", k_edge_minmax, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, ctx->facets.p, 2, ctx->ns,
+           &c->minmax_bits[0], &c->minmax_bits[1]);
+  if (ctx->ne)
+    LAUNCH("edge_minmax", k_edge_minmax, grid_for(ctx->ne, 256), 256, (const double2*)ctx->x.p, (const int32_t*)ctx->edges.p, 4,
+           ctx->ne, &c->minmax_bits[2], &c->minmax_bits[3]);
+  CK(cudaGetLastError());
+  TRY(fetch_counters(ctx));
+  auto as_d = [](unsigned long long b) { double d; memcpy(&d, &b, 8); return d; };
+  const double K = 2.0, k = K / (2.0 * 4.0);
+  double maxH = 0.0, minH = 1e100, maxh = 0.0, minh = 1e100;
+  if (ctx->ns) { minH = std::min(minH, as_d(ctx->h_counters->minmax_bits[0])); maxH = std::max(maxH, as_d(ctx->h_counters->minmax_bits[1])); }
+  if (ctx->ne) { minh = std::min(minh, as_d(ctx->h_counters->minmax_bits[2])); maxh = std::max(maxh, as_d(ctx->h_counters->minmax_bits[3])); }
+  maxH = K * maxH; minH = k * minH;
+  if (ctx->ns == 0) { maxH = K * maxh; minH = k * minh; }
+  ctx->prm.maxH = maxH; ctx->prm.minH = minH; ctx->prm.factor = maxh / minh;
+  return MMB_OK;
+}
+static int do_mark(mmb_context* ctx) {
+  const DevParams dp = dev_params(ctx->prm);
+  if (ctx->dim == 2)
+    LAUNCH("mark2d", k_mark2d, grid_for(ctx->nc, 256), 256, (const double2*)ctx->x.p, ctx->dist.p, ctx->cv[0].p, ctx->cv[1].p,
+           ctx->cv[2].p, ctx->perm.p, ctx->nc, dp, ctx->counters.p, ctx->mark.p, ctx->longest.p, ctx->counters.p);
+  else
+    LAUNCH("mark3d", k_mark3d, grid_for(ctx->nc, 256), 256, ctx->x.p, ctx->dist.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p,
+           ctx->cv[3].p, ctx->perm.p, ctx->nc, dp, ctx->counters.p, ctx->mark.p, ctx->longest.p, ctx->counters.p);
+  return MMB_OK;
+}
+int mmb_mark_elements(mmb_context* ctx, int run_distance, int8_t* marks_host, uint8_t* longest_edge_host, int64_t counts[2]) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  if (run_distance) TRY(do_distance(ctx));
+  REQUIRE(ctx->dist_valid, MMB_ERR_STATE, "markElements before Distance::update");
+  CK(cudaMemsetAsync(&ctx->counters.p->n_refine, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  TRY(do_mark(ctx));
+  if (marks_host) CK(cudaMemcpyAsync(marks_host, ctx->mark.p, (size_t)ctx->nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (longest_edge_host) CK(cudaMemcpyAsync(longest_edge_host, ctx->longest.p, (size_t)ctx->nc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaGetLastError());
+  if (marks_host || longest_edge_host || counts) {
+    TRY(fetch_counters(ctx));
+    if (counts) { counts[0] = (int64_t)ctx->h_counters->n_refine; counts[1] = (int64_t)ctx->h_counters->n_coarsen; }
+  }
+  return MMB_OK;
+}
+int mmb_mark_interface(mmb_context* ctx, int8_t* marks_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "mark_interface needs an uploaded 2-D mesh");
+  REQUIRE(ctx->dist_valid, MMB_ERR_STATE, "mark_interface before Distance::update");
+  if (ctx->ns == 0) return MMB_OK;
+  LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
+         (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
+  CK(cudaGetLastError());
+  if (marks_host) {
+    CK(cudaMemcpyAsync(marks_host, ctx->imark.p, (size_t)ctx->ns, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return MMB_OK;
+}
+
+// ---- projection -----------------------------------------------------------------------------------------
+int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host, const int32_t* new_cell_host, int64_t npairs,
+                     const double* old_xy_host, const int32_t* old_idx_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "projection needs an uploaded 2-D mesh");
+  REQUIRE(nnew >= 0 && npairs >= 0 && (nnew == 0 || (new_off_host && new_cell_host)) && (npairs == 0 || (old_xy_host && old_idx_host)),
+          MMB_ERR_INVALID_ARG, "mmb_upload_pairs: null arrays");
+  CK(ctx->new_off.ensure(nnew + 1)); CK(ctx->new_cell.ensure(nnew + 1)); CK(ctx->old_idx.ensure(npairs + 1));
+  CK(ctx->old_xy.ensure(6 * (size_t)npairs + 1)); CK(ctx->pair_vol.ensure(npairs + 1));
+  const int nb = (int)grid_for(nnew, 128);
+  CK(ctx->part_a.ensure(nb)); CK(ctx->part_b.ensure(nb));
+  if (nnew) {
+    CK(cudaMemcpyAsync(ctx->new_off.p, new_off_host, (size_t)(nnew + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->new_cell.p, new_cell_host, (size_t)nnew * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (npairs) {
+    CK(cudaMemcpyAsync(ctx->old_idx.p, old_idx_host, (size_t)npairs * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->old_xy.p, old_xy_host, 6 * (size_t)npairs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->nnew = nnew; ctx->npairs = npairs;
+  return MMB_OK;
+}
+static int do_project(mmb_context* ctx, int ncomp) {
+  if (ctx->nnew == 0) return MMB_OK;
+  const DevParams dp = dev_params(ctx->prm);
+  const unsigned nb = grid_for(ctx->nnew, 128);
+  if (ncomp == 1)
+    LAUNCH("project_p0", k_project<1>, nb, 128, (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p,
+           ctx->new_off.p, ctx->new_cell.p, ctx->nnew, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp,
+           ctx->part_a.p, ctx->part_b.p, ctx->counters.p);
+  else
+    LAUNCH("project_p1", k_project<3>, nb, 128, (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p,
+           ctx->new_off.p, ctx->new_cell.p, ctx->nnew, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp,
+           ctx->part_a.p, ctx->part_b.p, ctx->counters.p);
+  LAUNCH("reduce_partials", k_reduce_partials, 1, 1024, ctx->part_a.p, ctx->part_b.p, (int)nb, ctx->counters.p);
+  return MMB_OK;
+}
+static int stage_dofs(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_old_host) {
+  REQUIRE(ncomp == 1 || ncomp == 3, MMB_ERR_INVALID_ARG, "ncomp must be 1 (P0) or 3 (DG-P1)");
+  if (dofs_old_host) {
+    REQUIRE(n_old > 0, MMB_ERR_INVALID_ARG, "n_old must be positive");
+    CK(ctx->dofs_old.ensure((size_t)n_old * ncomp));
+    CK(cudaMemcpyAsync(ctx->dofs_old.p, dofs_old_host, (size_t)n_old * ncomp * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_old = n_old; ctx->dofs_ncomp = ncomp;
+  } else REQUIRE(ctx->dofs_ncomp == ncomp, MMB_ERR_STATE, "dofs_old == NULL but no resident DOFs of this ncomp");
+  if (ctx->dofs_new.cap < (size_t)ctx->nc * ncomp) {
+    CK(ctx->dofs_new.ensure((size_t)ctx->nc * ncomp));
+    CK(cudaMemsetAsync(ctx->dofs_new.p, 0, (size_t)ctx->nc * ncomp * sizeof(double), ctx->stream));
+  }
+  return MMB_OK;
+}
+int mmb_project(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_old_host, double* dofs_new_host, double* mass_new,
+                double* covered_area, int64_t* n_pieces) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "projection needs an uploaded 2-D mesh");
+  TRY(stage_dofs(ctx, ncomp, n_old, dofs_old_host));
+  CK(cudaMemsetAsync(&ctx->counters.p->n_pieces, 0, sizeof(unsigned long long), ctx->stream));
+  TRY(do_project(ctx, ncomp));
+  if (dofs_new_host) CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, (size_t)ctx->nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaGetLastError());
+  if (dofs_new_host || mass_new || covered_area || n_pieces) {
+    TRY(fetch_counters(ctx));
+    if (mass_new) *mass_new = ctx->h_counters->mass_new;
+    if (covered_area) *covered_area = ctx->h_counters->covered_area;
+    if (n_pieces) *n_pieces = (int64_t)ctx->h_counters->n_pieces;
+  }
+  return MMB_OK;
+}
+int mmb_intersection_volumes(mmb_context* ctx, double* vol_host) {
+  if (!ctx || !vol_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2 && ctx->nnew > 0, MMB_ERR_STATE, "no pairs uploaded");
+  LAUNCH("isect_volume", k_isect_volume, grid_for(ctx->nnew, 128), 128, (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p,
+         ctx->cv[2].p, ctx->new_off.p, ctx->new_cell.p, ctx->nnew, ctx->old_xy.p, ctx->pair_vol.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(vol_host, ctx->pair_vol.p, (size_t)ctx->npairs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MMB_OK;
+}
+
+// ---- whole step -----------------------------------------------------------------------------------------
+int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_step_result* res) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  REQUIRE(ncomp == 0 || ctx->dim == 2, MMB_ERR_INVALID_ARG, "projection is 2-D only (geometryInFather, entity.hh:573-594)");
+  TRY(stage_shifts(ctx, shifts_host));
+  if (ncomp) TRY(stage_dofs(ctx, ncomp, 0, nullptr));
+  TRY(zero_counters(ctx));
+  TRY(do_distance(ctx));            // markElements: indicator_.update()
+  TRY(do_mark(ctx));                //               bulk marks (+ longest edge)
+  if (ctx->dim == 2 && ctx->ns)
+    LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
+           (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
+  TRY(do_validate(ctx, true));      // ensureVertexMovement (trial move, coordinates untouched)
+  if (ncomp) TRY(do_project(ctx, ncomp));   // adapt(handle): old children -> new cells, before the real move
+  TRY(do_move(ctx));                // moveVertices
+  if (ctx->dim == 2) TRY(do_legality(ctx));   // in-circle flags of the moved mesh (input of the next host TDS pass)
+  CK(cudaGetLastError());
+  if (res) {
+    TRY(fetch_counters(ctx));
+    const Counters& c = *ctx->h_counters;
+    res->n_invalid = (int64_t)c.n_invalid; res->n_orient_nonpos = (int64_t)c.n_orient_nonpos; res->n_illegal = (int64_t)c.n_illegal;
+    res->n_refine = (int64_t)c.n_refine; res->n_coarsen = (int64_t)c.n_coarsen;
+    res->n_exact_orient = (int64_t)c.n_exact_orient; res->n_exact_incircle = (int64_t)c.n_exact_incircle;
+    res->n_pieces = (int64_t)c.n_pieces; memcpy(&res->max_dist, &c.max_dist_bits, 8);
+    res->mass_new = c.mass_new; res->covered_area = c.covered_area;
+    if (ctx->dim == 3 && c.n_invalid > 0) {
+      ctx->err = "Vertices could not be moved, because the removal of vertices is not supported in 3D!";
+      return MMB_ERR_INVALID_CELL_3D;
+    }
+  }
+  return MMB_OK;
+}
+
+// ---- 3-D P0 trace / skeleton ----------------------------------------------------------------------------
+int mmb_trace_skeleton_p0(mmb_context* ctx, int64_t nf, const int32_t* inside_host, const int32_t* outside_host,
+                          const double* u_bulk_host, int64_t n_bulk, const double* u_gamma_host, double* trace_in_host,
+                          double* trace_out_host, double* skeleton_host) {
+  if (!ctx || nf <= 0 || !inside_host || !outside_host || !u_bulk_host || !u_gamma_host || n_bulk <= 0) return MMB_ERR_INVALID_ARG;
+  CK(ctx->tr_in.ensure(nf)); CK(ctx->tr_out.ensure(nf)); CK(ctx->tr_u.ensure(n_bulk)); CK(ctx->tr_ug.ensure(nf));
+  CK(ctx->tr_a.ensure(nf)); CK(ctx->tr_b.ensure(nf)); CK(ctx->tr_c.ensure(nf));
+  CK(cudaMemcpyAsync(ctx->tr_in.p, inside_host, nf * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tr_out.p, outside_host, nf * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tr_u.p, u_bulk_host, n_bulk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tr_ug.p, u_gamma_host, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH("trace_skeleton", k_trace_skeleton, grid_for(nf, 256), 256, nf, ctx->tr_in.p, ctx->tr_out.p, ctx->tr_u.p, ctx->tr_ug.p,
+         ctx->tr_a.p, ctx->tr_b.p, ctx->tr_c.p);
+  CK(cudaGetLastError());
+  if (trace_in_host) CK(cudaMemcpyAsync(trace_in_host, ctx->tr_a.p, nf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (trace_out_host) CK(cudaMemcpyAsync(trace_out_host, ctx->tr_b.p, nf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (skeleton_host) CK(cudaMemcpyAsync(skeleton_host, ctx->tr_c.p, nf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MMB_OK;
+}
+
+// ---- predicate batches ----------------------------------------------------------------------------------
+int mmb_predicate_batch(mmb_context* ctx, int which, int64_t n, const double* pts_host, int8_t* sign_host, int64_t* n_exact) {
+  if (!ctx || which < 0 || which > 2 || n <= 0 || !pts_host || !sign_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(n < (1ll << 31), MMB_ERR_CAPACITY, "batch too large");
+  const int k = which == 0 ? 6 : (which == 1 ? 8 : 12);
+  CK(ctx->pred_pts.ensure((size_t)n * k)); CK(ctx->pred_sign.ensure(n)); CK(ctx->wl.ensure(n + 4));
+  CK(cudaMemcpyAsync(ctx->pred_pts.p, pts_host, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->wl_orient, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->n_exact_orient, 0, sizeof(unsigned long long), ctx->stream));
+  LAUNCH("pred_filter", k_pred_filter, grid_for(n, 256), 256, which, ctx->pred_pts.p, n, ctx->pred_sign.p, ctx->wl.p, ctx->counters.p);
+  LAUNCH("pred_exact", k_pred_exact, ctx->num_sms * 4, 128, which, ctx->pred_pts.p, ctx->wl.p, ctx->pred_sign.p, ctx->counters.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(sign_host, ctx->pred_sign.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(fetch_counters(ctx));
+  if (n_exact) *n_exact = (int64_t)ctx->h_counters->n_exact_orient;
+  return MMB_OK;
+}
+
+// ---- timing ---------------------------------------------------------------------------------------------
+int mmb_timing_enable(mmb_context* ctx, int on) { if (!ctx) return MMB_ERR_INVALID_ARG; ctx->timing = on != 0; return MMB_OK; }
+int mmb_timing_reset(mmb_context* ctx) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& t : ctx->timed) { ctx->event_pool.push_back(t.a); ctx->event_pool.push_back(t.b); }
+  ctx->timed.clear();
+  return MMB_OK;
+}
+int mmb_timing_get(mmb_context* ctx, int cap, const char** names, double* total_ms, int64_t* launches) {
+  if (!ctx) return 0;
+  cudaStreamSynchronize(ctx->stream);
+  std::vector<const char*> order; std::map<std::string, std::pair<double, int64_t>> agg; std::map<std::string, const char*> nm;
+  for (auto& t : ctx->timed) {
+    float ms = 0.f; cudaEventElapsedTime(&ms, t.a, t.b);
+    auto it = agg.find(t.name);
+    if (it == agg.end()) { agg[t.name] = { ms, 1 }; nm[t.name] = t.name; order.push_back(t.name); }
+    else { it->second.first += ms; it->second.second++; }
+  }
+  int n = 0;
+  for (auto* name : order) {
+    if (n < cap) { if (names) names[n] = name; if (total_ms) total_ms[n] = agg[name].first; if (launches) launches[n] = agg[name].second; }
+    ++n;
+  }
+  return n;
+}
+
+}  // extern "C"

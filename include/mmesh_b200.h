@@ -1,0 +1,159 @@
+/*
+ * mmesh_b200.h -- C-ABI of the B200-native moving-mesh hot path (drop-in boundary).
+ *
+ * The reference (samuelburbulla/dune-mmesh) has no FFI for this path: its boundary is the C++ member API
+ * of Dune::MMesh / RatioIndicator / Distance (dune/mmesh/grid/mmesh.hh, dune/mmesh/remeshing/*.hh),
+ * re-exported 1:1 to Python by dune/python/mmesh/grid.hh:82-137.  Each entry point below names the
+ * reference member it replaces.  Plain C types only; no exceptions cross this boundary; every function
+ * returns an mmb_status.  All `*_host` pointers are caller-owned HOST memory; a NULL output pointer means
+ * "leave the result resident on the device", a NULL shifts pointer means "use the resident shifts"
+ * (mmb_upload_shifts).  One context per GPU; calls on one context must be serialised by the caller
+ * (the reference is single-threaded and not re-entrant either, mmesh.hh:608,1787-1789).
+ *
+ * Snapshot conventions (what a host adapter extracts from a live Dune::MMesh):
+ *   x       [nv][dim] doubles, leaf vertex index order (indexsets.hh:242-245); same memory layout as
+ *                     std::vector<FieldVector<double,dim>>, so reference `shifts` vectors pass through as-is
+ *   cells   [nc][dim+1] int32, face->vertex(k)->info().index in CGAL TDS order (Triangulation_2.h:1152-1154)
+ *   perm    [nc] uint8, bits (2k+1:2k) = ElementInfo::cgalIndex[k] (cgal/defaults.hh:29, common.hh:55-65)
+ *   edges   [ne][4] int32 (a,b,c,d): edge (a,b); c = apex with (a,b,c) ccw; d = opposite apex, -1 on the hull
+ *   facets  [ns][dim] int32 interface facets, corners in DUNE facet order (lower persistent id first)
+ */
+#ifndef MMESH_B200_H
+#define MMESH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mmb_context mmb_context;
+
+typedef enum mmb_status {
+  MMB_OK = 0,
+  MMB_ERR_INVALID_ARG = 1,
+  MMB_ERR_CUDA = 2,
+  MMB_ERR_NCCL = 3,
+  MMB_ERR_INVALID_CELL_3D = 4, /* the DUNE_THROW(GridError) of mmesh.hh:1104-1107 */
+  MMB_ERR_CAPACITY = 5,
+  MMB_ERR_STATE = 6            /* e.g. mark before distance update, project before upload */
+} mmb_status;
+
+/* Mutable members of RatioIndicator (ratioindicator.hh:165-182,191-199) + the projection constants that are
+   hard-coded in the reference (polygoncutting.hh:63, cutsettriangulation.hh:60). */
+typedef struct mmb_params {
+  double minH, maxH, factor, distProportion;
+  double edgeRatio, radiusRatio;  /* 4, 30 */
+  double clip_eps;                /* 1e-14 */
+  double drop_area;               /* 1e-8 */
+  int32_t clip_translate;         /* 0 = reference arithmetic (default); 1 = clip relative to the new cell's vertex 0 */
+  int32_t pad_;
+} mmb_params;
+
+/* Scalars produced by one adapt step (all reductions are deterministic: fixed-shape trees, no float atomics). */
+typedef struct mmb_step_result {
+  int64_t n_invalid;      /* cells with signedVolume_ <= 0 after the trial move (mmesh.hh:1102) */
+  int64_t n_orient_nonpos;/* cells whose exact orientation sign is <= 0 */
+  int64_t n_illegal;      /* edges failing the in-circle test */
+  int64_t n_refine, n_coarsen; /* refineMarked_/coarsenMarked_ (mmesh.hh:725-731) */
+  int64_t n_exact_orient, n_exact_incircle; /* predicates that needed the exact fallback (diagnostic) */
+  int64_t n_pieces;       /* cut triangles kept by the projection */
+  double  max_dist;       /* Distance::maximum() (distance.hh:118-123) */
+  double  mass_new;       /* sum_K |K| mean(u_K) over projected cells */
+  double  covered_area;   /* sum of kept cut-triangle areas */
+} mmb_step_result;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+/* dim = 2 or 3.  stream = a cudaStream_t to launch on (as void*), or NULL for an internal stream. */
+int mmb_create(int device, int dim, void* stream, mmb_context** out);
+int mmb_destroy(mmb_context* ctx);
+const char* mmb_last_error(const mmb_context* ctx);
+void* mmb_stream(const mmb_context* ctx);
+int mmb_synchronize(mmb_context* ctx);
+
+/* ---- snapshot upload / download (outside the timed path, like the reference's CGAL TDS edits) ------------ */
+int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t nc, const int32_t* cells_host,
+                    const uint8_t* perm_host, int64_t ne, const int32_t* edges_host, int64_t ns,
+                    const int32_t* facets_host);
+int mmb_upload_coords(mmb_context* ctx, const double* x_host);      /* vh->point() = ... for every vertex */
+int mmb_download_coords(mmb_context* ctx, double* x_host);
+int mmb_upload_shifts(mmb_context* ctx, const double* shifts_host); /* make `shifts` resident */
+int mmb_set_params(mmb_context* ctx, const mmb_params* p);
+int mmb_get_params(const mmb_context* ctx, mmb_params* p);
+
+/* ---- the hot path ---------------------------------------------------------------------------------------- */
+/* RatioIndicator::init (ratioindicator.hh:62-91): minH/maxH/factor from interface + bulk edge lengths. */
+int mmb_indicator_init(mmb_context* ctx);
+
+/* MMesh::moveVertices (mmesh.hh:1421-1430): x <- x (+) shifts. */
+int mmb_move_vertices(mmb_context* ctx, const double* shifts_host);
+
+/* Numeric part of MMesh::ensureVertexMovement (mmesh.hh:1094-1134): evaluates every cell on x (+) shifts without
+   modifying x (restore = exact copy).  valid_fp[c] = !(signedVolume_ <= 0.0) bit-exact to the reference test;
+   orient_sign[c] = CGAL::orientation (Epick) in {-1,0,+1}.  dim==3 with an invalid cell returns
+   MMB_ERR_INVALID_CELL_3D after filling the outputs (mmesh.hh:1104-1107). */
+int mmb_trial_move_validate(mmb_context* ctx, const double* shifts_host, uint8_t* valid_fp_host,
+                            int8_t* orient_sign_host, int64_t* n_invalid);
+/* indices of the invalid cells in increasing order (<= cap entries written; returns the total count) */
+int mmb_invalid_cells(mmb_context* ctx, int32_t* cells_host, int64_t cap, int64_t* n_total);
+
+/* Per-edge Delaunay legality on the current coordinates: flag 1 legal, 0 illegal, 2 hull edge.
+   Predicate: CGAL Side_of_oriented_circle_2 (Delaunay_triangulation_2.h:663-681). */
+int mmb_legality(mmb_context* ctx, uint8_t* flags_host, int64_t* n_illegal);
+
+/* Distance::update + maximum (distance.hh:42-59,118-123), exact same per-pair arithmetic, BVH-culled. */
+int mmb_distance_update(mmb_context* ctx, double* dist_host, double* max_out);
+/* Distance::set for all vertices (distance.hh:84-90): overwrite the resident field. */
+int mmb_distance_set(mmb_context* ctx, const double* dist_host);
+
+/* RatioIndicator::update + MMesh::markElements bulk loop (ratioindicator.hh:94-160, mmesh.hh:736-743) and the
+   argmax of LongestEdgeRefinement::refinement (longestedgerefinement.hh:41-57).  counts = {refine, coarsen}.
+   run_distance != 0 performs indicator_.update() (distance update) first, like the reference. */
+int mmb_mark_elements(mmb_context* ctx, int run_distance, int8_t* marks_host, uint8_t* longest_edge_host,
+                      int64_t counts[2]);
+/* interface elements (mmesh.hh:745-748): marks per facet */
+int mmb_mark_interface(mmb_context* ctx, int8_t* marks_host);
+/* ordered compaction of marked cells (index order, as MMesh::adapt() visits them, mmesh.hh:832-864) */
+int mmb_marked_cells(mmb_context* ctx, int which /* +1 refine, -1 coarsen */, int32_t* cells_host, int64_t cap,
+                     int64_t* n_total);
+
+/* Conservative projection old -> new cells (numeric part of MMesh::adapt(handle), mmesh.hh:1138-1165 with
+   CutSetTriangulation cutsettriangulation.hh:31-62 and PolygonCutting polygoncutting.hh:17-137).
+   Pair CSR: new_off[nnew+1]; new_cell[nnew] indexes the uploaded mesh; old_xy[P][6] = CachingEntity::vertex_
+   (cachingentity.hh:83-89); old_idx[P] indexes dofs_old.  ncomp = 1 (P0/FV) or 3 (DG-P1, nodal, id-order corners).
+   dofs_new has ncomp entries for every cell of the uploaded mesh; only projected cells are written. */
+int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host, const int32_t* new_cell_host,
+                     int64_t npairs, const double* old_xy_host, const int32_t* old_idx_host);
+int mmb_project(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_old_host, double* dofs_new_host,
+                double* mass_new, double* covered_area, int64_t* n_pieces);
+/* MMeshCachingEntity::intersectionVolume (cachingentity.hh:154-167) for every uploaded pair */
+int mmb_intersection_volumes(mmb_context* ctx, double* vol_host);
+
+/* One whole adapt step on resident data, in the reference's user-loop order (doc/examples/moving.py:231-252):
+   markElements (distance + marks) -> ensureVertexMovement (trial validity) -> adapt(handle) projection of the
+   uploaded pairs onto the moved cells -> moveVertices -> legality of the moved mesh.
+   ncomp = 0 skips the projection.  res may be NULL (no host synchronisation at all). */
+int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_step_result* res);
+
+/* ---- 3-D extras -------------------------------------------------------------------------------------- */
+/* P0 interface-coupled transfer (dune/python/mmesh/pyskeletontrace.hh:42-64,133-160):
+   trace_in[f] = u[inside(f)], trace_out[f] = u[outside(f)], skeleton[f] = u_gamma[f]. */
+int mmb_trace_skeleton_p0(mmb_context* ctx, int64_t nf, const int32_t* inside_host, const int32_t* outside_host,
+                          const double* u_bulk_host, int64_t n_bulk, const double* u_gamma_host,
+                          double* trace_in_host, double* trace_out_host, double* skeleton_host);
+
+/* ---- instrumentation --------------------------------------------------------------------------------- */
+/* Per-kernel CUDA-event timing of the launches issued since the last mmb_timing_reset (on ctx's stream). */
+int mmb_timing_enable(mmb_context* ctx, int on);
+int mmb_timing_reset(mmb_context* ctx);
+/* returns the number of distinct kernels; fills up to cap entries (name pointers stay valid for ctx's life) */
+int mmb_timing_get(mmb_context* ctx, int cap, const char** names, double* total_ms, int64_t* launches);
+int64_t mmb_launch_count(const mmb_context* ctx); /* kernels launched by this context so far */
+
+/* predicate batches on raw points (config 4 stress; pts [n][k][2|3]); which: 0 orient2d, 1 incircle, 2 orient3d */
+int mmb_predicate_batch(mmb_context* ctx, int which, int64_t n, const double* pts_host, int8_t* sign_host,
+                        int64_t* n_exact);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMESH_B200_H */

@@ -1,0 +1,127 @@
+/*
+ * mmesh_oracle.h -- CPU ORACLE for the Dune-MMesh moving-mesh hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library.  The product
+ * path (dune-mmesh_b200/, include/mmesh_b200.h) never links, imports or calls it.
+ *
+ * It is a plain-C restatement of the reference algorithms, op for op, with the reference
+ * file:line each function follows (paths relative to the reference checkout).  The reference
+ * itself cannot be compiled here (no Boost / GMP / DUNE), so parity is
+ * pinned against (i) the golden values the reference's own tests assert (tests/golden/),
+ * (ii) python fractions.Fraction for every exact sign, (iii) the reference tests' tolerance
+ * properties (distance to y=0.5, clip area vs exact, conservation).  Bit-level op order of
+ * un-vendored dune-geometry/dune-common/dune-fem arithmetic is "parity unpinned" (restated
+ * from their published sources).
+ *
+ * All arrays are caller-owned.  Layout conventions are the ones of include/mmesh_b200.h:
+ *   xy      [nv][2]  interleaved doubles (same memory layout as std::vector<FieldVector<double,2>>)
+ *   cells   [nc][3]  int32 vertex indices in CGAL TDS (ccw) order, face->vertex(0..2)
+ *   perm    [nc]     uint8, bits (2k+1:2k) = cgalIndex[k] : id-sorted corner k is TDS vertex cgalIndex[k]
+ *   edges   [ne][4]  int32 (a,b,c,d): edge (a,b), c = apex with (a,b,c) ccw, d = opposite apex or -1
+ *   segs    [ns][2]  int32 interface segment corners in DUNE facet order (lower persistent id first)
+ */
+#ifndef MMESH_ORACLE_H
+#define MMESH_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_params {
+  double minH, maxH, factor, distProportion; /* ratioindicator.hh:191-199 */
+  double edgeRatio, radiusRatio;             /* 4, 30 (ratioindicator.hh:45-57) */
+  double clip_eps;                           /* 1e-14 polygoncutting.hh:63 */
+  double drop_area;                          /* 1e-8  cutsettriangulation.hh:60 */
+  int32_t clip_translate;                    /* 0 = reference arithmetic; 1 = translate to new-cell corner 0 first */
+  int32_t pad_;
+} orc_params;
+
+/* ---- exact predicates (true sign; CGAL Epick result by construction) ------------------- */
+int orc_orient2d(const double* p, const double* q, const double* r);
+int orc_orient3d(const double* p, const double* q, const double* r, const double* s);
+int orc_incircle(const double* p, const double* q, const double* r, const double* t);
+/* static-filter stage only: returns -1/0/+1, or 2 when the CGAL semi-static filter cannot decide */
+int orc_orient2d_filter(const double* p, const double* q, const double* r);
+int orc_orient3d_filter(const double* p, const double* q, const double* r, const double* s);
+int orc_incircle_filter(const double* p, const double* q, const double* r, const double* t);
+/* batch: pts [n][k][dim] */
+void orc_orient2d_batch(const double* pts, int64_t n, int8_t* sign);
+void orc_orient3d_batch(const double* pts, int64_t n, int8_t* sign);
+void orc_incircle_batch(const double* pts, int64_t n, int8_t* sign);
+
+/* ---- move / validity --------------------------------------------------------------------- */
+void orc_move(double* x, const double* shift, int64_t n_doubles);                 /* mmesh.hh:1421-1430 */
+/* trial move: validity evaluated on x (+) s, coordinates not modified */
+void orc_trial_validate_2d(const double* xy, const double* shift /*may be NULL*/, int64_t nv,
+                           const int32_t* cells, int64_t nc,
+                           uint8_t* valid_fp, int8_t* orient_sign, int64_t* n_invalid);
+void orc_trial_validate_3d(const double* xyz, const double* shift, int64_t nv,
+                           const int32_t* cells /*[nc][4]*/, int64_t nc,
+                           uint8_t* valid_fp, int8_t* orient_sign, int64_t* n_invalid);
+double orc_signed_area(const double* p, const double* q, const double* r);        /* Compute_area_2 */
+double orc_signed_volume(const double* p0, const double* p1, const double* p2, const double* p3);
+
+/* ---- per-edge Delaunay legality ---------------------------------------------------------- */
+/* flag: 1 legal, 0 illegal (incircle(a,b,c,d) > 0), 2 boundary (d < 0) */
+void orc_legality(const double* xy, const double* shift /*may be NULL*/, const int32_t* edges, int64_t ne,
+                  uint8_t* flag, int64_t* n_illegal);
+
+/* ---- distance field ---------------------------------------------------------------------- */
+double orc_point_segment_distance(const double* vp, const double* v0, const double* v1); /* distance.hh:143-156 */
+void orc_distance_2d(const double* xy, int64_t nv, const int32_t* segs, int64_t ns, double* dist); /* brute force */
+/* brute force restricted to a vertex subset (bounded CPU-baseline samples / full-size spot checks) */
+void orc_distance_2d_subset(const double* xy, const int32_t* vidx, int64_t nsub,
+                            const int32_t* segs, int64_t ns, double* dist_sub);
+void orc_distance_3d(const double* xyz, int64_t nv, const int32_t* tris /*[ns][3]*/, int64_t ns, double* dist);
+double orc_distance_max(const double* dist, int64_t nv);                           /* distance.hh:118-123 */
+
+/* ---- RatioIndicator ---------------------------------------------------------------------- */
+void orc_indicator_init_2d(const double* xy, const int32_t* edges, int64_t ne,
+                           const int32_t* segs, int64_t ns, orc_params* prm);     /* ratioindicator.hh:62-91 */
+void orc_mark_2d(const double* xy, const double* dist, const int32_t* cells, const uint8_t* perm, int64_t nc,
+                 const orc_params* prm, double maxDist,
+                 int8_t* mark, uint8_t* longest_edge, int64_t counts[2] /*refine, coarsen*/);
+void orc_mark_3d(const double* xyz, const double* dist, const int32_t* cells, const uint8_t* perm, int64_t nc,
+                 const orc_params* prm, double maxDist,
+                 int8_t* mark, uint8_t* longest_edge, int64_t counts[2]);
+/* interface elements: mark by length only */
+void orc_mark_interface_2d(const double* xy, const int32_t* segs, int64_t ns, const orc_params* prm,
+                           double maxDist, int8_t* mark);
+/* geometry helpers pinned by the reference's golden tests */
+void orc_cell_geometry_2d(const double* xy, const int32_t* cell, uint8_t perm,
+                          double* center2, double* volume, double* edge_centers6, double* circumcenter2);
+void orc_cell_geometry_3d(const double* xyz, const int32_t* cell, uint8_t perm,
+                          double* center3, double* volume, double* circumcenter3);
+
+/* ---- clipping / projection --------------------------------------------------------------- */
+/* Sutherland-Hodgman (polygoncutting.hh:17-96): subject/clip triangles, out <= 7 points; returns count */
+int orc_sutherland_hodgman(const double* subj6, const double* clip6, double eps, double* out14);
+double orc_polygon_area(const double* pts, int n);                                 /* polygoncutting.hh:121-137 */
+double orc_intersection_volume(const double* old6, const double* new6);            /* cachingentity.hh:154-167 */
+/* CutSetTriangulation (cutsettriangulation.hh:31-62): returns number of kept fan triangles (<=5),
+   tris [k][6] */
+int orc_cutset(const double* old6_cached, const double* new6_tds, const orc_params* prm, double* tris30);
+
+/* pairs CSR: new_off[nnew+1], new_cell[nnew] (index into cells/perm/xy), old_xy[P][6] cached corners
+   (id order), old_idx[P] index into dofs_old.  ncomp = 1 (P0) or 3 (DG-P1, nodal on id-order corners). */
+void orc_project(const double* xy, const int32_t* cells, const uint8_t* perm,
+                 const int64_t* new_off, const int32_t* new_cell, int64_t nnew,
+                 const double* old_xy, const int32_t* old_idx,
+                 const double* dofs_old, double* dofs_new, int ncomp,
+                 const orc_params* prm, double* mass_new, double* covered_area, int64_t* n_pieces);
+
+/* interface (1-D) transfer, interface/grid.hh:388-415 with P0 data */
+void orc_project_interface_p0(const double* new_len, const int64_t* new_off, int64_t nnew,
+                              const double* old_len, const int32_t* old_idx,
+                              const double* dofs_old, double* dofs_new);
+
+/* OpenMP threads used by the batch loops (the reference is single-threaded per rank; 1 by default) */
+void orc_set_threads(int n);
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
