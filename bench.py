@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- cells/s per adapt step (move + validate + legality + distance + mark + project) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                     (the CPU restatement of the reference path, all host cores)
+
+One "step" = mmb_adapt_step on the BASELINE.json config the metric is quoted on: the 2-D synthetic 16.8M-triangle
+Hilbert-sorted mesh with a multi-segment interface (configs[2]; it fits one GPU), DG-P1 projection of the
+self+face-neighbour pair set (phi = 1 stress).  `value` = whole-job cells/s with everything resident in HBM;
+`e2e` = the same step through the C-ABI with HOST buffers (shifts + old DOFs in, marks/flags/new DOFs out,
+pinned memory, copies inside the timed region).  The mesh snapshot and the pair list are uploaded once outside the
+timed region, like the reference's CGAL TDS edits.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "dune-mmesh_b200", "python")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cells/s per adapt step (move+validate+mark+project)"
+UNIT = "cells/s"
+
+# algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md "kernels"): fp64 coords, int32 indices, 1-byte flags
+def algorithmic_bytes(name, nv, nc, ne, ns, npairs, nnew, ncomp):
+    t = {
+        "validate2d": nc * (12 + 2) + nv * (16 + 16),
+        "legality": ne * (16 + 1) + nv * 16,
+        "distance2d": nv * (16 + 8) + ns * 48,
+        "mark2d": nc * (12 + 1 + 2) + nv * (16 + 8),
+        "move": nv * 48,
+        "scale_shifts": nv * 32,
+        "project_p0": npairs * (48 + 4 + 8) + nnew * (8 + 4 + 12 + 1 + 48 + 8),
+        "project_p1": npairs * (48 + 4 + 24) + nnew * (8 + 4 + 12 + 1 + 48 + 24),
+    }
+    return t.get(name)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(args):
+    from mmesh_b200 import synth
+    t0 = time.time()
+    if args.config == 3:
+        m = synth.config3(nx=args.nx, ny=args.ny)
+        name = "config3: 2-D %dx%d lattice, %d triangles, Hilbert-sorted, 4 sinusoidal interface polylines" % (args.nx, args.ny, 2 * args.nx * args.ny)
+    elif args.config == 2:
+        m = synth.config2(n=args.nx)
+        name = "config2: 2-D rotating-circle interface, %d triangles" % (2 * args.nx * args.nx)
+    else:
+        m = synth.config1(n=args.nx)
+        name = "config1: 2-D unit square, %d triangles, straight interface" % (2 * args.nx * args.nx)
+    s = synth.shifts_uniform(m, 0.3 * m.h, 30)
+    new_off, new_cell, old_xy, old_idx = synth.pairs_self_and_neighbours(m, m.xy - s)
+    c = m.xy[m.cells]
+    k = np.stack([np.take_along_axis(m.cells, ((m.perm >> (2 * i)) & 3)[:, None].astype(np.int64), 1)[:, 0] for i in range(3)], 1)
+    pk = (m.xy - s)[k]
+    dofs = np.sin(np.pi * pk[..., 0]) * np.sin(np.pi * pk[..., 1])          # DG-P1 nodal values of sin(pi x) sin(pi y)
+    del c
+    return dict(mesh=m, shifts=s, new_off=new_off, new_cell=new_cell, old_xy=old_xy, old_idx=old_idx, dofs=np.ascontiguousarray(dofs),
+                name=name, gen_s=time.time() - t0)
+
+
+def cpu_reference_step(O, w, sample_cells, prm, threads):
+    """The restated reference path on a contiguous Hilbert range of cells (a bounded sample of the workload):
+    brute-force Distance::update for the sample's vertices, marks, trial validity, legality of the sample's edges,
+    projection of the sample's pairs, moveVertices of the sample's vertices."""
+    m = w["mesh"]
+    O.set_threads(threads)
+    cells = m.cells[:sample_cells]
+    vs = np.unique(cells)
+    t0 = time.perf_counter()
+    dsub = O.distance_2d_subset(m.xy, vs, m.segs)
+    dist = np.zeros(m.nv)
+    dist[vs] = dsub
+    maxd = O.distance_max(dsub)
+    O.mark(m.xy, dist, cells, m.perm[:sample_cells], prm, prm.distProportion * maxd)
+    O.trial_validate(m.xy, w["shifts"], cells)
+    ne_s = int(np.searchsorted(m.edge_cell, sample_cells))     # edges are ordered by their left (lower-index) cell
+    O.legality(m.xy, None, m.edges[:ne_s])
+    P = int(w["new_off"][sample_cells])
+    O.project(m.xy, m.cells, m.perm, w["new_off"][:sample_cells + 1], w["new_cell"][:sample_cells], w["old_xy"][:P], w["old_idx"][:P],
+              w["dofs"], m.nc, 3, prm)
+    O.move(m.xy[vs], w["shifts"][vs])
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path = the restated oracle (the reference itself
+    cannot be compiled here: no Boost/GMP/DUNE), with all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as O
+    O.build()
+    w = make_workload(args)
+    m = w["mesh"]
+    prm = O.indicator_init_2d(m.xy, m.edges, m.segs, O.Params.default())
+    threads = os.cpu_count() or 1
+    sample = min(m.nc, args.cpu_sample)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_step(O, w, sample, prm, threads)
+    ts = [cpu_reference_step(O, w, sample, prm, threads) for _ in range(max(1, min(args.steps, 3)))]
+    dt = float(np.mean(ts))
+    val = sample / dt
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": min(args.warmup, 1),
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": w["name"], "projection": "DG-P1, self+face-neighbour pairs (phi=1)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "first %d cells of the Hilbert order (of %d), brute-force O(Nv*Ns) distance as in the reference" % (sample, m.nc)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--nx", type=int, default=None)
+    ap.add_argument("--ny", type=int, default=None)
+    ap.add_argument("--cpu-sample", type=int, default=32768)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.nx is None:
+        args.nx = {3: 4096, 2: 708, 1: 100}[args.config]
+    if args.ny is None:
+        args.ny = args.nx // 2 if args.config == 3 else args.nx
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    from mmesh_b200 import capi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from mmesh_b200 import multigpu
+        multigpu.bench_main(args, world, rank, local_rank, METRIC, UNIT, algorithmic_bytes, ClockSampler, make_workload)
+        return
+
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    w = make_workload(args)
+    m = w["mesh"]
+    ctx = capi.Context(dim=2, device=local_rank, stream=stream.cuda_stream)
+    ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
+    prm = ctx.indicator_init()
+    ctx.upload_pairs(w["new_off"], w["new_cell"], w["old_xy"], w["old_idx"])
+    ncomp = 3
+    ctx.project(ncomp, w["dofs"], download=False)          # DOFs resident
+    ctx.upload_shifts(w["shifts"])
+    nv, nc, ne, ns = m.nv, m.nc, m.edges.shape[0], m.segs.shape[0]
+    npairs, nnew = w["old_idx"].shape[0], w["new_cell"].shape[0]
+
+    def step_resident():
+        ctx.adapt_step(None, ncomp=ncomp, want_result=False)
+        ctx.scale_shifts(-1.0)                              # next step moves back: the mesh stays in place on average
+
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.synchronize()
+    res_check = ctx.adapt_step(None, ncomp=ncomp, want_result=True)
+    ctx.scale_shifts(-1.0)
+    ctx.synchronize()
+
+    # ---- timed region: K resident steps, CUDA events on the launching stream, per-kernel events inside ----
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.3)
+    ctx.timing_enable(True)
+    ctx.timing_reset()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - l0
+    per_kernel = ctx.timing_get()
+    ctx.timing_enable(False)
+    ctx.timing_reset()
+    clk = clocks.stop()
+    ms_per_step = ms / args.steps
+    value = nc / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kern = []
+    for name, (tot_ms, cnt) in per_kernel.items():
+        ab = algorithmic_bytes(name, nv, nc, ne, ns, npairs, nnew, ncomp)
+        avg = tot_ms / cnt
+        kern.append({"kernel": name, "avg_ms": avg, "share": tot_ms / ms, "launches_per_step": cnt / args.steps,
+                     "algorithmic_bytes": ab, "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None,
+                     "frac": (ab / (avg * 1e-3) / 1e9 / peak) if ab else None})
+    kern.sort(key=lambda k: -k["share"])
+    dom = kern[0]
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": None, "peak_source": peak_src}
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        L = capi.lib()
+        h = ctx._h
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        sh = [pin(w["shifts"]), pin(-w["shifts"])]
+        dofs_in = pin(w["dofs"])
+        dofs_out = torch.empty((nc, ncomp), dtype=torch.float64).pin_memory()
+        marks = torch.empty(nc, dtype=torch.int8).pin_memory()
+        longest = torch.empty(nc, dtype=torch.uint8).pin_memory()
+        valid = torch.empty(nc, dtype=torch.uint8).pin_memory()
+        orient = torch.empty(nc, dtype=torch.int8).pin_memory()
+        eflag = torch.empty(ne, dtype=torch.uint8).pin_memory()
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        res = capi.StepResult()
+
+        def step_e2e(i):
+            rc = L.mmb_adapt_step_host(h, P(sh[i & 1]), ctypes.c_int(ncomp), ctypes.c_int64(nc), P(dofs_in), P(dofs_out), P(marks),
+                                       P(longest), P(valid), P(orient), P(eflag), ctypes.byref(res))
+            ctx._ck(rc)
+
+        for i in range(2):
+            step_e2e(i)
+        ke = max(2, min(args.steps, 10)) // 2 * 2
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(ke):
+            step_e2e(i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / ke
+        h2d = nv * 16 + nc * ncomp * 8
+        d2h = nc * ncomp * 8 + 4 * nc + ne + ctypes.sizeof(capi.StepResult)
+        e2e = {"value": nc / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": ke,
+               "note": "shifts + old DG-P1 DOFs in; marks, longest-edge, valid_fp, orient_sign, edge flags, new DOFs, scalars out"}
+
+    # ---- CPU baseline on a bounded sample ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle as O
+        oprm = O.Params.from_buffer_copy(bytes(prm))
+        sample = min(nc, args.cpu_sample)
+        dt = cpu_reference_step(O, w, sample, oprm, 1)
+        cpu = {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+               "sample": "first %d cells of the Hilbert order (of %d), brute-force O(Nv*Ns) distance as in the reference" % (sample, nc)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "cells": nc, "vertices": nv, "edges": ne, "interface_segments": ns,
+                       "projection": "DG-P1, self+face-neighbour pairs (phi=1, %d pairs)" % npairs,
+                       "l2_policy": "inputs larger than L2 (%.2f GB touched per step)" % (sum(k["algorithmic_bytes"] or 0 for k in kern) / 1e9),
+                       "step": "distance+mark -> trial validate -> project -> move -> legality (+ shifts *= -1)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "kernels": kern, "check": res_check.asdict(), "setup_s": w["gen_s"]}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

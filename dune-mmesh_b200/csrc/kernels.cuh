@@ -79,6 +79,16 @@ __global__ void __launch_bounds__(256) k_move(double2* __restrict__ x, const dou
   }
 }
 
+// mmesh.hh:1130: for (GlobalCoordinate& s : shifts) s *= -1.0;  (any scale; exact for +-1)
+__global__ void __launch_bounds__(256) k_scale(double2* __restrict__ s, double a, int64_t n2) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    double2 v = s[i];
+    v.x *= a; v.y *= a;
+    s[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K1  trial move + validity, 2-D.  mmesh.hh:1094-1134 (ensureVertexMovement): signedVolume_ <= 0.0 on
 //     x (+) s in TDS vertex order (mmesh.hh:1169-1172 -> CGAL/Cartesian/function_objects.h:918-926), plus the

@@ -288,6 +288,14 @@ int mmb_upload_shifts(mmb_context* ctx, const double* shifts_host) {
   ctx->has_shift = true;
   return MMB_OK;
 }
+int mmb_scale_shifts(mmb_context* ctx, double a) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->has_shift, MMB_ERR_STATE, "no resident shifts");
+  const int64_t n2 = ((int64_t)ctx->nv * ctx->dim + 1) / 2;
+  LAUNCH("scale_shifts", k_scale, std::min<unsigned>(grid_for(n2, 256), ctx->num_sms * 16), 256, (double2*)ctx->shift.p, a, n2);
+  CK(cudaGetLastError());
+  return MMB_OK;
+}
 static int stage_shifts(mmb_context* ctx, const double* shifts_host) {
   if (shifts_host) return mmb_upload_shifts(ctx, shifts_host);
   REQUIRE(ctx->has_shift, MMB_ERR_STATE, "shifts == NULL but no resident shifts (mmb_upload_shifts)");
@@ -621,12 +629,11 @@ int mmb_intersection_volumes(mmb_context* ctx, double* vol_host) {
 }
 
 // ---- whole step -----------------------------------------------------------------------------------------
-int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_step_result* res) {
-  if (!ctx) return MMB_ERR_INVALID_ARG;
+static int step_core(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host) {
   REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
   REQUIRE(ncomp == 0 || ctx->dim == 2, MMB_ERR_INVALID_ARG, "projection is 2-D only (geometryInFather, entity.hh:573-594)");
   TRY(stage_shifts(ctx, shifts_host));
-  if (ncomp) TRY(stage_dofs(ctx, ncomp, 0, nullptr));
+  if (ncomp) TRY(stage_dofs(ctx, ncomp, n_old, dofs_old_host));
   TRY(zero_counters(ctx));
   TRY(do_distance(ctx));            // markElements: indicator_.update()
   TRY(do_mark(ctx));                //               bulk marks (+ longest edge)
@@ -638,6 +645,9 @@ int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_s
   TRY(do_move(ctx));                // moveVertices
   if (ctx->dim == 2) TRY(do_legality(ctx));   // in-circle flags of the moved mesh (input of the next host TDS pass)
   CK(cudaGetLastError());
+  return MMB_OK;
+}
+static int step_result(mmb_context* ctx, mmb_step_result* res) {
   if (res) {
     TRY(fetch_counters(ctx));
     const Counters& c = *ctx->h_counters;
@@ -651,6 +661,27 @@ int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_s
       return MMB_ERR_INVALID_CELL_3D;
     }
   }
+  return MMB_OK;
+}
+int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_step_result* res) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  TRY(step_core(ctx, shifts_host, ncomp, 0, nullptr));
+  return step_result(ctx, res);
+}
+int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host,
+                        double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host, uint8_t* valid_fp_host,
+                        int8_t* orient_sign_host, uint8_t* edge_flags_host, mmb_step_result* res) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  TRY(step_core(ctx, shifts_host, ncomp, n_old, dofs_old_host));
+  const size_t nc = (size_t)ctx->nc;
+  if (marks_host) CK(cudaMemcpyAsync(marks_host, ctx->mark.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (longest_edge_host) CK(cudaMemcpyAsync(longest_edge_host, ctx->longest.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (edge_flags_host && ctx->ne) CK(cudaMemcpyAsync(edge_flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dofs_new_host && ncomp) CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (res) return step_result(ctx, res);
+  CK(cudaStreamSynchronize(ctx->stream));
   return MMB_OK;
 }
 

@@ -15,10 +15,10 @@ _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "NCCL error", 4: "invalid 
 
 EXPORTS = [
     "mmb_create", "mmb_destroy", "mmb_last_error", "mmb_stream", "mmb_synchronize", "mmb_upload_mesh",
-    "mmb_upload_coords", "mmb_download_coords", "mmb_upload_shifts", "mmb_set_params", "mmb_get_params",
+    "mmb_upload_coords", "mmb_download_coords", "mmb_upload_shifts", "mmb_scale_shifts", "mmb_set_params", "mmb_get_params",
     "mmb_indicator_init", "mmb_move_vertices", "mmb_trial_move_validate", "mmb_invalid_cells", "mmb_legality",
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
-    "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_trace_skeleton_p0",
+    "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
     "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
@@ -143,6 +143,9 @@ class Context:
         s = _f64(s)
         self._ck(lib().mmb_upload_shifts(self._h, _p(s)))
         self._ck(lib().mmb_synchronize(self._h))
+
+    def scale_shifts(self, a):
+        self._ck(lib().mmb_scale_shifts(self._h, C.c_double(a)))
 
     def set_params(self, prm):
         self._ck(lib().mmb_set_params(self._h, C.byref(prm)))

@@ -106,18 +106,19 @@ def build_edges(cells, nv):
     o = np.lexsort((lk, lc))
     edges = edges[o]
     left, right = left[o], right[o]
+    edge_cell = lc[o].astype(np.int32)
     nb = np.full((nc, 3), -1, np.int32)
     inner = right >= 0
     nb[cell_of[left[inner]], left[inner] // nc] = cell_of[right[inner]]
     nb[cell_of[right[inner]], right[inner] // nc] = cell_of[left[inner]]
-    return edges, nb
+    return edges, nb, edge_cell
 
 
 class Mesh2D:
     dim = 2
 
     def __init__(self):
-        self.xy = self.vid = self.vflags = self.cells = self.perm = self.edges = self.nb = self.segs = None
+        self.xy = self.vid = self.vflags = self.cells = self.perm = self.edges = self.nb = self.segs = self.edge_cell = None
         self.h = None
         self.lat = None      # (i, j) lattice coordinates per vertex (index order), for analytic fields
 
@@ -243,7 +244,7 @@ def lattice2d(nx, ny, Lx=1.0, Ly=1.0, jitter=0.2, seed=1, curves=(), hilbert=Tru
     m.vflags = (is_if[vorder].astype(np.uint8) | (boundary[vorder].astype(np.uint8) << 1)).astype(np.uint8)
     m.perm = pack_perm(cells)                                # cells still hold persistent ids here
     m.cells = np.ascontiguousarray(vrank[cells].astype(np.int32))
-    m.edges, m.nb = build_edges(m.cells, nv)
+    m.edges, m.nb, m.edge_cell = build_edges(m.cells, nv)
     if seg_l:
         sg = np.concatenate(seg_l, axis=0)
         sg = np.where((sg[:, 0] < sg[:, 1])[:, None], sg, sg[:, ::-1])   # lower persistent id first

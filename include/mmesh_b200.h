@@ -77,6 +77,8 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
 int mmb_upload_coords(mmb_context* ctx, const double* x_host);      /* vh->point() = ... for every vertex */
 int mmb_download_coords(mmb_context* ctx, double* x_host);
 int mmb_upload_shifts(mmb_context* ctx, const double* shifts_host); /* make `shifts` resident */
+/* resident shifts *= a (the `s *= -1.0` of mmesh.hh:1130 when a == -1; exact for +-1) */
+int mmb_scale_shifts(mmb_context* ctx, double a);
 int mmb_set_params(mmb_context* ctx, const mmb_params* p);
 int mmb_get_params(const mmb_context* ctx, mmb_params* p);
 
@@ -130,9 +132,16 @@ int mmb_intersection_volumes(mmb_context* ctx, double* vol_host);
 
 /* One whole adapt step on resident data, in the reference's user-loop order (doc/examples/moving.py:231-252):
    markElements (distance + marks) -> ensureVertexMovement (trial validity) -> adapt(handle) projection of the
-   uploaded pairs onto the moved cells -> moveVertices -> legality of the moved mesh.
+   uploaded pairs -> moveVertices -> in-circle legality of the moved mesh (input of the next host TDS pass).
    ncomp = 0 skips the projection.  res may be NULL (no host synchronisation at all). */
 int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_step_result* res);
+
+/* The same step with HOST buffers for every per-step field (the drop-in call a host adapter makes each step):
+   shifts and the old DOFs go in, marks / longest-edge / valid_fp / orient_sign / edge flags / new DOFs and the scalars
+   come out.  Any output pointer may be NULL.  dofs_old_host == NULL keeps the resident DOFs. */
+int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host,
+                        double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host, uint8_t* valid_fp_host,
+                        int8_t* orient_sign_host, uint8_t* edge_flags_host, mmb_step_result* res);
 
 /* ---- 3-D extras -------------------------------------------------------------------------------------- */
 /* P0 interface-coupled transfer (dune/python/mmesh/pyskeletontrace.hh:42-64,133-160):

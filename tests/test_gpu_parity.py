@@ -1,0 +1,319 @@
+"""GPU parity tests: every kernel of the hot path, called through the C-ABI (mmesh_b200.capi -> libmmesh_b200.so),
+against the CPU oracle on the same seeded inputs.  Integer / flag / mark outputs must be bit-exact; distances are
+asserted bit-exact too (same arithmetic, conservative culling); projected DOFs within 1e-12 relative, mass 1e-13.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh1(n=100):
+    from mmesh_b200 import synth
+    return synth.config1(n=n)
+
+
+def _upload(ctx, m):
+    ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
+
+
+def test_library_fails_loudly_without_fallback():
+    """The product path has no CPU fallback: a bad device index is an error, not a silent CPU run."""
+    from mmesh_b200 import capi
+    with pytest.raises(capi.MMeshError):
+        capi.Context(dim=2, device=977)
+
+
+def test_move_and_trial_validity_2d(gpu_ctx_factory, oracle):
+    from mmesh_b200 import synth
+    m = _mesh1()
+    ctx = gpu_ctx_factory(2)
+    _upload(ctx, m)
+    # large shifts: many inverted cells, so both branches of `signedVolume_ <= 0` are exercised
+    for amp, seed in ((0.3, 30), (0.9, 31)):
+        s = synth.shifts_uniform(m, amp * m.h, seed)
+        valid, sign, ninv = ctx.trial_move_validate(s)
+        rv, rs, rn = oracle.trial_validate(m.xy, s, m.cells)
+        assert np.array_equal(valid, rv) and np.array_equal(sign, rs) and ninv == rn
+        assert np.array_equal(ctx.invalid_cells(), np.nonzero(rv == 0)[0])
+        # trial move must leave the coordinates untouched (restore_mode = exact copy)
+        assert np.array_equal(ctx.download_coords(), m.xy)
+    assert rn > 0
+    # real move: bit-identical to x (+) s
+    ctx.move_vertices(s)
+    assert np.array_equal(ctx.download_coords(), oracle.move(m.xy, s))
+    # and the reference's move-back quirk (x (+) s) (+) (-s)
+    ctx.scale_shifts(-1.0)
+    ctx.move_vertices(None)
+    assert np.array_equal(ctx.download_coords(), oracle.move(oracle.move(m.xy, s), -s))
+
+
+def test_validity_zero_area_cells(gpu_ctx_factory, oracle):
+    """Cells with exactly zero / tiny signed area: valid_fp follows the inexact test, orient_sign the exact one."""
+    m = _mesh1(20)
+    xy = m.xy.copy()
+    # collapse some vertices onto neighbours / make cells exactly degenerate
+    c = m.cells
+    xy[c[::7, 2]] = 0.5 * (xy[c[::7, 0]] + xy[c[::7, 1]])
+    ctx = gpu_ctx_factory(2)
+    ctx.upload_mesh(xy, m.cells, m.perm, m.edges, m.segs)
+    s = np.zeros_like(xy)
+    valid, sign, ninv = ctx.trial_move_validate(s)
+    rv, rs, rn = oracle.trial_validate(xy, s, m.cells)
+    assert np.array_equal(valid, rv) and np.array_equal(sign, rs) and ninv == rn
+    assert (rs == 0).sum() > 0
+
+
+def test_legality(gpu_ctx_factory, oracle):
+    m = _mesh1()
+    ctx = gpu_ctx_factory(2)
+    _upload(ctx, m)
+    flags, nill = ctx.legality()
+    rf, rn = oracle.legality(m.xy, None, m.edges)
+    assert np.array_equal(flags, rf) and nill == rn and nill > 0
+    assert (flags == 2).sum() == 400
+
+
+def test_distance_bit_exact(gpu_ctx_factory, oracle):
+    from mmesh_b200 import synth
+    for m in (_mesh1(), synth.config2(n=120)):
+        ctx = gpu_ctx_factory(2)
+        _upload(ctx, m)
+        d, mx = ctx.distance_update()
+        rd = oracle.distance_2d(m.xy, m.segs)
+        assert np.array_equal(d, rd)
+        assert mx == oracle.distance_max(rd)
+
+
+def test_distance_no_interface(gpu_ctx_factory, oracle):
+    m = _mesh1(10)
+    ctx = gpu_ctx_factory(2)
+    ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, None)
+    d, mx = ctx.distance_update()
+    assert np.all(d == 1e100) and mx == 1e100            # distance.hh:45
+
+
+def test_marks_bit_exact(gpu_ctx_factory, oracle):
+    from mmesh_b200 import synth, capi
+    for m in (_mesh1(), synth.config2(n=120)):
+        ctx = gpu_ctx_factory(2)
+        _upload(ctx, m)
+        prm = ctx.indicator_init()
+        oprm = oracle.indicator_init_2d(m.xy, m.edges, m.segs, oracle.Params.default())
+        assert (prm.minH, prm.maxH, prm.factor) == (oprm.minH, oprm.maxH, oprm.factor)
+        rd = oracle.distance_2d(m.xy, m.segs)
+        for scale_min, scale_max, prop in ((1.0, 1.0, 1.0), (3.0, 0.45, 0.5), (0.2, 0.3, 0.25)):
+            p = capi.Params.from_buffer_copy(bytes(prm))
+            p.minH, p.maxH, p.distProportion = prm.minH * scale_min, prm.maxH * scale_max, prop
+            ctx.set_params(p)
+            marks, le, counts = ctx.mark_elements(run_distance=True)
+            op = oracle.Params.from_buffer_copy(bytes(p))
+            rm, rle, rc = oracle.mark(m.xy, rd, m.cells, m.perm, op, prop * oracle.distance_max(rd))
+            assert np.array_equal(marks, rm) and np.array_equal(le, rle) and tuple(counts) == tuple(rc)
+            assert np.array_equal(ctx.marked_cells(+1), np.nonzero(rm == 1)[0])
+            assert np.array_equal(ctx.marked_cells(-1), np.nonzero(rm == -1)[0])
+            assert np.array_equal(ctx.mark_interface(), oracle.mark_interface_2d(m.xy, m.segs, op, prop * oracle.distance_max(rd)))
+        assert len(set(np.unique(rm))) >= 2
+
+
+def test_marks_nan_semantics(gpu_ctx_factory, oracle):
+    """maxDist == 0 => l = NaN: device must keep IEEE NaN comparisons."""
+    from mmesh_b200 import capi
+    m = _mesh1(30)
+    ctx = gpu_ctx_factory(2)
+    _upload(ctx, m)
+    prm = ctx.indicator_init()
+    ctx.distance_set(np.zeros(m.nv))
+    marks, le, counts = ctx.mark_elements(run_distance=False)
+    rm, rle, rc = oracle.mark(m.xy, np.zeros(m.nv), m.cells, m.perm, oracle.Params.from_buffer_copy(bytes(prm)), 0.0)
+    assert np.array_equal(marks, rm) and np.array_equal(le, rle)
+
+
+def test_projection_p0_p1(gpu_ctx_factory, oracle):
+    from mmesh_b200 import capi
+    from projection_cases import diagonal_flip_case
+    case = diagonal_flip_case(n=64, seed=9)
+    ctx = gpu_ctx_factory(2)
+    ctx.upload_mesh(case["xy"], case["cells"], case["perm"], None, None)
+    ctx.upload_pairs(case["new_off"], case["new_cell"], case["old_xy"], case["old_idx"])
+    rng = np.random.default_rng(3)
+    for translate in (0, 1):
+        prm = ctx.get_params()
+        prm.clip_translate = translate
+        ctx.set_params(prm)
+        oprm = oracle.Params.from_buffer_copy(bytes(prm))
+        u_old = rng.uniform(-1, 2, case["n_old"])
+        got, mass, cov, npc = ctx.project(1, u_old)
+        ref, rmass, rcov, rnpc = oracle.project(case["xy"], case["cells"], case["perm"], case["new_off"], case["new_cell"],
+                                                case["old_xy"], case["old_idx"], u_old, case["cells"].shape[0], 1, oprm)
+        assert npc == rnpc
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+        if translate == 0:
+            assert np.array_equal(got, ref)      # same accumulation order => same bits
+        assert abs(mass - rmass) <= 1e-13 * abs(rmass) and abs(cov - rcov) <= 1e-13 * rcov
+        mass_old = float(np.sum(case["old_vol"] * u_old))
+        assert abs(mass - mass_old) <= 1e-13 * abs(mass_old)
+        d_old = rng.uniform(-1, 2, (case["n_old"], 3))
+        got, mass, cov, npc = ctx.project(3, d_old)
+        ref, rmass, rcov, rnpc = oracle.project(case["xy"], case["cells"], case["perm"], case["new_off"], case["new_cell"],
+                                                case["old_xy"], case["old_idx"], d_old, case["cells"].shape[0], 3, oprm)
+        assert npc == rnpc
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+        assert abs(mass - rmass) <= 1e-13 * abs(rmass)
+    # P1 reproduces linears, conserves mass
+    f = lambda p: 0.3 + 1.7 * p[..., 0] - 0.9 * p[..., 1]
+    d_old = f(case["old_xy"].reshape(-1, 3, 2)[case["first_pair_of_old"]])
+    got, mass, _, _ = ctx.project(3, d_old)
+    assert np.max(np.abs(got - f(case["new_corners_idorder"]))) < 1e-12
+    assert abs(mass - float(np.sum(case["old_vol"] * d_old.mean(axis=1)))) <= 1e-13 * abs(mass)
+    # intersection volumes (cachingentity.hh:154-167) and the conservation check of movement.cc:89-94
+    vols = ctx.intersection_volumes()
+    ref = np.array([oracle.intersection_volume(case["old_xy"][p], case["new6"][i])
+                    for i in range(case["new_cell"].shape[0]) for p in range(case["new_off"][i], case["new_off"][i + 1])])
+    assert np.array_equal(vols, ref)
+    assert np.max(np.abs(np.add.reduceat(vols, case["new_off"][:-1]) - case["new_vol"])) < 1e-8
+
+
+def test_projection_stress_pairs(gpu_ctx_factory, oracle):
+    """The benchmark's pair set-up (self + face neighbours, moved mesh) incl. dropped slivers and empty cuts."""
+    from mmesh_b200 import synth
+    m = _mesh1(60)
+    s = synth.shifts_uniform(m, 0.3 * m.h, 30)
+    new_off, new_cell, old_xy, old_idx = synth.pairs_self_and_neighbours(m, m.xy - s)
+    ctx = gpu_ctx_factory(2)
+    _upload(ctx, m)
+    ctx.upload_pairs(new_off, new_cell, old_xy, old_idx)
+    prm = ctx.get_params()
+    prm.drop_area = 1e-8
+    ctx.set_params(prm)
+    oprm = oracle.Params.from_buffer_copy(bytes(prm))
+    rng = np.random.default_rng(4)
+    for ncomp in (1, 3):
+        u = rng.uniform(0, 1, (m.nc, ncomp)) if ncomp == 3 else rng.uniform(0, 1, m.nc)
+        got, mass, cov, npc = ctx.project(ncomp, u)
+        ref, rmass, rcov, rnpc = oracle.project(m.xy, m.cells, m.perm, new_off, new_cell, old_xy, old_idx, u, m.nc, ncomp, oprm)
+        assert npc == rnpc
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+        assert abs(mass - rmass) <= 1e-13 * abs(rmass) and abs(cov - rcov) <= 1e-13 * rcov
+
+
+def test_predicate_batches_config4(gpu_ctx_factory, oracle):
+    """BASELINE config 4: cocircular/collinear lattice perturbed by 1e-15 -- the exact fallback decides everything."""
+    from mmesh_b200 import synth
+    ctx = gpu_ctx_factory(2)
+    for perturb in (0.0, 1e-15):
+        m = synth.config4(n=128, perturb=perturb)
+        tri = np.concatenate([m.xy[m.cells[:, 0]], m.xy[m.cells[:, 1]], m.xy[m.cells[:, 2]]], 1)
+        got, nex = ctx.predicate_batch(0, tri)
+        assert np.array_equal(got, oracle.orient2d_batch(tri))
+        e = m.edges[m.edges[:, 3] >= 0]
+        quad = np.concatenate([m.xy[e[:, 0]], m.xy[e[:, 1]], m.xy[e[:, 2]], m.xy[e[:, 3]]], 1)
+        got, nex = ctx.predicate_batch(1, quad)
+        ref = oracle.incircle_batch(quad)
+        assert np.array_equal(got, ref)
+        if perturb == 0.0:
+            lat = m.lat
+            diag = np.abs(lat[e[:, 0]] - lat[e[:, 1]]).sum(1) == 2
+            assert np.all(ref[diag] == 0) and nex == 0        # cocircular quads: decided by the interval stage (exact zeros)
+        else:
+            assert nex > 0
+        # collinear lattice triples (i, i+k, i+2k)
+        rng = np.random.default_rng(6)
+        a = rng.integers(0, 64, size=(20000, 2))
+        d = rng.integers(-3, 4, size=(20000, 2))
+        P = np.stack([a, a + d, a + 2 * d], 1) / 128.0
+        if perturb:
+            P = P + rng.uniform(-perturb, perturb, P.shape)
+        got, _ = ctx.predicate_batch(0, P.reshape(-1, 6))
+        ref = oracle.orient2d_batch(P.reshape(-1, 6))
+        assert np.array_equal(got, ref)
+        if perturb == 0.0:
+            assert np.all(ref == 0)
+    # the mesh-level kernels on the perturbed lattice
+    _upload(ctx, m)
+    valid, sign, ninv = ctx.trial_move_validate(np.zeros_like(m.xy))
+    rv, rs, rn = oracle.trial_validate(m.xy, None, m.cells)
+    assert np.array_equal(valid, rv) and np.array_equal(sign, rs)
+    flags, nill = ctx.legality()
+    rf, rnill = oracle.legality(m.xy, None, m.edges)
+    assert np.array_equal(flags, rf) and nill == rnill
+
+
+def test_orient3d_batch(gpu_ctx_factory, oracle):
+    rng = np.random.default_rng(8)
+    base = rng.integers(0, 6, size=(30000, 4, 3)) / 8.0
+    pts = base + np.where(rng.uniform(size=(30000, 1, 1)) < 0.5, 0.0, rng.uniform(-1e-15, 1e-15, size=(30000, 4, 3)))
+    ctx = gpu_ctx_factory(3)
+    got, nex = ctx.predicate_batch(2, pts.reshape(-1, 12))
+    ref = oracle.orient3d_batch(pts.reshape(-1, 12))
+    assert np.array_equal(got, ref) and (ref == 0).sum() > 100
+
+
+def test_3d_path(gpu_ctx_factory, oracle):
+    from mmesh_b200 import synth, capi
+    m = synth.lattice3d(12)
+    ctx = gpu_ctx_factory(3)
+    ctx.upload_mesh(m.xyz, m.cells, m.perm, None, m.tris)
+    s = synth.shifts_uniform(m, 0.05 * m.h, 50)
+    valid, sign, ninv = ctx.trial_move_validate(s)
+    rv, rs, rn = oracle.trial_validate(m.xyz, s, m.cells, dim=3)
+    assert np.array_equal(valid, rv) and np.array_equal(sign, rs) and ninv == rn == 0
+    # an invalid 3-D cell is the GridError of mmesh.hh:1104-1107
+    big = synth.shifts_uniform(m, 0.9 * m.h, 51)
+    with pytest.raises(capi.GridError) as ei:
+        ctx.trial_move_validate(big)
+    rv, rs, rn = oracle.trial_validate(m.xyz, big, m.cells, dim=3)
+    assert np.array_equal(ei.value.valid_fp, rv) and np.array_equal(ei.value.orient_sign, rs) and ei.value.n_invalid == rn
+    d, mx = ctx.distance_update()
+    rd = oracle.distance_3d(m.xyz, m.tris)
+    assert np.array_equal(d, rd) and mx == oracle.distance_max(rd)
+    prm = ctx.get_params()
+    prm.minH, prm.maxH, prm.factor = 0.25 * m.h, 1.3 * m.h, 1.5
+    ctx.set_params(prm)
+    marks, le, counts = ctx.mark_elements(run_distance=False)
+    rm, rle, rc = oracle.mark(m.xyz, rd, m.cells, m.perm, oracle.Params.from_buffer_copy(bytes(prm)), oracle.distance_max(rd), dim=3)
+    assert np.array_equal(marks, rm) and np.array_equal(le, rle) and tuple(counts) == tuple(rc)
+    assert 0 < rc[0] < m.nc
+    ctx.move_vertices(s)
+    assert np.array_equal(ctx.download_coords(), oracle.move(m.xyz, s))
+    # P0 trace / skeleton transfer
+    rng = np.random.default_rng(2)
+    nf = m.tris.shape[0]
+    inside = rng.integers(0, m.nc, nf).astype(np.int32)
+    outside = rng.integers(-1, m.nc, nf).astype(np.int32)
+    u = rng.uniform(size=m.nc)
+    ug = rng.uniform(size=nf)
+    tin, tout, sk = ctx.trace_skeleton_p0(inside, outside, u, ug)
+    assert np.array_equal(tin, u[inside]) and np.array_equal(tout, np.where(outside >= 0, u[np.maximum(outside, 0)], 0.0))
+    assert np.array_equal(sk, ug)
+
+
+def test_adapt_step_composition(gpu_ctx_factory, oracle):
+    """mmb_adapt_step == markElements -> ensureVertexMovement -> adapt(handle) -> moveVertices -> legality."""
+    from mmesh_b200 import synth
+    m = _mesh1(80)
+    s = synth.shifts_uniform(m, 0.3 * m.h, 30)
+    new_off, new_cell, old_xy, old_idx = synth.pairs_self_and_neighbours(m, m.xy - s)
+    ctx = gpu_ctx_factory(2)
+    _upload(ctx, m)
+    prm = ctx.indicator_init()
+    ctx.upload_pairs(new_off, new_cell, old_xy, old_idx)
+    rng = np.random.default_rng(5)
+    dofs = rng.uniform(size=(m.nc, 3))
+    ctx.project(3, dofs, download=False)      # makes the DOFs resident
+    ctx.upload_shifts(s)
+    res = ctx.adapt_step(None, ncomp=3)
+    oprm = oracle.Params.from_buffer_copy(bytes(prm))
+    rd = oracle.distance_2d(m.xy, m.segs)
+    rm, _, rc = oracle.mark(m.xy, rd, m.cells, m.perm, oprm, oracle.distance_max(rd))
+    rv, rs, rn = oracle.trial_validate(m.xy, s, m.cells)
+    _, rmass, rcov, rnpc = oracle.project(m.xy, m.cells, m.perm, new_off, new_cell, old_xy, old_idx, dofs, m.nc, 3, oprm)
+    moved = oracle.move(m.xy, s)
+    rf, rnill = oracle.legality(moved, None, m.edges)
+    assert res.n_invalid == rn and res.n_orient_nonpos == (rs <= 0).sum()
+    assert (res.n_refine, res.n_coarsen) == tuple(rc)
+    assert res.n_illegal == rnill and res.n_pieces == rnpc
+    assert res.max_dist == oracle.distance_max(rd)
+    assert abs(res.mass_new - rmass) <= 1e-13 * abs(rmass) and abs(res.covered_area - rcov) <= 1e-13 * rcov
+    assert np.array_equal(ctx.download_coords(), moved)
+    assert ctx.launch_count > 0
