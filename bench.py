@@ -195,7 +195,8 @@ def main():
         return
 
     torch.cuda.set_device(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: the library launches on it, the events time it
+    torch.cuda.set_stream(stream)
     w = make_workload(args)
     m = w["mesh"]
     ctx = capi.Context(dim=2, device=local_rank, stream=stream.cuda_stream)
