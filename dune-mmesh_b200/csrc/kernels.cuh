@@ -270,38 +270,67 @@ k_pred_exact(int which, const double* __restrict__ pts, const int32_t* __restric
 // ------------------------------------------------------------------------------------------------------
 struct SegLeaf { double c0x, c0y, c1x, c1y, n0, n1; };   // facet corners (AffineGeometry::corner) + Plane normal
 
-// leaves in Morton order of the (upload-time) midpoints; boxes: node i in [1, 2L), children 2i, 2i+1
+// AABB tree over the facets in Morton order of their (upload-time) midpoints: implicit heap, node i in [1, 2L),
+// children 2i / 2i+1, leaves at L + s.  Boxes are float4 (minx, miny, maxx, maxy) rounded OUTWARD, so every fp32
+// test below is a rigorous lower bound; the per-facet arithmetic stays fp64 and identical to the reference.
+__device__ __forceinline__ float4 box_merge(float4 a, float4 b) {
+  return make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+// One launch refits the whole tree: each block reduces 256 leaves in shared memory (8 levels); the block that
+// finishes last (atomic ticket) reduces the remaining top levels.
 __global__ void __launch_bounds__(256)
-k_seg_prepare(const double2* __restrict__ xy, const int2* __restrict__ segs_sorted, int ns, int L,
-              SegLeaf* __restrict__ leaf, double4* __restrict__ box) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= L) return;
-  double4 b = make_double4(INFINITY, INFINITY, -INFINITY, -INFINITY);
-  if (i < ns) {
+k_bvh_build2d(const double2* __restrict__ xy, const int2* __restrict__ segs_sorted, int ns, int L,
+              SegLeaf* __restrict__ leaf, float4* __restrict__ box, unsigned* __restrict__ ticket) {
+  __shared__ float4 sb[512];
+  __shared__ bool last;
+  const int t = threadIdx.x;
+  const int W = L < 256 ? L : 256;                       // leaves per block (power of two)
+  const int i = blockIdx.x * W + t;
+  float4 b = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+  if (t < W && i < ns) {
     const int2 s = segs_sorted[i];
     const double2 v0 = ldg2(xy + s.x), v1 = ldg2(xy + s.y);
     SegLeaf f;
     f.c0x = v0.x; f.c0y = v0.y;
-    f.c1x = v0.x + 1.0 * (v1.x - v0.x);                    // corner(1) = origin + J^T e_1
+    f.c1x = v0.x + 1.0 * (v1.x - v0.x);                  // corner(1) = origin + J^T e_1
     f.c1y = v0.y + 1.0 * (v1.y - v0.y);
-    double n0 = f.c0x - f.c1x, n1 = f.c0y - f.c1y;         // n_ = a - b
-    { const double t = n0; n0 = n1; n1 = t; }              // swap
+    double n0 = f.c0x - f.c1x, n1 = f.c0y - f.c1y;       // Plane: n_ = a - b
+    { const double tt = n0; n0 = n1; n1 = tt; }          // std::swap(n_[0], n_[1])
     n0 *= -1.0;
     double nn = 0.0; nn += n0 * n0; nn += n1 * n1; nn = sqrt(nn);
     f.n0 = n0 / nn; f.n1 = n1 / nn;
     leaf[i] = f;
-    b = make_double4(fmin(f.c0x, f.c1x), fmin(f.c0y, f.c1y), fmax(f.c0x, f.c1x), fmax(f.c0y, f.c1y));
+    b = make_float4(__double2float_rd(fmin(f.c0x, f.c1x)), __double2float_rd(fmin(f.c0y, f.c1y)),
+                    __double2float_ru(fmax(f.c0x, f.c1x)), __double2float_ru(fmax(f.c0y, f.c1y)));
   }
-  box[L + i] = b;
-}
-__global__ void __launch_bounds__(1024) k_bvh_upper(int L, double4* __restrict__ box) {
-  for (int lvl = L >> 1; lvl >= 1; lvl >>= 1) {
-    for (int i = lvl + threadIdx.x; i < 2 * lvl; i += blockDim.x) {
-      const double4 a = box[2 * i], b = box[2 * i + 1];
-      box[i] = make_double4(fmin(a.x, b.x), fmin(a.y, b.y), fmax(a.z, b.z), fmax(a.w, b.w));
+  if (t < W) { sb[W + t] = b; box[L + i] = b; }
+  const int g0 = L / W + blockIdx.x;                     // global index of this block's subtree root
+  for (int w = W >> 1, d = 1; w >= 1; w >>= 1, ++d) {
+    __syncthreads();
+    if (t < w) {
+      const float4 m = box_merge(sb[2 * (w + t)], sb[2 * (w + t) + 1]);
+      sb[w + t] = m;
+      // local node (w + t) sits `lev` levels below the subtree root, offset t inside its level
+      int lev = 0; for (int x = w; x > 1; x >>= 1) ++lev;
+      box[((size_t)g0 << lev) + t] = m;
     }
+  }
+  if (L <= W) return;                                    // single block: done (root written above)
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  const int nb = L / W;                                  // top tree: leaves are the nb subtree roots at [nb, 2nb)
+  for (int w = nb >> 1; w >= 1; w >>= 1) {
+    for (int j = w + t; j < 2 * w; j += 256) {
+      const float4 a = __ldcg(box + 2 * j), c = __ldcg(box + 2 * j + 1);
+      box[j] = box_merge(a, c);
+    }
+    __threadfence_block();
     __syncthreads();
   }
+  if (t == 0) *ticket = 0;
 }
 __device__ __forceinline__ double seg_distance(const SegLeaf& f, double px, double py) {
   {  // i = 0: vi = c0, vj = c1
@@ -318,58 +347,90 @@ __device__ __forceinline__ double seg_distance(const SegLeaf& f, double px, doub
   double sd = 0.0; sd += f.n0 * dx; sd += f.n1 * dy;
   return fabs(sd);
 }
-__device__ __forceinline__ double box_dist2(const double4 b, double px, double py) {
-  const double dx = fmax(fmax(b.x - px, px - b.z), 0.0), dy = fmax(fmax(b.y - py, py - b.w), 0.0);
-  return dx * dx + dy * dy;
-}
-__global__ void __launch_bounds__(256)
-k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restrict__ leaf,
-             const double4* __restrict__ box, int ns, int L, double* __restrict__ dist, Counters* __restrict__ cnt) {
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double best = 1e100;
-  if (v < nv && ns > 0) {
-    const double2 p = ldg2(xy + v);
-    const double4 root = ldg4(box + 1);
-    const double diag = (root.z - root.x) + (root.w - root.y);   // >= any facet length
-    // conservative cull threshold: a node whose box distance exceeds T cannot hold a facet whose *computed*
-    // distance is below `best` (computed vs true distance differ by O(1e-15 (d + len)))
-    double T2;
-    { const double T = best + 1e-12 * (best + diag); T2 = T * T * (1.0 + 1e-12); }
-    int stack[40]; double sd2[40]; int sp = 0;
-    int node = 1;
+struct DistQuery {
+  double px, py, best, diag;
+  float pxlo, pxhi, pylo, pyhi, T2f;
+  int arg;
+  // conservative cull threshold: a node whose box distance exceeds T cannot hold a facet whose *computed* distance
+  // is below `best` (computed and true distance differ by O(1e-15 (d + len)); diag >= any facet length)
+  __device__ __forceinline__ void set_threshold() {
+    const double T = best + 1e-12 * (best + diag);
+    T2f = __double2float_ru(T * T * (1.0 + 1e-12));
+  }
+  // rigorous fp32 lower bound of the squared distance from the query point to a (outward-rounded) box
+  __device__ __forceinline__ float lb2(const float4 b) const {
+    const float dx = fmaxf(fmaxf(__fsub_rd(b.x, pxhi), __fsub_rd(pxlo, b.z)), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(b.y, pyhi), __fsub_rd(pylo, b.w)), 0.f);
+    return __fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy));
+  }
+  __device__ __forceinline__ void eval_leaf(const SegLeaf* __restrict__ leaf, int s) {
+    const SegLeaf f = leaf[s];
+    const double d = seg_distance(f, px, py);
+    if (d < best) { best = d; arg = s; set_threshold(); }          // distance.hh:137-138
+  }
+  // nearest-first depth-first search of the subtree rooted at `root`
+  __device__ __forceinline__ void dfs(const SegLeaf* __restrict__ leaf, const float4* __restrict__ box, int ns, int L, int root) {
+    int stack[32]; float sd2[32]; int sp = 0;
+    int node = root;
     for (;;) {
       if (node >= L) {
-        const int s = node - L;
-        if (s < ns) {
-          const SegLeaf f = leaf[s];
-          const double d = seg_distance(f, p.x, p.y);
-          if (d < best) {                                           // distance.hh:137-138
-            best = d;
-            const double T = best + 1e-12 * (best + diag); T2 = T * T * (1.0 + 1e-12);
-          }
-        }
+        if (node - L < ns) eval_leaf(leaf, node - L);
         node = 0;
       } else {
-        const double dl = box_dist2(ldg4(box + 2 * node), p.x, p.y);
-        const double dr = box_dist2(ldg4(box + 2 * node + 1), p.x, p.y);
+        const float dl = lb2(__ldg(box + 2 * node)), dr = lb2(__ldg(box + 2 * node + 1));
         const bool lf = dl <= dr;
-        const double dn = lf ? dl : dr, df = lf ? dr : dl;
+        const float dn = lf ? dl : dr, df = lf ? dr : dl;
         const int nn = 2 * node + (lf ? 0 : 1), nf = 2 * node + (lf ? 1 : 0);
-        if (dn > T2) node = 0;
-        else {
-          if (!(df > T2)) { stack[sp] = nf; sd2[sp] = df; ++sp; }
-          node = nn;
-        }
+        if (dn > T2f) node = 0;
+        else { if (!(df > T2f)) { stack[sp] = nf; sd2[sp] = df; ++sp; } node = nn; }
       }
       if (node == 0) {
-        while (sp > 0) { --sp; if (!(sd2[sp] > T2)) { node = stack[sp]; break; } }
+        while (sp > 0) { --sp; if (!(sd2[sp] > T2f)) { node = stack[sp]; break; } }
         if (node == 0) break;
       }
     }
   }
-  if (v < nv) dist[v] = best;
+};
+// Per vertex: start from a hint facet (last step's nearest facet; on a cold start the warp leader's full search
+// seeds its Hilbert-neighbours), then walk leaf -> root testing each sibling subtree once.  The siblings along
+// that path partition all other leaves, so the result is the minimum over ALL facets, like distance.hh:42-59.
+__global__ void __launch_bounds__(256)
+k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restrict__ leaf,
+             const float4* __restrict__ box, int ns, int L, double* __restrict__ dist, int32_t* __restrict__ hint,
+             Counters* __restrict__ cnt) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = v < nv && ns > 0;
+  DistQuery q;
+  q.best = 1e100; q.arg = -1;
+  if (live) {
+    const double2 p = ldg2(xy + v);
+    q.px = p.x; q.py = p.y;
+    q.pxlo = __double2float_rd(p.x); q.pxhi = __double2float_ru(p.x);
+    q.pylo = __double2float_rd(p.y); q.pyhi = __double2float_ru(p.y);
+    const float4 root = __ldg(box + 1);
+    q.diag = ((double)root.z - (double)root.x) + ((double)root.w - (double)root.y);
+    q.set_threshold();
+  }
+  int h = live ? hint[v] : 0;
+  if (h >= ns) h = -1;
+  const unsigned cold = __ballot_sync(0xffffffffu, live && h < 0);
+  if (cold) {                                            // cold start: one full search per warp seeds the others
+    const int leader = __ffs(cold) - 1;
+    if ((threadIdx.x & 31) == leader) q.dfs(leaf, box, ns, L, 1);
+    const int seed = __shfl_sync(0xffffffffu, q.arg, leader);
+    if (live && h < 0) h = seed;
+  }
+  if (live) {
+    q.eval_leaf(leaf, h);
+    for (int node = L + h; node > 1; node >>= 1) {
+      const int sib = node ^ 1;
+      if (!(q.lb2(__ldg(box + sib)) > q.T2f)) q.dfs(leaf, box, ns, L, sib);
+    }
+    hint[v] = q.arg;
+  }
+  if (v < nv) dist[v] = q.best;
   // Distance::maximum (distance.hh:118-123): max starting from 0.0; non-negative doubles order like integers
-  unsigned long long bits = (v < nv) ? (unsigned long long)__double_as_longlong(best) : 0ull;
+  unsigned long long bits = (v < nv) ? (unsigned long long)__double_as_longlong(q.best) : 0ull;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, bits, o); bits = t > bits ? t : bits; }
   __shared__ unsigned long long sm[8];
@@ -578,44 +639,55 @@ k_compact_scatter(const uint8_t* __restrict__ flags, int64_t n, uint8_t match, c
 constexpr int MAXPOLY = 12;   // rigorous bound for triangle x triangle with the epsilon cases is 9
 struct Poly { double x[MAXPOLY], y[MAXPOLY]; int n; };
 
-__device__ __forceinline__ void line_isect(double p1x, double p1y, double p2x, double p2y, double q1x, double q1y,
-                                           double q2x, double q2y, double& ox, double& oy) {
-  double dPx = p1x - p2x, dPy = p1y - p2y, dQx = q1x - q2x, dQy = q1y - q2y;
-  const double scale = dPx * dQy - dQx * dPy;
-  const double fq = q1x * q2y - q1y * q2x;
-  const double fp = p1x * p2y - p1y * p2x;
-  dPx *= fq; dPy *= fq; dQx *= fp; dQy *= fp;
-  ox = (dQx - dPx) / scale; oy = (dQy - dPy) / scale;
-}
+// Sutherland-Hodgman, polygoncutting.hh:17-96.  Same case analysis and the same arithmetic as the reference; the
+// side value of a vertex is computed once and reused as `second` of one edge and `first` of the next (identical
+// expression, identical bits), and the q1 x q2 term of lineIntersectionPoint (:100-114) is hoisted per clip edge.
 __device__ __forceinline__ void sh_clip(const double cx[3], const double cy[3], const double ex[3], const double ey[3],
-                                        double eps, Poly& out) {
-  Poly in;
-  out.n = 3;
+                                        double eps, Poly& A, Poly& B, Poly*& result) {
+  Poly* in = &B; Poly* out = &A;
+  out->n = 3;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { out.x[i] = cx[i]; out.y[i] = cy[i]; }
+  for (int i = 0; i < 3; ++i) { out->x[i] = cx[i]; out->y[i] = cy[i]; }
 #pragma unroll 1
   for (int ci = 0; ci < 3; ++ci) {
     const int cn = ci == 2 ? 0 : ci + 1;
     const double q1x = ex[ci], q1y = ey[ci], q2x = ex[cn], q2y = ey[cn];
     const double dQx = q2x - q1x, dQy = q2y - q1y;
     const double q2xq1 = q1y * q2x - q1x * q2y;
-    in = out; out.n = 0;
-    for (int ii = 0; ii < in.n; ++ii) {
-      const int i2 = ii + 1 == in.n ? 0 : ii + 1;
-      const double first = -dQx * in.y[ii] + dQy * in.x[ii] + q2xq1;
-      const double second = -dQx * in.y[i2] + dQy * in.x[i2] + q2xq1;
-      if (first > eps && second < -eps) {
-        line_isect(in.x[ii], in.y[ii], in.x[i2], in.y[i2], q1x, q1y, q2x, q2y, out.x[out.n], out.y[out.n]); out.n++;
-        out.x[out.n] = in.x[i2]; out.y[out.n] = in.y[i2]; out.n++;
-      } else if (first < -eps && second > eps) {
-        line_isect(in.x[ii], in.y[ii], in.x[i2], in.y[i2], q1x, q1y, q2x, q2y, out.x[out.n], out.y[out.n]); out.n++;
-      } else if (first >= -eps && second > eps) {
-      } else {
-        out.x[out.n] = in.x[i2]; out.y[out.n] = in.y[i2]; out.n++;
+    const double ndQx = -dQx;
+    const double iQx = q1x - q2x, iQy = q1y - q2y;          // deltaQ of lineIntersectionPoint
+    const double fq = q1x * q2y - q1y * q2x;
+    { Poly* t = in; in = out; out = t; }
+    const int n = in->n;
+    int m = 0;
+    if (n > 0) {
+      const double f0 = ndQx * in->y[0] + dQy * in->x[0] + q2xq1;
+      double first = f0;
+      double ax = in->x[0], ay = in->y[0];
+#pragma unroll 1
+      for (int ii = 0; ii < n; ++ii) {
+        const int i2 = ii + 1 == n ? 0 : ii + 1;
+        const double bx = in->x[i2], by = in->y[i2];
+        const double second = i2 == 0 ? f0 : ndQx * by + dQy * bx + q2xq1;
+        const bool c1 = first > eps && second < -eps;
+        const bool c2 = first < -eps && second > eps;
+        if (c1 || c2) {
+          double dPx = ax - bx, dPy = ay - by;
+          const double scale = dPx * iQy - iQx * dPy;
+          const double fp = ax * by - ay * bx;
+          dPx *= fq; dPy *= fq;
+          out->x[m] = (iQx * fp - dPx) / scale; out->y[m] = (iQy * fp - dPy) / scale; ++m;
+          if (c1) { out->x[m] = bx; out->y[m] = by; ++m; }
+        } else if (!(first >= -eps && second > eps)) {
+          out->x[m] = bx; out->y[m] = by; ++m;
+        }
+        first = second; ax = bx; ay = by;
+        if (m > MAXPOLY - 2) { m = 0; break; }
       }
-      if (out.n > MAXPOLY - 2) { out.n = 0; return; }
     }
+    out->n = m;
   }
+  result = out;
 }
 struct Aff2 { double ox, oy, i00, i01, i10, i11, vol; };
 __device__ __forceinline__ Aff2 aff2_make(double c0x, double c0y, double c1x, double c1y, double c2x, double c2y) {
@@ -636,102 +708,212 @@ __device__ __forceinline__ void aff2_local(const Aff2& g, double x, double y, do
   xi = l0; eta = l1;
 }
 
-// cut one (old, new) pair; old6 = CachingEntity::vertex_; e = new cell TDS-order corners.
-// On return poly holds the clipped polygon (possibly translated by -org when prm.clip_translate).
-__device__ __forceinline__ void cut_pair(const double* __restrict__ old6, const double ex_[3], const double ey_[3],
-                                         const DevParams& prm, Poly& poly, double cux[3], double cuy[3], double& orgx,
-                                         double& orgy) {
-  double cx[3], cy[3], ex[3], ey[3];
-  const double o0x = old6[0], o0y = old6[1];
-  const double j00 = old6[2] - o0x, j01 = old6[3] - o0y, j10 = old6[4] - o0x, j11 = old6[5] - o0y;
-  cx[0] = o0x; cy[0] = o0y;                                           // cgeo.corner(i), cutsettriangulation.hh:40
-  cx[1] = (o0x + 1.0 * j00) + 0.0 * j10; cy[1] = (o0y + 1.0 * j01) + 0.0 * j11;
-  cx[2] = (o0x + 0.0 * j00) + 1.0 * j10; cy[2] = (o0y + 0.0 * j01) + 1.0 * j11;
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// ---- shared-memory Sutherland-Hodgman, organised in convergent passes ------------------------------------------
+// lineIntersectionPoint, polygoncutting.hh:100-114 (iQ = q1 - q2, fq = q1 x q2 hoisted per clip edge)
+__device__ __forceinline__ double2 line_isect(double ax, double ay, double bx, double by, double iQx, double iQy, double fq) {
+  double dPx = ax - bx, dPy = ay - by;
+  const double scale = dPx * iQy - iQx * dPy;
+  const double fp = ax * by - ay * bx;
+  dPx *= fq; dPy *= fq;
+  return make_double2((iQx * fp - dPx) / scale, (iQy * fp - dPy) / scale);
+}
+// One clip edge (q1 -> q2) of polygoncutting.hh:17-96 applied to the polygon load(0..n-1), n <= NMAX; the result
+// goes to store(0..m-1), m <= n + n/2 is returned.  Same case analysis, operand order and IEEE operations as the
+// reference, but split into three passes so that the lanes of a warp stay together:
+//   1. side value of every vertex, case code of every edge (outside->inside, inside->outside, drop, keep),
+//   2. the crossing points (a convex polygon has at most one edge of each crossing kind),
+//   3. emission in edge order (pure data movement; further crossings of a kind -- only possible through the
+//      epsilon band -- are computed in place).
+template <int NMAX, class Load, class Store>
+__device__ __forceinline__ int clip_stage(Load load, int n, double q1x, double q1y, double q2x, double q2y, double eps,
+                                          Store store) {
+  if (n <= 0) return 0;
+  const double dQx = q2x - q1x, dQy = q2y - q1y;
+  const double q2xq1 = q1y * q2x - q1x * q2y;
+  const double ndQx = -dQx;
+  const double iQx = q1x - q2x, iQy = q1y - q2y;
+  const double fq = q1x * q2y - q1y * q2x;
+  double f[NMAX];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { ex[i] = ex_[i]; ey[i] = ey_[i]; }
-  orgx = 0.0; orgy = 0.0;
-  if (prm.clip_translate) {
-    orgx = ex[0]; orgy = ey[0];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { cx[i] -= orgx; cy[i] -= orgy; ex[i] -= orgx; ey[i] -= orgy; }
+  for (int i = 0; i < NMAX; ++i) {
+    f[i] = 0.0;
+    if (i < n) { double x, y; load(i, x, y); f[i] = ndQx * y + dQy * x + q2xq1; }
   }
+  unsigned codes = 0;           // 2 bits per edge: 0 keep second point, 1 X + second point, 2 X only, 3 nothing
+  int e1 = -1, e2 = -1;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { cux[i] = cx[i]; cuy[i] = cy[i]; }
-  // cutsettriangulation.hh:46-49: orientation value truncated to int
-  const double od = (cy[1] - cy[0]) * (cx[2] - cx[1]) - (cx[1] - cx[0]) * (cy[2] - cy[1]);
-  const int o = (fabs(od) < 2147483648.0) ? (int)od : 0;
-  if (o > 0) { double t = cx[1]; cx[1] = cx[2]; cx[2] = t; t = cy[1]; cy[1] = cy[2]; cy[2] = t; }
-  sh_clip(cx, cy, ex, ey, prm.clip_eps, poly);
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      const double first = f[i];
+      double second = f[0];
+      if (i + 1 < NMAX) { if (i + 1 < n) second = f[i + 1 < NMAX ? i + 1 : 0]; }
+      unsigned c = 0;
+      if (first > eps && second < -eps) { c = 1; if (e1 < 0) e1 = i; }
+      else if (first < -eps && second > eps) { c = 2; if (e2 < 0) e2 = i; }
+      else if (first >= -eps && second > eps) c = 3;
+      codes |= c << (2 * i);
+    }
+  }
+  double2 X1 = make_double2(0.0, 0.0), X2 = X1;
+  if (e1 >= 0) { double ax, ay, bx, by; load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by); X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+  if (e2 >= 0) { double ax, ay, bx, by; load(e2, ax, ay); load(e2 + 1 == n ? 0 : e2 + 1, bx, by); X2 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    const unsigned c = (codes >> (2 * i)) & 3u;
+    if (c == 3u) continue;
+    double bx, by;
+    load(i + 1 == n ? 0 : i + 1, bx, by);
+    if (c != 0u) {
+      double2 X = c == 1u ? X1 : X2;
+      if (i != (c == 1u ? e1 : e2)) { double ax, ay; load(i, ax, ay); X = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+      store(m, X.x, X.y); ++m;
+    }
+    if (c <= 1u) { store(m, bx, by); ++m; }
+  }
+  return m;
 }
 
-template <int NCOMP>
-__global__ void __launch_bounds__(128)
+// Conservative projection old -> new.  LPC lanes cooperate on one new cell (LPC = 1: one thread walks the pairs
+// sequentially, so every bit of the P0 accumulation follows the reference order; LPC = 4: lane q clips pairs
+// q, q+4, ... and the per-pair partial sums are added in pair order).  The polygons of the three clip stages
+// (<= 4, <= 6, <= 9 vertices) live in shared memory in [slot][thread] layout (bank = thread => conflict free).
+constexpr int PROJ_THREADS = 128;
+template <int NCOMP, int LPC, int MINB>
+__global__ void __launch_bounds__(PROJ_THREADS, MINB)
 k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1,
           const int32_t* __restrict__ cv2, const uint8_t* __restrict__ perm, const long long* __restrict__ new_off,
           const int32_t* __restrict__ new_cell, int64_t nnew, const double* __restrict__ old_xy,
           const int32_t* __restrict__ old_idx, const double* __restrict__ dofs_old, double* __restrict__ dofs_new,
           DevParams prm, double* __restrict__ part_mass, double* __restrict__ part_cov, Counters* __restrict__ cnt) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double2 sA[4][PROJ_THREADS];
+  __shared__ double2 sB[6][PROJ_THREADS];
+  __shared__ double2 sC[9][PROJ_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t gid = (int64_t)blockIdx.x * PROJ_THREADS + tid;
+  const int64_t i = gid / LPC;
+  const int q = (int)(gid % LPC);
+  const int lane = tid & 31, lead = lane - q;
+  const bool live = i < nnew;
   double mass = 0.0, cov = 0.0;
   unsigned npc = 0;
-  if (i < nnew) {
-    const int K = new_cell[i];
+  int K = 0; long long p0 = 0, p1 = 0;
+  double ex[3] = { 0, 0, 0 }, ey[3] = { 0, 0, 0 }, kx[3], ky[3], orgx = 0.0, orgy = 0.0, volK = 1.0;
+  Aff2 gK;
+  if (live) {
+    K = new_cell[i]; p0 = new_off[i]; p1 = new_off[i + 1];
     const int v[3] = { __ldg(cv0 + K), __ldg(cv1 + K), __ldg(cv2 + K) };
-    const unsigned p = __ldg(perm + K);
-    double ex[3], ey[3];
+    const unsigned pm = __ldg(perm + K);
 #pragma unroll
-    for (int t = 0; t < 3; ++t) { const double2 q = ldg2(xy + v[t]); ex[t] = q.x; ey[t] = q.y; }
-    double kx[3], ky[3];
+    for (int t = 0; t < 3; ++t) { const double2 c = ldg2(xy + v[t]); ex[t] = c.x; ey[t] = c.y; }
 #pragma unroll
-    for (int t = 0; t < 3; ++t) { const int s = (p >> (2 * t)) & 3; kx[t] = ex[s]; ky[t] = ey[s]; }
-    const double volK = aff2_make(kx[0], ky[0], kx[1], ky[1], kx[2], ky[2]).vol;   // element.geometry().volume()
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    bool initialize = true;
-    for (long long pr = new_off[i]; pr < new_off[i + 1]; ++pr) {
-      Poly poly; double cux[3], cuy[3], orgx, orgy;
-      cut_pair(old_xy + 6 * pr, ex, ey, prm, poly, cux, cuy, orgx, orgy);
-      if (poly.n < 3) continue;
-      const double* uo = dofs_old + (int64_t)NCOMP * old_idx[pr];
-      Aff2 gK, gO;
-      double u0 = 0, u1 = 0, u2 = 0;
-      if (NCOMP == 3) {
-        gK = aff2_make(kx[0] - orgx, ky[0] - orgy, kx[1] - orgx, ky[1] - orgy, kx[2] - orgx, ky[2] - orgy);
-        gO = aff2_make(cux[0], cuy[0], cux[1], cuy[1], cux[2], cuy[2]);
-        u0 = uo[0]; u1 = uo[1]; u2 = uo[2];
-      } else u0 = uo[0];
-      for (int t = 1; t < poly.n - 1; ++t) {
-        const double T[6] = { poly.x[0], poly.y[0], poly.x[t], poly.y[t], poly.x[t + 1], poly.y[t + 1] };
-        const double a00 = T[2] - T[0], a01 = T[3] - T[1], a10 = T[4] - T[0], a11 = T[5] - T[1];
-        const double aT = fabs(a00 * a11 - a10 * a01) * 0.5;
-        if (!(aT > prm.drop_area)) continue;                          // cutsettriangulation.hh:60
-        cov += aT; npc++;
-        if (NCOMP == 1) {
-          const double w = aT / volK;                                 // FV restrictLocal weight |son|/|father|
-          if (initialize) acc0 = w * u0; else acc0 += w * u0;
-        } else {
-          const double wq = aT / 3;
+    for (int t = 0; t < 3; ++t) { const int s = (pm >> (2 * t)) & 3; kx[t] = s == 0 ? ex[0] : (s == 1 ? ex[1] : ex[2]); ky[t] = s == 0 ? ey[0] : (s == 1 ? ey[1] : ey[2]); }
+    volK = aff2_make(kx[0], ky[0], kx[1], ky[1], kx[2], ky[2]).vol;      // element.geometry().volume()
+    if (prm.clip_translate) {
+      orgx = ex[0]; orgy = ey[0];
 #pragma unroll
-          for (int m = 0; m < 3; ++m) {
-            const int m2 = m == 2 ? 0 : m + 1;
-            const double x = 0.5 * (T[2 * m] + T[2 * m2]), y = 0.5 * (T[2 * m + 1] + T[2 * m2 + 1]);
-            double xo, eo, xn, en;
-            aff2_local(gO, x, y, xo, eo);
-            aff2_local(gK, x, y, xn, en);
-            const double uval = u0 * (1.0 - xo - eo) + u1 * xo + u2 * eo;
-            const double f = wq * uval;
-            acc0 += f * (1.0 - xn - en); acc1 += f * xn; acc2 += f * en;
+      for (int t = 0; t < 3; ++t) { ex[t] -= orgx; ey[t] -= orgy; }
+    }
+    if (NCOMP == 3) gK = aff2_make(kx[0] - orgx, ky[0] - orgy, kx[1] - orgx, ky[1] - orgy, kx[2] - orgx, ky[2] - orgy);
+  }
+  double acc0 = 0.0; bool initialize = true;     // P0 running value (reference order)
+  double R1 = 0.0, R2 = 0.0, U = 0.0;            // P1 totals over pairs
+  long long maxr = live ? (p1 - p0 + LPC - 1) / LPC : 0;
+  if (LPC > 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const long long t = __shfl_xor_sync(0xffffffffu, maxr, o); maxr = t > maxr ? t : maxr; }
+  }
+  for (long long r = 0; r < maxr; ++r) {
+    const long long pr = p0 + LPC * r + q;
+    double r1 = 0.0, r2 = 0.0, u = 0.0;          // P1 partial sums of this pair
+    if (live && pr < p1) {
+      // old corners: cgeo.corner(i) of the cached vertex_ (cutsettriangulation.hh:40)
+      const double2* o6 = reinterpret_cast<const double2*>(old_xy + 6 * pr);
+      const double2 o0 = __ldg(o6), o1 = __ldg(o6 + 1), o2 = __ldg(o6 + 2);
+      const double j00 = o1.x - o0.x, j01 = o1.y - o0.y, j10 = o2.x - o0.x, j11 = o2.y - o0.y;
+      double cx[3], cy[3];
+      cx[0] = o0.x; cy[0] = o0.y;
+      cx[1] = (o0.x + 1.0 * j00) + 0.0 * j10; cy[1] = (o0.y + 1.0 * j01) + 0.0 * j11;
+      cx[2] = (o0.x + 0.0 * j00) + 1.0 * j10; cy[2] = (o0.y + 0.0 * j01) + 1.0 * j11;
+      if (prm.clip_translate) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { cx[t] -= orgx; cy[t] -= orgy; }
+      }
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      Aff2 gO;
+      {
+        const double* uo = dofs_old + (int64_t)NCOMP * __ldg(old_idx + pr);
+        u0 = __ldg(uo);
+        if (NCOMP == 3) { u1 = __ldg(uo + 1); u2 = __ldg(uo + 2); gO = aff2_make(cx[0], cy[0], cx[1], cy[1], cx[2], cy[2]); }
+      }
+      // cutsettriangulation.hh:46-49: orientation value truncated to int
+      const double od = (cy[1] - cy[0]) * (cx[2] - cx[1]) - (cx[1] - cx[0]) * (cy[2] - cy[1]);
+      const int o = (fabs(od) < 2147483648.0) ? (int)od : 0;
+      const bool sw = o > 0;
+      sB[0][tid] = make_double2(cx[0], cy[0]);
+      sB[1][tid] = sw ? make_double2(cx[2], cy[2]) : make_double2(cx[1], cy[1]);
+      sB[2][tid] = sw ? make_double2(cx[1], cy[1]) : make_double2(cx[2], cy[2]);
+      auto ldA = [&](int k, double& x, double& y) { const double2 v = sA[k][tid]; x = v.x; y = v.y; };
+      auto ldB = [&](int k, double& x, double& y) { const double2 v = sB[k][tid]; x = v.x; y = v.y; };
+      auto stA = [&](int k, double x, double y) { sA[k][tid] = make_double2(x, y); };
+      auto stB = [&](int k, double x, double y) { sB[k][tid] = make_double2(x, y); };
+      auto stC = [&](int k, double x, double y) { sC[k][tid] = make_double2(x, y); };
+      const int nA = clip_stage<3>(ldB, 3, ex[0], ey[0], ex[1], ey[1], prm.clip_eps, stA);
+      const int nB = clip_stage<4>(ldA, nA, ex[1], ey[1], ex[2], ey[2], prm.clip_eps, stB);
+      const int nC = clip_stage<6>(ldB, nB, ex[2], ey[2], ex[0], ey[0], prm.clip_eps, stC);
+      // fan (points[0], points[j-1], points[j]), cutsettriangulation.hh:57-61
+      double fx = 0, fy = 0, fu = 0, ff1 = 0, ff2 = 0, px = 0, py = 0, pu = 0, pf1 = 0, pf2 = 0;
+      for (int j = 0; j < nC; ++j) {
+        const double2 P = sC[j][tid];
+        double uj = 0, f1 = 0, f2 = 0;
+        if (NCOMP == 3) {
+          double xo, eo;
+          aff2_local(gO, P.x, P.y, xo, eo);
+          uj = u0 * (1.0 - xo - eo) + u1 * xo + u2 * eo;
+          aff2_local(gK, P.x, P.y, f1, f2);
+        }
+        if (j == 0) { fx = P.x; fy = P.y; fu = uj; ff1 = f1; ff2 = f2; }
+        else if (j >= 2) {
+          const double a00 = px - fx, a01 = py - fy, a10 = P.x - fx, a11 = P.y - fy;
+          const double aT = fabs(a00 * a11 - a10 * a01) * 0.5;
+          if (aT > prm.drop_area) {                                     // cutsettriangulation.hh:60
+            cov += aT; npc++;
+            if (NCOMP == 1) {
+              const double w = aT / volK;                               // FV restrictLocal weight |son|/|father|
+              if (initialize) acc0 = w * u0; else acc0 += w * u0;
+              initialize = false;
+            } else {
+              const double su = fu + pu + uj;
+              const double s1 = ff1 + pf1 + f1, s2 = ff2 + pf2 + f2;
+              const double d1 = fu * ff1 + pu * pf1 + uj * f1;
+              const double d2 = fu * ff2 + pu * pf2 + uj * f2;
+              const double w12 = aT / 12;
+              r1 += w12 * (su * s1 + d1);
+              r2 += w12 * (su * s2 + d2);
+              u += (aT / 3) * su;
+            }
           }
         }
-        initialize = false;
+        px = P.x; py = P.y; pu = uj; pf1 = f1; pf2 = f2;
       }
     }
+    if (NCOMP == 3) {
+      if (LPC == 1) { R1 += r1; R2 += r2; U += u; }
+      else {
+#pragma unroll
+        for (int l = 0; l < LPC; ++l) { R1 += shfl_d(r1, lead + l); R2 += shfl_d(r2, lead + l); U += shfl_d(u, lead + l); }
+      }
+    }
+  }
+  if (live && q == 0) {
     if (NCOMP == 1) {
       dofs_new[K] = acc0;
       mass = volK * acc0;
     } else {
-      const double S = acc0 + acc1 + acc2;
+      const double R0 = U - R1 - R2;
       const double f = 3.0 / volK;
-      const double r0 = f * (4.0 * acc0 - S), r1 = f * (4.0 * acc1 - S), r2 = f * (4.0 * acc2 - S);
+      const double r0 = f * (4.0 * R0 - U), r1 = f * (4.0 * R1 - U), r2 = f * (4.0 * R2 - U);
       dofs_new[3 * (int64_t)K] = r0; dofs_new[3 * (int64_t)K + 1] = r1; dofs_new[3 * (int64_t)K + 2] = r2;
       mass = volK * ((r0 + r1 + r2) / 3.0);
     }
@@ -741,9 +923,9 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
   for (int o = 16; o > 0; o >>= 1) { mass += __shfl_xor_sync(0xffffffffu, mass, o); cov += __shfl_xor_sync(0xffffffffu, cov, o); }
   npc = warp_sum(npc);
   __shared__ double sm[4], sc[4]; __shared__ unsigned sn[4];
-  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = mass; sc[threadIdx.x >> 5] = cov; sn[threadIdx.x >> 5] = npc; }
+  if (lane == 0) { sm[tid >> 5] = mass; sc[tid >> 5] = cov; sn[tid >> 5] = npc; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     part_mass[blockIdx.x] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
     part_cov[blockIdx.x] = (sc[0] + sc[1]) + (sc[2] + sc[3]);
     atomicAdd(&cnt->n_pieces, (unsigned long long)(sn[0] + sn[1] + sn[2] + sn[3]));
@@ -754,10 +936,8 @@ __global__ void __launch_bounds__(1024)
 k_reduce_partials(const double* __restrict__ a, const double* __restrict__ b, int n, Counters* __restrict__ cnt) {
   __shared__ double sa[1024], sb[1024];
   double xa = 0.0, xb = 0.0;
-  // each thread owns a contiguous chunk (fixed for a given n) and sums it left to right
-  const int chunk = (n + 1023) / 1024;
-  const int lo = threadIdx.x * chunk, hi = min(n, lo + chunk);
-  for (int i = lo; i < hi; ++i) { xa += a[i]; xb += b[i]; }
+  // thread t sums elements t, t+1024, ... (coalesced; the order is a fixed function of n => deterministic)
+  for (int i = threadIdx.x; i < n; i += 1024) { xa += a[i]; xb += b[i]; }
   sa[threadIdx.x] = xa; sb[threadIdx.x] = xb;
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
@@ -781,14 +961,14 @@ k_isect_volume(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, 
   for (long long pr = new_off[i]; pr < new_off[i + 1]; ++pr) {
     const double* o = old_xy + 6 * pr;
     const double cx[3] = { o[0], o[2], o[4] }, cy[3] = { o[1], o[3], o[5] };
-    Poly poly;
-    sh_clip(cx, cy, ex, ey, 1e-14, poly);
+    Poly A, B; Poly* poly;
+    sh_clip(cx, cy, ex, ey, 1e-14, A, B, poly);
     double area = 0.0;
-    if (poly.n >= 3) {
-      for (int a = 0; a < poly.n; ++a) {
-        const int b = a + 1 == poly.n ? 0 : a + 1;
-        area += poly.x[a] * poly.y[b];
-        area -= poly.x[b] * poly.y[a];
+    if (poly->n >= 3) {
+      for (int a = 0; a < poly->n; ++a) {
+        const int b = a + 1 == poly->n ? 0 : a + 1;
+        area += poly->x[a] * poly->y[b];
+        area -= poly->x[b] * poly->y[a];
       }
     }
     vol[pr] = fabs(0.5 * area);

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -51,7 +52,7 @@ struct mmb_context {
   bool has_shift = false, dist_valid = false, mesh_ok = false;
   // bvh
   int L = 1;
-  DBuf<SegLeaf> seg_leaf; DBuf<double4> box2;
+  DBuf<SegLeaf> seg_leaf; DBuf<float4> box2; DBuf<int32_t> seg_hint; DBuf<unsigned> ticket;
   DBuf<TriLeaf> tri_leaf; DBuf<double> box3;
   // projection
   int64_t nnew = 0, npairs = 0, n_old = 0;
@@ -149,7 +150,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->perm.release(); ctx->valid_fp.release(); ctx->edge_flag.release(); ctx->longest.release();
   ctx->orient.release(); ctx->mark.release(); ctx->imark.release(); ctx->edges.release();
   ctx->wl.release(); ctx->list_out.release(); ctx->block_count.release(); ctx->counters.release();
-  ctx->seg_leaf.release(); ctx->box2.release(); ctx->tri_leaf.release(); ctx->box3.release();
+  ctx->seg_leaf.release(); ctx->box2.release(); ctx->seg_hint.release(); ctx->ticket.release(); ctx->tri_leaf.release(); ctx->box3.release();
   ctx->new_off.release(); ctx->new_cell.release(); ctx->old_idx.release(); ctx->old_xy.release();
   ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
   ctx->tr_in.release(); ctx->tr_out.release(); ctx->tr_u.release(); ctx->tr_ug.release();
@@ -257,7 +258,11 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
     CK(cudaMemcpyAsync(ctx->facets_sorted.p, sorted.data(), sorted.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // `sorted` is a stack-owned staging buffer
   }
-  if (dim == 2) { CK(ctx->seg_leaf.ensure(L)); CK(ctx->box2.ensure(2 * (size_t)L)); }
+  if (dim == 2) {
+    CK(ctx->seg_leaf.ensure(L)); CK(ctx->box2.ensure(2 * (size_t)L)); CK(ctx->seg_hint.ensure(nv)); CK(ctx->ticket.ensure(1));
+    CK(cudaMemsetAsync(ctx->seg_hint.p, 0xFF, (size_t)nv * sizeof(int32_t), ctx->stream));    // -1: no hint yet
+    CK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
+  }
   else { CK(ctx->tri_leaf.ensure(L)); CK(ctx->box3.ensure(12 * (size_t)L)); }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
@@ -441,12 +446,11 @@ static int do_distance(mmb_context* ctx) {
   const int ns = (int)ctx->ns, L = ctx->L;
   if (ctx->dim == 2) {
     if (ns) {
-      LAUNCH("seg_prepare", k_seg_prepare, grid_for(L, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets_sorted.p, ns, L,
-             ctx->seg_leaf.p, ctx->box2.p);
-      LAUNCH("bvh_upper", k_bvh_upper, 1, 1024, L, ctx->box2.p);
+      LAUNCH("bvh_build2d", k_bvh_build2d, L < 256 ? 1 : L / 256, 256, (const double2*)ctx->x.p, (const int2*)ctx->facets_sorted.p,
+             ns, L, ctx->seg_leaf.p, ctx->box2.p, ctx->ticket.p);
     }
     LAUNCH("distance2d", k_distance2d, grid_for(ctx->nv, 256), 256, (const double2*)ctx->x.p, ctx->nv, ctx->seg_leaf.p,
-           ctx->box2.p, ns, L, ctx->dist.p, ctx->counters.p);
+           ctx->box2.p, ns, L, ctx->dist.p, ctx->seg_hint.p, ctx->counters.p);
   } else {
     if (ns) {
       LAUNCH("tri_prepare", k_tri_prepare, grid_for(L, 256), 256, ctx->x.p, ctx->facets_sorted.p, ns, L, ctx->tri_leaf.p, ctx->box3.p);
@@ -557,7 +561,7 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
           MMB_ERR_INVALID_ARG, "mmb_upload_pairs: null arrays");
   CK(ctx->new_off.ensure(nnew + 1)); CK(ctx->new_cell.ensure(nnew + 1)); CK(ctx->old_idx.ensure(npairs + 1));
   CK(ctx->old_xy.ensure(6 * (size_t)npairs + 1)); CK(ctx->pair_vol.ensure(npairs + 1));
-  const int nb = (int)grid_for(nnew, 128);
+  const int nb = (int)grid_for(4 * nnew, PROJ_THREADS);
   CK(ctx->part_a.ensure(nb)); CK(ctx->part_b.ensure(nb));
   if (nnew) {
     CK(cudaMemcpyAsync(ctx->new_off.p, new_off_host, (size_t)(nnew + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -571,18 +575,28 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
   ctx->nnew = nnew; ctx->npairs = npairs;
   return MMB_OK;
 }
+#define PROJ_ARGS (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p, ctx->new_off.p, ctx->new_cell.p, \
+                  ctx->nnew, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp, ctx->part_a.p, ctx->part_b.p, ctx->counters.p
+static int proj_variant() { static int v = -1; if (v < 0) { const char* e = getenv("MMB_PROJ_VARIANT"); v = e ? atoi(e) : 0; } return v; }
 static int do_project(mmb_context* ctx, int ncomp) {
   if (ctx->nnew == 0) return MMB_OK;
   const DevParams dp = dev_params(ctx->prm);
-  const unsigned nb = grid_for(ctx->nnew, 128);
-  if (ncomp == 1)
-    LAUNCH("project_p0", k_project<1>, nb, 128, (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p,
-           ctx->new_off.p, ctx->new_cell.p, ctx->nnew, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp,
-           ctx->part_a.p, ctx->part_b.p, ctx->counters.p);
-  else
-    LAUNCH("project_p1", k_project<3>, nb, 128, (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p,
-           ctx->new_off.p, ctx->new_cell.p, ctx->nnew, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp,
-           ctx->part_a.p, ctx->part_b.p, ctx->counters.p);
+  unsigned nb;
+  if (ncomp == 1) {
+    nb = grid_for(ctx->nnew, PROJ_THREADS);
+    LAUNCH("project_p0", (k_project<1, 1, 1>), nb, PROJ_THREADS, PROJ_ARGS);
+  } else {
+    const int var = proj_variant();
+    const int lpc = (var == 1 || var == 4) ? 4 : 1;
+    nb = grid_for(lpc * ctx->nnew, PROJ_THREADS);
+    switch (var) {
+      case 1: LAUNCH("project_p1", (k_project<3, 4, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 2: LAUNCH("project_p1", (k_project<3, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 3: LAUNCH("project_p1", (k_project<3, 1, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 4: LAUNCH("project_p1", (k_project<3, 4, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      default: LAUNCH("project_p1", (k_project<3, 1, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
+    }
+  }
   LAUNCH("reduce_partials", k_reduce_partials, 1, 1024, ctx->part_a.p, ctx->part_b.p, (int)nb, ctx->counters.p);
   return MMB_OK;
 }

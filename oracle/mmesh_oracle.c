@@ -714,8 +714,8 @@ typedef struct { double c[3][2]; double e[3][2]; } cut_in;
 
 /* dune/mmesh/grid/cutsettriangulation.hh:31-62.  old6 = CachingEntity::vertex_ (cachingentity.hh:83-89),
    corners re-derived through AffineGeometry::corner (:40); new6 = host->vertex(i)->point() TDS order (:42). */
-static int cutset(const double* old6, const double* new6, const orc_params* prm, double tris[][6],
-                  double c_unswapped[3][2], double origin[2]) {
+static int cutpoly(const double* old6, const double* new6, const orc_params* prm, double pts[MAXPOLY][2],
+                   double c_unswapped[3][2], double origin[2]) {
   double c[3][2], e[3][2];
   double j00 = old6[2] - old6[0], j01 = old6[3] - old6[1], j10 = old6[4] - old6[0], j11 = old6[5] - old6[1];
   c[0][0] = old6[0]; c[0][1] = old6[1];
@@ -735,8 +735,13 @@ static int cutset(const double* old6, const double* new6, const orc_params* prm,
   double od = (c[1][1] - c[0][1]) * (c[2][0] - c[1][0]) - (c[1][0] - c[0][0]) * (c[2][1] - c[1][1]);
   int o = (fabs(od) < 2147483648.0) ? (int)od : 0;
   if (o > 0) { double t0 = c[1][0], t1 = c[1][1]; c[1][0] = c[2][0]; c[1][1] = c[2][1]; c[2][0] = t0; c[2][1] = t1; }
-  double pts[MAXPOLY][2];
   int n = sh_clip(c, e, prm->clip_eps, pts);
+  return n < 3 ? 0 : n;
+}
+static int cutset(const double* old6, const double* new6, const orc_params* prm, double tris[][6],
+                  double c_unswapped[3][2], double origin[2]) {
+  double pts[MAXPOLY][2];
+  int n = cutpoly(old6, new6, prm, pts, c_unswapped, origin);
   if (n < 3) return 0;
   int nt = 0;
   for (int i = 1; i < n - 1; ++i) {
@@ -778,8 +783,14 @@ static inline void aff2_local(const aff2* g, const double x[2], double* xi, doub
 }
 
 /* mmesh.hh:1138-1165 adapt(handle) loop.  Transfer definitions (dune-fem is un-vendored):
-   P0 : u_new[K]  (=|+=) (|T| / |K|) * u_old[K']              (FV restrictLocal with weight |son|/|father|)
-   P1 : local L2 projection, nodal basis on id-order corners, 3 edge-midpoint quadrature per cut triangle */
+   P0 : u_new[K]  (=|+=) (|T| / |K|) * u_old[K']   per cut triangle, in the reference's visiting order
+        (FV restrictLocal with weight |son|/|father|).
+   P1 : local L2 projection onto the nodal basis of the id-ordered corners of K.  For a cut triangle T with
+        vertices v_j the product of two linear functions is integrated exactly by
+            int_T u phi = |T|/12 * ( (sum_j u_j)(sum_j phi_j) + sum_j u_j phi_j ),
+        u_j = u_old(v_j) (barycentric in the cached old cell), phi_j = barycentric coordinates of v_j in K
+        (AffineGeometry::local).  phi_0 = 1 - phi_1 - phi_2 is eliminated through int_T u = |T|/3 sum_j u_j.
+        Each (old,new) pair accumulates its own partial sums; pairs are then added in CSR order. */
 void orc_project(const double* xy, const int32_t* cells, const uint8_t* perm, const int64_t* new_off,
                  const int32_t* new_cell, int64_t nnew, const double* old_xy, const int32_t* old_idx,
                  const double* dofs_old, double* dofs_new, int ncomp, const orc_params* prm, double* mass_new,
@@ -791,52 +802,59 @@ void orc_project(const double* xy, const int32_t* cells, const uint8_t* perm, co
     double e6[6], k[3][2];
     for (int t = 0; t < 3; ++t) { e6[2 * t] = xy[2 * (int64_t)cells[3 * K + t]]; e6[2 * t + 1] = xy[2 * (int64_t)cells[3 * K + t] + 1]; }
     corners2d(xy, cells + 3 * K, perm[K], k);
-    double acc[3] = { 0.0, 0.0, 0.0 }; int initialize = 1;
-    aff2 gK; double volK;
+    double acc0 = 0.0; int initialize = 1;           /* P0 */
+    double R1 = 0.0, R2 = 0.0, U = 0.0;              /* P1 totals over pairs */
+    double volK;
     { aff2 g0; aff2_init(&g0, k[0], k[1], k[2]); volK = g0.vol; }       /* element.geometry().volume() */
     for (int64_t p = new_off[i]; p < new_off[i + 1]; ++p) {
-      double tris[MAXPOLY][6], cu[3][2], org[2];
-      int nt = cutset(old_xy + 6 * p, e6, prm, tris, cu, org);
-      if (nt == 0) continue;
+      double cu[3][2], org[2], pts[MAXPOLY][2];
+      int n = cutpoly(old_xy + 6 * p, e6, prm, pts, cu, org);
+      if (n < 3) continue;
       const double* uo = dofs_old + (int64_t)ncomp * old_idx[p];
-      aff2 gO; memset(&gO, 0, sizeof gO); memset(&gK, 0, sizeof gK);
+      double uj[MAXPOLY], f1[MAXPOLY], f2[MAXPOLY];
       if (ncomp == 3) {
-        double kk[3][2];
+        aff2 gK, gO; double kk[3][2];
         for (int t = 0; t < 3; ++t) { kk[t][0] = k[t][0] - org[0]; kk[t][1] = k[t][1] - org[1]; }
         aff2_init(&gK, kk[0], kk[1], kk[2]);
         aff2_init(&gO, cu[0], cu[1], cu[2]);
+        for (int j = 0; j < n; ++j) {
+          double xo, eo;
+          aff2_local(&gO, pts[j], &xo, &eo);
+          uj[j] = uo[0] * (1.0 - xo - eo) + uo[1] * xo + uo[2] * eo;
+          aff2_local(&gK, pts[j], &f1[j], &f2[j]);
+        }
       }
-      for (int t = 0; t < nt; ++t) {
-        const double* T = tris[t];
-        double a00 = T[2] - T[0], a01 = T[3] - T[1], a10 = T[4] - T[0], a11 = T[5] - T[1];
+      double r1 = 0.0, r2 = 0.0, u = 0.0;            /* per-pair partial sums */
+      for (int t = 1; t < n - 1; ++t) {
+        double a00 = pts[t][0] - pts[0][0], a01 = pts[t][1] - pts[0][1];
+        double a10 = pts[t + 1][0] - pts[0][0], a11 = pts[t + 1][1] - pts[0][1];
         double aT = fabs(a00 * a11 - a10 * a01) * 0.5;
+        if (!(aT > prm->drop_area)) continue;                          /* cutsettriangulation.hh:60 */
         cov += aT; npc++;
         if (ncomp == 1) {
           double w = aT / volK;
-          if (initialize) acc[0] = w * uo[0]; else acc[0] += w * uo[0];
+          if (initialize) acc0 = w * uo[0]; else acc0 += w * uo[0];
+          initialize = 0;
         } else {
-          double wq = aT / 3;
-          for (int m = 0; m < 3; ++m) {
-            const int m2 = (m + 1) % 3;
-            double x[2] = { 0.5 * (T[2 * m] + T[2 * m2]), 0.5 * (T[2 * m + 1] + T[2 * m2 + 1]) };
-            double xo, eo, xn, en;
-            aff2_local(&gO, x, &xo, &eo);
-            aff2_local(&gK, x, &xn, &en);
-            double uval = uo[0] * (1.0 - xo - eo) + uo[1] * xo + uo[2] * eo;
-            double f = wq * uval;
-            acc[0] += f * (1.0 - xn - en); acc[1] += f * xn; acc[2] += f * en;
-          }
+          const double su = uj[0] + uj[t] + uj[t + 1];
+          const double s1 = f1[0] + f1[t] + f1[t + 1], s2 = f2[0] + f2[t] + f2[t + 1];
+          const double d1 = uj[0] * f1[0] + uj[t] * f1[t] + uj[t + 1] * f1[t + 1];
+          const double d2 = uj[0] * f2[0] + uj[t] * f2[t] + uj[t + 1] * f2[t + 1];
+          const double w12 = aT / 12;
+          r1 += w12 * (su * s1 + d1);
+          r2 += w12 * (su * s2 + d2);
+          u += (aT / 3) * su;
         }
-        initialize = 0;
       }
+      R1 += r1; R2 += r2; U += u;
     }
     if (ncomp == 1) {
-      dofs_new[K] = acc[0];
-      mass += (long double)volK * acc[0];
+      dofs_new[K] = acc0;
+      mass += (long double)volK * acc0;
     } else {
-      double S = acc[0] + acc[1] + acc[2];
-      double f = 3.0 / volK;
-      double u0 = f * (4.0 * acc[0] - S), u1 = f * (4.0 * acc[1] - S), u2 = f * (4.0 * acc[2] - S);
+      const double R0 = U - R1 - R2;
+      const double f = 3.0 / volK;
+      double u0 = f * (4.0 * R0 - U), u1 = f * (4.0 * R1 - U), u2 = f * (4.0 * R2 - U);
       dofs_new[3 * (int64_t)K] = u0; dofs_new[3 * (int64_t)K + 1] = u1; dofs_new[3 * (int64_t)K + 2] = u2;
       mass += (long double)volK * ((u0 + u1 + u2) / 3.0);
     }
