@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(256) k_scale(double2* __restrict__ s, double a
 template <bool SHIFT>
 __global__ void __launch_bounds__(256)
 k_validate2d(const double2* __restrict__ xy, const double2* __restrict__ sh, const int4* __restrict__ cv0,
-             const int4* __restrict__ cv1, const int4* __restrict__ cv2, int64_t nc4, int64_t nc,
-             uint32_t* __restrict__ valid4, uint32_t* __restrict__ orient4, int32_t* __restrict__ wl,
+             const int4* __restrict__ cv1, const int4* __restrict__ cv2, int64_t nc4, int64_t nc, int64_t own_lo,
+             int64_t own_hi, uint32_t* __restrict__ valid4, uint32_t* __restrict__ orient4, int32_t* __restrict__ wl,
              Counters* __restrict__ cnt) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned ninv = 0, nnonpos = 0;
@@ -126,12 +126,13 @@ k_validate2d(const double2* __restrict__ xy, const double2* __restrict__ sh, con
       const double area = det / 2;                           // Compute_area_2: determinant(...)/2
       const bool ok = !(area <= 0.0);                        // mmesh.hh:1102
       const bool live = 4 * g + j < nc;
+      const bool own = 4 * g + j >= own_lo && 4 * g + j < own_hi;      // halo cells are evaluated but not counted
       need[j] = live && (s == SIGN_UNKNOWN);
       if (s == SIGN_UNKNOWN) s = 0;
       vbits |= (uint32_t)(ok ? 1u : 0u) << (8 * j);
       obits |= ((uint32_t)(uint8_t)(int8_t)s) << (8 * j);
-      ninv += (live && !ok);
-      nnonpos += (live && !need[j] && s <= 0);
+      ninv += (own && !ok);
+      nnonpos += (own && !need[j] && s <= 0);
     }
     valid4[g] = vbits;
     orient4[g] = obits;
@@ -146,7 +147,7 @@ template <bool SHIFT>
 __global__ void __launch_bounds__(128)
 k_exact_orient2d(const double2* __restrict__ xy, const double2* __restrict__ sh, const int32_t* __restrict__ cv0,
                  const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2, const int32_t* __restrict__ wl,
-                 int8_t* __restrict__ orient, Counters* __restrict__ cnt) {
+                 int64_t own_lo, int64_t own_hi, int8_t* __restrict__ orient, Counters* __restrict__ cnt) {
   const unsigned long long n = cnt->wl_orient;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   unsigned nnonpos = 0, nexact = 0;
@@ -160,7 +161,7 @@ k_exact_orient2d(const double2* __restrict__ xy, const double2* __restrict__ sh,
     int s = orient2d_interval(P.x, P.y, Q.x, Q.y, R.x, R.y);
     if (s == SIGN_UNKNOWN) { s = orient2d_exact(P.x, P.y, Q.x, Q.y, R.x, R.y); nexact++; }
     orient[c] = (int8_t)s;
-    nnonpos += (s <= 0);
+    nnonpos += (s <= 0 && c >= own_lo && c < own_hi);
   }
   block_count_add<128>(nnonpos, nexact, &cnt->n_orient_nonpos, &cnt->n_exact_orient);
 }
@@ -502,8 +503,8 @@ __device__ __forceinline__ int indicator2d(const double2 c0, const double2 c1, c
 __global__ void __launch_bounds__(256)
 k_mark2d(const double2* __restrict__ xy, const double* __restrict__ dist, const int32_t* __restrict__ cv0,
          const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2, const uint8_t* __restrict__ perm, int64_t nc,
-         DevParams prm, const Counters* __restrict__ cin, int8_t* __restrict__ mark, uint8_t* __restrict__ longest,
-         Counters* __restrict__ cnt) {
+         int64_t own_lo, int64_t own_hi, DevParams prm, const Counters* __restrict__ cin, int8_t* __restrict__ mark,
+         uint8_t* __restrict__ longest, Counters* __restrict__ cnt) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned nref = 0, ncoa = 0;
   if (c < nc) {
@@ -518,7 +519,8 @@ k_mark2d(const double2* __restrict__ xy, const double* __restrict__ dist, const 
     const int m = indicator2d(c0, c1, c2, d0, d1, d2, prm, maxDist, le);
     mark[c] = (int8_t)m;
     longest[c] = (uint8_t)le;
-    nref = (m > 0); ncoa = (m < 0);
+    const bool own = c >= own_lo && c < own_hi;
+    nref = (own && m > 0); ncoa = (own && m < 0);
   }
   block_count_add<256>(nref, ncoa, &cnt->n_refine, &cnt->n_coarsen);
 }
@@ -1171,6 +1173,26 @@ k_trace_skeleton(int64_t nf, const int32_t* __restrict__ inside, const int32_t* 
   tin[f] = __ldg(u + inside[f]);
   tout[f] = outside[f] >= 0 ? __ldg(u + outside[f]) : 0.0;
   skel[f] = __ldg(ug + f);
+}
+
+// halo exchange helpers: owned values -> contiguous send buffer, received values -> halo slots
+__global__ void __launch_bounds__(256)
+k_gather2(const double2* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, double2* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void __launch_bounds__(256)
+k_scatter2(double2* __restrict__ dst, const int32_t* __restrict__ idx, int64_t n, const double2* __restrict__ src) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = src[i];
+}
+// the additive scalars of a step as one double vector (counts < 2^53 are exact), ready for a single all-reduce
+__global__ void k_reduce_vector(const Counters* __restrict__ c, double* __restrict__ v) {
+  if (threadIdx.x == 0) {
+    v[0] = (double)c->n_invalid; v[1] = (double)c->n_orient_nonpos; v[2] = (double)c->n_illegal;
+    v[3] = (double)c->n_refine; v[4] = (double)c->n_coarsen; v[5] = (double)c->n_exact_orient;
+    v[6] = (double)c->n_exact_incircle; v[7] = (double)c->n_pieces; v[8] = c->mass_new; v[9] = c->covered_area;
+  }
 }
 
 // AoS -> SoA transposition of the uploaded cell table

@@ -39,6 +39,9 @@ struct mmb_context {
   cudaStream_t stream = nullptr; bool own_stream = false;
   std::string err;
   int64_t nv = 0, nc = 0, ne = 0, ns = 0, nc_pad = 0;
+  int64_t own_lo = 0, own_hi = 0;   // owned cell range (counts); halo cells outside it are evaluated but not counted
+  DBuf<int32_t> halo_send_idx, halo_recv_idx; DBuf<double2> halo_send, halo_recv; int64_t n_halo_send = 0, n_halo_recv = 0;
+  DBuf<double> reduce_vec;
   mmb_params prm{};
   // mesh
   DBuf<double> x, shift, dist;
@@ -155,6 +158,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
   ctx->tr_in.release(); ctx->tr_out.release(); ctx->tr_u.release(); ctx->tr_ug.release();
   ctx->tr_a.release(); ctx->tr_b.release(); ctx->tr_c.release(); ctx->pred_pts.release(); ctx->pred_sign.release();
+  ctx->halo_send_idx.release(); ctx->halo_recv_idx.release(); ctx->halo_send.release(); ctx->halo_recv.release(); ctx->reduce_vec.release();
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -211,6 +215,7 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
   const int dim = ctx->dim, k = dim + 1;
   ctx->mesh_ok = false;
   ctx->nv = nv; ctx->nc = nc; ctx->ne = ne; ctx->ns = ns;
+  ctx->own_lo = 0; ctx->own_hi = nc; ctx->n_halo_send = ctx->n_halo_recv = 0;
   ctx->nc_pad = (nc + 3) / 4 * 4;
   const size_t nx = (size_t)nv * dim + 2;
   CK(ctx->x.ensure(nx)); CK(ctx->shift.ensure(nx)); CK(ctx->dist.ensure(nv));
@@ -332,18 +337,18 @@ static int do_validate(mmb_context* ctx, bool with_shift) {
     const int64_t nc4 = ctx->nc_pad / 4;
     if (with_shift)
       LAUNCH("validate2d", k_validate2d<true>, grid_for(nc4, 256), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, nc4, ctx->nc,
+             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, nc4, ctx->nc, ctx->own_lo, ctx->own_hi,
              (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
     else
       LAUNCH("validate2d", k_validate2d<false>, grid_for(nc4, 256), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, nc4, ctx->nc,
+             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, nc4, ctx->nc, ctx->own_lo, ctx->own_hi,
              (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
     if (with_shift)
       LAUNCH("exact_orient2d", k_exact_orient2d<true>, fb, 128, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->orient.p, c);
+             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->own_lo, ctx->own_hi, ctx->orient.p, c);
     else
       LAUNCH("exact_orient2d", k_exact_orient2d<false>, fb, 128, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->orient.p, c);
+             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->own_lo, ctx->own_hi, ctx->orient.p, c);
   } else {
     if (with_shift)
       LAUNCH("validate3d", k_validate3d<true>, grid_for(ctx->nc, 256), 256, ctx->x.p, ctx->shift.p, ctx->cv[0].p, ctx->cv[1].p,
@@ -515,7 +520,7 @@ static int do_mark(mmb_context* ctx) {
   const DevParams dp = dev_params(ctx->prm);
   if (ctx->dim == 2)
     LAUNCH("mark2d", k_mark2d, grid_for(ctx->nc, 256), 256, (const double2*)ctx->x.p, ctx->dist.p, ctx->cv[0].p, ctx->cv[1].p,
-           ctx->cv[2].p, ctx->perm.p, ctx->nc, dp, ctx->counters.p, ctx->mark.p, ctx->longest.p, ctx->counters.p);
+           ctx->cv[2].p, ctx->perm.p, ctx->nc, ctx->own_lo, ctx->own_hi, dp, ctx->counters.p, ctx->mark.p, ctx->longest.p, ctx->counters.p);
   else
     LAUNCH("mark3d", k_mark3d, grid_for(ctx->nc, 256), 256, ctx->x.p, ctx->dist.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p,
            ctx->cv[3].p, ctx->perm.p, ctx->nc, dp, ctx->counters.p, ctx->mark.p, ctx->longest.p, ctx->counters.p);
@@ -735,6 +740,82 @@ int mmb_predicate_batch(mmb_context* ctx, int which, int64_t n, const double* pt
   CK(cudaMemcpyAsync(sign_host, ctx->pred_sign.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   TRY(fetch_counters(ctx));
   if (n_exact) *n_exact = (int64_t)ctx->h_counters->n_exact_orient;
+  return MMB_OK;
+}
+
+// ---- multi-GPU plumbing: ownership, halo pack/unpack, phased step ------------------------------------------------
+int mmb_set_owned_cells(mmb_context* ctx, int64_t lo, int64_t hi) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && 0 <= lo && lo <= hi && hi <= ctx->nc, MMB_ERR_INVALID_ARG, "bad owned range");
+  ctx->own_lo = lo; ctx->own_hi = hi;
+  return MMB_OK;
+}
+int mmb_halo_setup(mmb_context* ctx, int64_t n_send, const int32_t* send_idx_host, int64_t n_recv, const int32_t* recv_idx_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && n_send >= 0 && n_recv >= 0 && (n_send == 0 || send_idx_host) && (n_recv == 0 || recv_idx_host),
+          MMB_ERR_INVALID_ARG, "mmb_halo_setup: bad arguments");
+  CK(ctx->halo_send_idx.ensure(n_send + 1)); CK(ctx->halo_recv_idx.ensure(n_recv + 1));
+  CK(ctx->halo_send.ensure(n_send + 1)); CK(ctx->halo_recv.ensure(n_recv + 1)); CK(ctx->reduce_vec.ensure(16));
+  if (n_send) CK(cudaMemcpyAsync(ctx->halo_send_idx.p, send_idx_host, n_send * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_recv) CK(cudaMemcpyAsync(ctx->halo_recv_idx.p, recv_idx_host, n_recv * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n_halo_send = n_send; ctx->n_halo_recv = n_recv;
+  return MMB_OK;
+}
+int mmb_halo_pack_shifts(mmb_context* ctx) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2 && ctx->has_shift, MMB_ERR_STATE, "halo pack needs a 2-D mesh with resident shifts");
+  if (ctx->n_halo_send)
+    LAUNCH("halo_pack", k_gather2, grid_for(ctx->n_halo_send, 256), 256, (const double2*)ctx->shift.p, ctx->halo_send_idx.p,
+           ctx->n_halo_send, ctx->halo_send.p);
+  CK(cudaGetLastError());
+  return MMB_OK;
+}
+int mmb_halo_unpack_shifts(mmb_context* ctx) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2 && ctx->has_shift, MMB_ERR_STATE, "halo unpack needs a 2-D mesh with resident shifts");
+  if (ctx->n_halo_recv)
+    LAUNCH("halo_unpack", k_scatter2, grid_for(ctx->n_halo_recv, 256), 256, (double2*)ctx->shift.p, ctx->halo_recv_idx.p,
+           ctx->n_halo_recv, (const double2*)ctx->halo_recv.p);
+  CK(cudaGetLastError());
+  return MMB_OK;
+}
+int mmb_device_buffer(mmb_context* ctx, int which, void** ptr, int64_t* bytes) {
+  if (!ctx || !ptr || !bytes) return MMB_ERR_INVALID_ARG;
+  switch (which) {
+    case 0: *ptr = ctx->halo_send.p; *bytes = ctx->n_halo_send * (int64_t)sizeof(double2); break;
+    case 1: *ptr = ctx->halo_recv.p; *bytes = ctx->n_halo_recv * (int64_t)sizeof(double2); break;
+    case 2: *ptr = &ctx->counters.p->max_dist_bits; *bytes = 8; break;
+    case 3: *ptr = ctx->reduce_vec.p; *bytes = 16 * 8; break;
+    default: return MMB_ERR_INVALID_ARG;
+  }
+  return MMB_OK;
+}
+// phase A: counters reset + Distance::update on the local vertices (local max in the counters)
+int mmb_step_phase_distance(mmb_context* ctx) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  TRY(zero_counters(ctx));
+  TRY(do_distance(ctx));
+  CK(cudaGetLastError());
+  return MMB_OK;
+}
+// phase B: everything after the global max distance is known; leaves the additive scalars in the reduce vector
+int mmb_step_phase_rest(mmb_context* ctx, int ncomp) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->has_shift, MMB_ERR_STATE, "no mesh / shifts");
+  if (ncomp) TRY(stage_dofs(ctx, ncomp, 0, nullptr));
+  TRY(do_mark(ctx));
+  if (ctx->dim == 2 && ctx->ns)
+    LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
+           (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
+  TRY(do_validate(ctx, true));
+  if (ncomp) TRY(do_project(ctx, ncomp));
+  TRY(do_move(ctx));
+  if (ctx->dim == 2) TRY(do_legality(ctx));
+  CK(ctx->reduce_vec.ensure(16));
+  LAUNCH("reduce_vector", k_reduce_vector, 1, 32, ctx->counters.p, ctx->reduce_vec.p);
+  CK(cudaGetLastError());
   return MMB_OK;
 }
 

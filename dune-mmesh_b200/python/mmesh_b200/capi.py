@@ -19,7 +19,8 @@ EXPORTS = [
     "mmb_indicator_init", "mmb_move_vertices", "mmb_trial_move_validate", "mmb_invalid_cells", "mmb_legality",
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
-    "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
+    "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
+    "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
 
@@ -273,6 +274,31 @@ class Context:
         nex = C.c_int64()
         self._ck(lib().mmb_predicate_batch(self._h, C.c_int(which), C.c_int64(pts.shape[0]), _p(pts), _p(out), C.byref(nex)))
         return out, nex.value
+
+    # ---- multi-GPU plumbing ----
+    def set_owned_cells(self, lo, hi):
+        self._ck(lib().mmb_set_owned_cells(self._h, C.c_int64(lo), C.c_int64(hi)))
+
+    def halo_setup(self, send_idx, recv_idx):
+        send_idx, recv_idx = _i32(send_idx), _i32(recv_idx)
+        self._ck(lib().mmb_halo_setup(self._h, C.c_int64(send_idx.shape[0]), _p(send_idx), C.c_int64(recv_idx.shape[0]), _p(recv_idx)))
+
+    def halo_pack_shifts(self):
+        self._ck(lib().mmb_halo_pack_shifts(self._h))
+
+    def halo_unpack_shifts(self):
+        self._ck(lib().mmb_halo_unpack_shifts(self._h))
+
+    def device_buffer(self, which):
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._ck(lib().mmb_device_buffer(self._h, C.c_int(which), C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def step_phase_distance(self):
+        self._ck(lib().mmb_step_phase_distance(self._h))
+
+    def step_phase_rest(self, ncomp):
+        self._ck(lib().mmb_step_phase_rest(self._h, C.c_int(ncomp)))
 
     # ---- instrumentation ----
     def timing_enable(self, on=True):

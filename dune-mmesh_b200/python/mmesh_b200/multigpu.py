@@ -1,0 +1,202 @@
+"""One process per GPU: Hilbert-range shards + one-ring halos; torch.distributed (NCCL over NVLink) carries only the
+halo shift exchange and two tiny reductions per step (max distance; the additive step scalars).
+
+The kernels and the pack/unpack of the halo buffers are the library's own (libmmesh_b200.so); torch is plumbing:
+it wraps the library's device buffers as tensors for the collectives and provides the stream + events.
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+from . import capi, partition
+
+
+class _DevBuf:
+    """Expose a raw device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def device_tensor(torch, ptr, nbytes, dtype):
+    if nbytes == 0 or not ptr:
+        return torch.empty(0, dtype=dtype, device="cuda")
+    item = {torch.float64: ("<f8", 8), torch.int64: ("<i8", 8)}[dtype]
+    return torch.as_tensor(_DevBuf(ptr, (nbytes // item[1],), item[0]), device="cuda")
+
+
+def exchange_rows(dist, send, recv, send_counts, recv_counts, rank, world):
+    """Variable-size all-to-all of rows.  NCCL: one all_to_all_single; gloo (CPU tests): isend/irecv pairs."""
+    if dist.get_backend() == "nccl":
+        dist.all_to_all_single(recv, send, output_split_sizes=[int(c) for c in recv_counts],
+                               input_split_sizes=[int(c) for c in send_counts])
+        return
+    so = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64)
+    ro = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
+    reqs = []
+    for p in range(world):
+        if p == rank:
+            continue
+        if recv_counts[p]:
+            reqs.append(dist.irecv(recv[ro[p]:ro[p + 1]], src=p))
+        if send_counts[p]:
+            reqs.append(dist.isend(send[so[p]:so[p + 1]].contiguous(), dst=p))
+    for r in reqs:
+        r.wait()
+
+
+class ShardedMesh:
+    """A rank's shard living in one mmb context, plus the collectives of one adapt step."""
+
+    def __init__(self, torch, dist, ctx, shard):
+        self.torch, self.dist, self.ctx, self.sh = torch, dist, ctx, shard
+        ctx.upload_mesh(shard.xy, shard.cells, shard.perm, shard.edges, shard.segs)
+        ctx.set_owned_cells(shard.own_lo, shard.own_hi)
+        ctx.halo_setup(shard.send_idx, shard.recv_idx)
+        ps, ns = ctx.device_buffer(0)
+        pr, nr = ctx.device_buffer(1)
+        self.send = device_tensor(torch, ps, ns, torch.float64).view(-1, 2)
+        self.recv = device_tensor(torch, pr, nr, torch.float64).view(-1, 2)
+        pm, nm = ctx.device_buffer(2)
+        self.maxword = device_tensor(torch, pm, nm, torch.int64)
+        pv, nvb = ctx.device_buffer(3)
+        self.vec = device_tensor(torch, pv, nvb, torch.float64)
+
+    def exchange_shifts(self):
+        self.ctx.halo_pack_shifts()
+        exchange_rows(self.dist, self.send, self.recv, self.sh.send_counts, self.sh.recv_counts, self.sh.rank, self.sh.world)
+        self.ctx.halo_unpack_shifts()
+
+    def step(self, ncomp):
+        """markElements -> ensureVertexMovement -> adapt(handle) -> moveVertices -> legality on this shard."""
+        dist, torch = self.dist, self.torch
+        self.exchange_shifts()                                   # halo vertex exchange (owned shifts -> halos)
+        self.ctx.step_phase_distance()
+        dist.all_reduce(self.maxword, op=dist.ReduceOp.MAX)      # Distance::maximum() over all ranks
+        self.ctx.step_phase_rest(ncomp)
+        dist.all_reduce(self.vec, op=dist.ReduceOp.SUM)          # counts + mass in one small vector
+
+    def result(self):
+        v = self.vec.cpu().numpy()
+        md = self.maxword.cpu().numpy().view(np.float64)[0]
+        names = ["n_invalid", "n_orient_nonpos", "n_illegal", "n_refine", "n_coarsen", "n_exact_orient", "n_exact_incircle", "n_pieces"]
+        out = {k: int(v[i]) for i, k in enumerate(names)}
+        out.update(max_dist=float(md), mass_new=float(v[8]), covered_area=float(v[9]))
+        return out
+
+
+def global_indicator_params(m):
+    """RatioIndicator::init (ratioindicator.hh:62-91) on the GLOBAL mesh, evaluated on the host so that every rank
+    uses identical parameters (same IEEE operations as the device kernel: sqrt(dx*dx + dy*dy))."""
+    def lens(a, b):
+        d = m.xy[b] - m.xy[a]
+        return np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+    K, k = 2.0, 2.0 / (2.0 * 4.0)
+    bl = lens(m.edges[:, 0], m.edges[:, 1])
+    maxh, minh = bl.max(), bl.min()
+    if len(m.segs):
+        il = lens(m.segs[:, 0], m.segs[:, 1])
+        maxH, minH = K * il.max(), k * il.min()
+    else:
+        maxH, minH = K * maxh, k * minh
+    return float(minH), float(maxH), float(maxh / minh)
+
+
+def bench_main(args, world, rank, local_rank, METRIC, UNIT, algorithmic_bytes, ClockSampler, make_workload):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    w = make_workload(args)
+    m = w["mesh"]
+    t0 = time.time()
+    shard = partition.make_shard(m, world, rank, w["new_off"], w["new_cell"], w["old_xy"], w["old_idx"])
+    part_s = time.time() - t0
+    ctx = capi.Context(dim=2, device=local_rank, stream=stream.cuda_stream)
+    sm = ShardedMesh(torch, dist, ctx, shard)
+    minH, maxH, factor = global_indicator_params(m)
+    prm = ctx.get_params()
+    prm.minH, prm.maxH, prm.factor = minH, maxH, factor
+    ctx.set_params(prm)
+    ncomp = 3
+    ctx.upload_pairs(shard.new_off, shard.new_cell, shard.old_xy, shard.old_idx)
+    ctx.project(ncomp, w["dofs"][shard.lcells], download=False)
+    # every rank supplies the shifts of its OWNED vertices only; halo entries are filled by the exchange
+    s_local = w["shifts"][shard.lverts].copy()
+    s_local[~shard.owned_vertex] = 0.0
+    ctx.upload_shifts(s_local)
+
+    def step():
+        sm.step(ncomp)
+        ctx.scale_shifts(-1.0)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    res_check = sm.result()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ctx.timing_enable(True)
+    ctx.timing_reset()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)                       # max over ranks, device-timed
+    ms = float(ms.item())
+    launches = ctx.launch_count - l0
+    per_kernel = ctx.timing_get()
+    ctx.timing_enable(False)
+    ctx.timing_reset()
+    clk = clocks.stop() if rank == 0 else None
+    halo = torch.tensor([shard.recv_idx.shape[0], shard.lcells.shape[0] - (shard.c1 - shard.c0), shard.lverts.shape[0]],
+                        device="cuda", dtype=torch.float64)
+    dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        nc = m.nc
+        value = nc / (ms_per_step * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))), "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        lnv, lnc, lne, lns = shard.xy.shape[0], shard.cells.shape[0], shard.edges.shape[0], shard.segs.shape[0]
+        kern = []
+        for name, (tot_ms, cnt) in per_kernel.items():
+            ab = algorithmic_bytes(name, lnv, lnc, lne, lns, shard.old_idx.shape[0], shard.new_cell.shape[0], ncomp)
+            avg = tot_ms / cnt
+            kern.append({"kernel": name, "avg_ms": avg, "share": tot_ms / ms, "launches_per_step": cnt / args.steps,
+                         "algorithmic_bytes": ab, "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None,
+                         "frac": (ab / (avg * 1e-3) / 1e9 / peak) if ab else None})
+        kern.sort(key=lambda k: -k["share"])
+        dom = kern[0]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": w["name"], "cells": nc, "parallelism": "hilbert-range shards x%d, one-ring halo" % world,
+                           "projection": "DG-P1, self+face-neighbour pairs (phi=1)",
+                           "collectives_per_step": "1 all_to_all (halo shifts, <= %d vertices/rank), 1 all_reduce MAX (8 B), 1 all_reduce SUM (128 B)" % int(halo[0].item()),
+                           "halo_cells_max": int(halo[1].item()), "local_vertices_max": int(halo[2].item()),
+                           "l2_policy": "per-rank working set %.2f GB per step" % (sum(k["algorithmic_bytes"] or 0 for k in kern) / 1e9)},
+                "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                             "frac": dom["frac"], "traffic": None, "scope": "rank 0 shard"},
+                "cpu_baseline": None,
+                "e2e": None, "gpu_launches": int(launches), "clocks": clk, "kernels": kern, "check": res_check,
+                "setup_s": w["gen_s"], "partition_s": part_s}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.destroy_process_group()

@@ -143,6 +143,23 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
                         double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host, uint8_t* valid_fp_host,
                         int8_t* orient_sign_host, uint8_t* edge_flags_host, mmb_step_result* res);
 
+/* ---- multi-GPU plumbing (one context per rank; the collectives themselves are issued by the host, e.g.
+   torch.distributed / NCCL, on the buffers exposed by mmb_device_buffer) ------------------------------------------
+   The mesh is sharded by contiguous Hilbert ranges of cells (the reference's own scheme is contiguous ranges of the
+   iteration order, dune/mmesh/misc/partitionhelper.hh:175-200) with a one-ring halo.  Halo cells are evaluated
+   redundantly but only cells in [lo, hi) enter the counters. */
+int mmb_set_owned_cells(mmb_context* ctx, int64_t lo, int64_t hi);
+/* vertex halo: send_idx = local indices of owned vertices other ranks need (concatenated per peer), recv_idx = local
+   indices of the halo vertices in the order their values arrive */
+int mmb_halo_setup(mmb_context* ctx, int64_t n_send, const int32_t* send_idx_host, int64_t n_recv, const int32_t* recv_idx_host);
+int mmb_halo_pack_shifts(mmb_context* ctx);      /* resident shifts[send_idx] -> send buffer */
+int mmb_halo_unpack_shifts(mmb_context* ctx);    /* recv buffer -> resident shifts[recv_idx] */
+/* which: 0 halo send buffer, 1 halo recv buffer (double2 per vertex), 2 the max-distance word (uint64, all-reduce MAX),
+   3 the additive step scalars (double[16], all-reduce SUM; layout of mmb_step_result without max_dist) */
+int mmb_device_buffer(mmb_context* ctx, int which, void** device_ptr, int64_t* bytes);
+int mmb_step_phase_distance(mmb_context* ctx);            /* counters = 0; Distance::update on the local vertices */
+int mmb_step_phase_rest(mmb_context* ctx, int ncomp);     /* mark -> validate -> project -> move -> legality */
+
 /* ---- 3-D extras -------------------------------------------------------------------------------------- */
 /* P0 interface-coupled transfer (dune/python/mmesh/pyskeletontrace.hh:42-64,133-160):
    trace_in[f] = u[inside(f)], trace_out[f] = u[outside(f)], skeleton[f] = u_gamma[f]. */

@@ -1,0 +1,56 @@
+"""Run under torchrun: the sharded step must reproduce the single-GPU step (counts bit-exact, mass to 1e-13).
+   python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/mgpu_check.py [nx]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dune-mmesh_b200", "python"))
+import numpy as np
+import torch
+import torch.distributed as dist
+from mmesh_b200 import capi, multigpu, partition, synth
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+nx = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+m = synth.config3(nx=nx, ny=nx // 2)
+s = synth.shifts_uniform(m, 0.3 * m.h, 30)
+new_off, new_cell, old_xy, old_idx = synth.pairs_self_and_neighbours(m, m.xy - s)
+rng = np.random.default_rng(1)
+dofs = rng.uniform(size=(m.nc, 3))
+minH, maxH, factor = multigpu.global_indicator_params(m)
+sh = partition.make_shard(m, world, rank, new_off, new_cell, old_xy, old_idx)
+ctx = capi.Context(2, lr, stream.cuda_stream)
+sm = multigpu.ShardedMesh(torch, dist, ctx, sh)
+prm = ctx.get_params(); prm.minH, prm.maxH, prm.factor = minH, maxH, factor; prm.drop_area = 1e-12; ctx.set_params(prm)
+ctx.upload_pairs(sh.new_off, sh.new_cell, sh.old_xy, sh.old_idx)
+ctx.project(3, dofs[sh.lcells], download=False)
+sl = s[sh.lverts].copy(); sl[~sh.owned_vertex] = 0.0
+ctx.upload_shifts(sl)
+sm.step(3)
+torch.cuda.synchronize()
+got = sm.result()
+
+
+ok = True
+if rank == 0:
+    ref = capi.Context(2, lr)
+    ref.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
+    p2 = ref.indicator_init()
+    assert (p2.minH, p2.maxH, p2.factor) == (minH, maxH, factor), ((p2.minH, p2.maxH, p2.factor), (minH, maxH, factor))
+    p2.drop_area = 1e-12; ref.set_params(p2)
+    ref.upload_pairs(new_off, new_cell, old_xy, old_idx)
+    ref.project(3, dofs, download=False)
+    r = ref.adapt_step(s, 3).asdict()
+    for k in ("n_invalid", "n_orient_nonpos", "n_illegal", "n_refine", "n_coarsen", "n_pieces", "max_dist"):
+        if got[k] != r[k]:
+            ok = False; print("MISMATCH", k, got[k], r[k])
+    for k in ("mass_new", "covered_area"):
+        if abs(got[k] - r[k]) > 1e-13 * abs(r[k]):
+            ok = False; print("MISMATCH", k, got[k], r[k])
+    print("mgpu_check world", world, "cells", m.nc, "OK" if ok else "FAILED", got)
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, 0)
+ctx.close()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
