@@ -786,7 +786,7 @@ template <int NCOMP, int LPC, int MINB>
 __global__ void __launch_bounds__(PROJ_THREADS, MINB)
 k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1,
           const int32_t* __restrict__ cv2, const uint8_t* __restrict__ perm, const long long* __restrict__ new_off,
-          const int32_t* __restrict__ new_cell, int64_t nnew, const double* __restrict__ old_xy,
+          const int32_t* __restrict__ new_cell, int64_t i_begin, int64_t nnew, const double* __restrict__ old_xy,
           const int32_t* __restrict__ old_idx, const double* __restrict__ dofs_old, double* __restrict__ dofs_new,
           DevParams prm, double* __restrict__ part_mass, double* __restrict__ part_cov, Counters* __restrict__ cnt) {
   __shared__ double2 sA[4][PROJ_THREADS];
@@ -794,7 +794,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
   __shared__ double2 sC[9][PROJ_THREADS];
   const int tid = threadIdx.x;
   const int64_t gid = (int64_t)blockIdx.x * PROJ_THREADS + tid;
-  const int64_t i = gid / LPC;
+  const int64_t i = i_begin + gid / LPC;           // new cells [i_begin, nnew) of the pair CSR
   const int q = (int)(gid % LPC);
   const int lane = tid & 31, lead = lane - q;
   const bool live = i < nnew;

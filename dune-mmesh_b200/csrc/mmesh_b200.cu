@@ -61,6 +61,8 @@ struct mmb_context {
   int64_t nnew = 0, npairs = 0, n_old = 0;
   DBuf<long long> new_off; DBuf<int32_t> new_cell, old_idx; DBuf<double> old_xy, dofs_old, dofs_new, part_a, part_b, pair_vol;
   int dofs_ncomp = 0;
+  std::vector<int64_t> chunk_i; std::vector<int32_t> chunk_cell_lo, chunk_cell_hi; bool chunks_ok = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr; std::vector<cudaEvent_t> pipe_ev;
   // 3-D trace
   DBuf<int32_t> tr_in, tr_out; DBuf<double> tr_u, tr_ug, tr_a, tr_b, tr_c;
   // misc
@@ -160,6 +162,9 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->tr_a.release(); ctx->tr_b.release(); ctx->tr_c.release(); ctx->pred_pts.release(); ctx->pred_sign.release();
   ctx->halo_send_idx.release(); ctx->halo_recv_idx.release(); ctx->halo_send.release(); ctx->halo_recv.release(); ctx->reduce_vec.release();
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+  for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return MMB_OK;
@@ -566,7 +571,7 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
           MMB_ERR_INVALID_ARG, "mmb_upload_pairs: null arrays");
   CK(ctx->new_off.ensure(nnew + 1)); CK(ctx->new_cell.ensure(nnew + 1)); CK(ctx->old_idx.ensure(npairs + 1));
   CK(ctx->old_xy.ensure(6 * (size_t)npairs + 1)); CK(ctx->pair_vol.ensure(npairs + 1));
-  const int nb = (int)grid_for(4 * nnew, PROJ_THREADS);
+  const int nb = (int)grid_for(4 * nnew, PROJ_THREADS) + 64;   // + slack for chunked launches
   CK(ctx->part_a.ensure(nb)); CK(ctx->part_b.ensure(nb));
   if (nnew) {
     CK(cudaMemcpyAsync(ctx->new_off.p, new_off_host, (size_t)(nnew + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -578,31 +583,50 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
   }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->nnew = nnew; ctx->npairs = npairs;
+  // chunk table for the pipelined host-buffer step: new cells are listed in ascending cell order (element iteration
+  // order, mmesh.hh:1143), so chunk k of the CSR writes DOFs of cells [cell_lo[k], cell_hi[k]]
+  ctx->chunk_i.clear(); ctx->chunk_cell_lo.clear(); ctx->chunk_cell_hi.clear();
+  const int C = nnew >= (1 << 16) ? 8 : 1;
+  bool ascending = true;
+  for (int64_t i = 1; i < nnew && ascending; ++i) ascending = new_cell_host[i] > new_cell_host[i - 1];
+  ctx->chunks_ok = ascending && nnew > 0;
+  for (int k = 0; k <= C; ++k) ctx->chunk_i.push_back(nnew * k / C);
+  for (int k = 0; k < C && nnew > 0; ++k) {
+    ctx->chunk_cell_lo.push_back(new_cell_host[ctx->chunk_i[k]]);
+    ctx->chunk_cell_hi.push_back(new_cell_host[ctx->chunk_i[k + 1] - 1]);
+  }
   return MMB_OK;
 }
 #define PROJ_ARGS (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p, ctx->new_off.p, ctx->new_cell.p, \
-                  ctx->nnew, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp, ctx->part_a.p, ctx->part_b.p, ctx->counters.p
+                  i0, i1, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp, ctx->part_a.p + pb0, ctx->part_b.p + pb0, ctx->counters.p
 static int proj_variant() { static int v = -1; if (v < 0) { const char* e = getenv("MMB_PROJ_VARIANT"); v = e ? atoi(e) : 0; } return v; }
-static int do_project(mmb_context* ctx, int ncomp) {
-  if (ctx->nnew == 0) return MMB_OK;
+// projection of the new cells [i0, i1) of the pair CSR; per-block partial sums go to part_[pb0 ...); returns #blocks
+static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, int pb0, int* nblocks) {
   const DevParams dp = dev_params(ctx->prm);
   unsigned nb;
   if (ncomp == 1) {
-    nb = grid_for(ctx->nnew, PROJ_THREADS);
-    LAUNCH("project_p0", (k_project<1, 1, 1>), nb, PROJ_THREADS, PROJ_ARGS);
+    nb = grid_for(i1 - i0, PROJ_THREADS);
+    LAUNCH("project_p0", (k_project<1, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS);
   } else {
     const int var = proj_variant();
     const int lpc = (var == 1 || var == 4) ? 4 : 1;
-    nb = grid_for(lpc * ctx->nnew, PROJ_THREADS);
+    nb = grid_for(lpc * (i1 - i0), PROJ_THREADS);
     switch (var) {
       case 1: LAUNCH("project_p1", (k_project<3, 4, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      case 2: LAUNCH("project_p1", (k_project<3, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 3: LAUNCH("project_p1", (k_project<3, 1, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 4: LAUNCH("project_p1", (k_project<3, 4, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      default: LAUNCH("project_p1", (k_project<3, 1, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 5: LAUNCH("project_p1", (k_project<3, 1, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      default: LAUNCH("project_p1", (k_project<3, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
     }
   }
-  LAUNCH("reduce_partials", k_reduce_partials, 1, 1024, ctx->part_a.p, ctx->part_b.p, (int)nb, ctx->counters.p);
+  *nblocks = (int)nb;
+  return MMB_OK;
+}
+static int do_project(mmb_context* ctx, int ncomp) {
+  if (ctx->nnew == 0) return MMB_OK;
+  int nb = 0;
+  TRY(project_range(ctx, ncomp, 0, ctx->nnew, 0, &nb));
+  LAUNCH("reduce_partials", k_reduce_partials, 1, 1024, ctx->part_a.p, ctx->part_b.p, nb, ctx->counters.p);
   return MMB_OK;
 }
 static int stage_dofs(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_old_host) {
@@ -687,20 +711,92 @@ int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_s
   TRY(step_core(ctx, shifts_host, ncomp, 0, nullptr));
   return step_result(ctx, res);
 }
+// Host-buffer step, pipelined over three streams: the H2D of the shifts overlaps Distance::update + marks, the H2D of
+// the old DOFs overlaps the validity pass, the projection runs in chunks whose new DOFs stream back while the next
+// chunk is computed, and the flag arrays return behind the kernels that produced them.  (Pinned host buffers are
+// needed for real overlap; pageable ones still work, serialised by the driver.)
 int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host,
                         double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host, uint8_t* valid_fp_host,
                         int8_t* orient_sign_host, uint8_t* edge_flags_host, mmb_step_result* res) {
   if (!ctx) return MMB_ERR_INVALID_ARG;
-  TRY(step_core(ctx, shifts_host, ncomp, n_old, dofs_old_host));
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  REQUIRE(ncomp == 0 || ctx->dim == 2, MMB_ERR_INVALID_ARG, "projection is 2-D only (geometryInFather, entity.hh:573-594)");
+  REQUIRE(ncomp == 0 || ncomp == 1 || ncomp == 3, MMB_ERR_INVALID_ARG, "ncomp must be 0, 1 (P0) or 3 (DG-P1)");
+  REQUIRE(shifts_host || ctx->has_shift, MMB_ERR_STATE, "shifts == NULL but no resident shifts");
+  if (!ctx->s_h2d) { CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)); }
+  while (ctx->pipe_ev.size() < 24) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->pipe_ev.push_back(e); }
+  cudaStream_t S0 = ctx->stream, S1 = ctx->s_h2d, S2 = ctx->s_d2h;
+  cudaEvent_t* ev = ctx->pipe_ev.data();
   const size_t nc = (size_t)ctx->nc;
-  if (marks_host) CK(cudaMemcpyAsync(marks_host, ctx->mark.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
-  if (longest_edge_host) CK(cudaMemcpyAsync(longest_edge_host, ctx->longest.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
-  if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
-  if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
-  if (edge_flags_host && ctx->ne) CK(cudaMemcpyAsync(edge_flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, ctx->stream));
-  if (dofs_new_host && ncomp) CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // buffers must exist before any asynchronous copy targets them
+  if (ncomp) {
+    if (dofs_old_host) { REQUIRE(n_old > 0, MMB_ERR_INVALID_ARG, "n_old must be positive"); CK(ctx->dofs_old.ensure((size_t)n_old * ncomp)); }
+    else REQUIRE(ctx->dofs_ncomp == ncomp, MMB_ERR_STATE, "dofs_old == NULL but no resident DOFs of this ncomp");
+    if (ctx->dofs_new.cap < nc * ncomp) { CK(ctx->dofs_new.ensure(nc * ncomp)); CK(cudaMemsetAsync(ctx->dofs_new.p, 0, nc * ncomp * sizeof(double), S0)); }
+  }
+  CK(cudaEventRecord(ev[0], S0));                                  // everything issued so far (previous step) is ordered first
+  CK(cudaStreamWaitEvent(S1, ev[0], 0)); CK(cudaStreamWaitEvent(S2, ev[0], 0));
+  // S1: inputs
+  if (shifts_host) CK(cudaMemcpyAsync(ctx->shift.p, shifts_host, (size_t)ctx->nv * ctx->dim * sizeof(double), cudaMemcpyHostToDevice, S1));
+  ctx->has_shift = true;
+  CK(cudaEventRecord(ev[1], S1));
+  if (ncomp && dofs_old_host) {
+    CK(cudaMemcpyAsync(ctx->dofs_old.p, dofs_old_host, (size_t)n_old * ncomp * sizeof(double), cudaMemcpyHostToDevice, S1));
+    ctx->n_old = n_old; ctx->dofs_ncomp = ncomp;
+  }
+  CK(cudaEventRecord(ev[2], S1));
+  // S0: markElements needs neither shifts nor DOFs
+  TRY(zero_counters(ctx));
+  TRY(do_distance(ctx));
+  TRY(do_mark(ctx));
+  if (ctx->dim == 2 && ctx->ns)
+    LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
+           (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
+  CK(cudaEventRecord(ev[3], S0));
+  CK(cudaStreamWaitEvent(S2, ev[3], 0));
+  if (marks_host) CK(cudaMemcpyAsync(marks_host, ctx->mark.p, nc, cudaMemcpyDeviceToHost, S2));
+  if (longest_edge_host) CK(cudaMemcpyAsync(longest_edge_host, ctx->longest.p, nc, cudaMemcpyDeviceToHost, S2));
+  CK(cudaStreamWaitEvent(S0, ev[1], 0));                           // shifts have landed
+  TRY(do_validate(ctx, true));
+  CK(cudaEventRecord(ev[4], S0));
+  CK(cudaStreamWaitEvent(S2, ev[4], 0));
+  if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, nc, cudaMemcpyDeviceToHost, S2));
+  if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, nc, cudaMemcpyDeviceToHost, S2));
+  if (ncomp && ctx->nnew) {
+    CK(cudaStreamWaitEvent(S0, ev[2], 0));                         // old DOFs have landed
+    const bool chunked = ctx->chunks_ok && dofs_new_host;
+    const int C = chunked ? (int)ctx->chunk_cell_lo.size() : 1;
+    int pb = 0;
+    for (int k = 0; k < C; ++k) {
+      const int64_t i0 = chunked ? ctx->chunk_i[k] : 0, i1 = chunked ? ctx->chunk_i[k + 1] : ctx->nnew;
+      int nb = 0;
+      TRY(project_range(ctx, ncomp, i0, i1, pb, &nb));
+      pb += nb;
+      if (dofs_new_host) {
+        CK(cudaEventRecord(ev[8 + k], S0));
+        CK(cudaStreamWaitEvent(S2, ev[8 + k], 0));
+        // chunk k owns cells (hi of chunk k-1, hi of chunk k]; cells outside the projected set keep their old values
+        const size_t lo = chunked ? (k == 0 ? 0 : (size_t)ctx->chunk_cell_hi[k - 1] + 1) : 0;
+        const size_t hi = chunked ? (k == C - 1 ? nc : (size_t)ctx->chunk_cell_hi[k] + 1) : nc;
+        if (hi > lo)
+          CK(cudaMemcpyAsync(dofs_new_host + lo * ncomp, ctx->dofs_new.p + lo * ncomp, (hi - lo) * ncomp * sizeof(double), cudaMemcpyDeviceToHost, S2));
+      }
+    }
+    LAUNCH("reduce_partials", k_reduce_partials, 1, 1024, ctx->part_a.p, ctx->part_b.p, pb, ctx->counters.p);
+  } else if (ncomp && dofs_new_host) {
+    CK(cudaStreamWaitEvent(S2, ev[4], 0));
+    CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, S2));
+  }
+  TRY(do_move(ctx));
+  if (ctx->dim == 2) TRY(do_legality(ctx));
+  CK(cudaEventRecord(ev[5], S0));
+  CK(cudaStreamWaitEvent(S2, ev[5], 0));
+  if (edge_flags_host && ctx->ne) CK(cudaMemcpyAsync(edge_flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, S2));
+  CK(cudaEventRecord(ev[6], S2));
+  CK(cudaStreamWaitEvent(S0, ev[6], 0));                           // the step is complete on S0 only when all copies are
+  CK(cudaGetLastError());
   if (res) return step_result(ctx, res);
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(S0));
   return MMB_OK;
 }
 

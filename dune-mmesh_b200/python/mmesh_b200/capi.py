@@ -259,6 +259,21 @@ class Context:
         self._ck(rc)
         return res
 
+    def adapt_step_host(self, shifts, ncomp, dofs_old):
+        """The per-step drop-in call with host buffers for every field (mmb_adapt_step_host)."""
+        s, d = _f64(shifts), _f64(dofs_old)
+        out = dict(marks=np.empty(self.nc, np.int8), longest=np.empty(self.nc, np.uint8), valid_fp=np.empty(self.nc, np.uint8),
+                   orient_sign=np.empty(self.nc, np.int8), edge_flags=np.empty(self.ne, np.uint8),
+                   dofs_new=np.zeros(self.nc * max(ncomp, 1), np.float64))
+        res = StepResult()
+        self._ck(lib().mmb_adapt_step_host(self._h, _p(s), C.c_int(ncomp), C.c_int64(0 if d is None else d.size // max(ncomp, 1)), _p(d),
+                                           _p(out["dofs_new"]) if ncomp else None, _p(out["marks"]), _p(out["longest"]),
+                                           _p(out["valid_fp"]), _p(out["orient_sign"]), _p(out["edge_flags"]), C.byref(res)))
+        if ncomp > 1:
+            out["dofs_new"] = out["dofs_new"].reshape(self.nc, ncomp)
+        out["result"] = res
+        return out
+
     def trace_skeleton_p0(self, inside, outside, u_bulk, u_gamma):
         inside, outside, u_bulk, u_gamma = _i32(inside), _i32(outside), _f64(u_bulk), _f64(u_gamma)
         nf = inside.shape[0]

@@ -317,3 +317,37 @@ def test_adapt_step_composition(gpu_ctx_factory, oracle):
     assert abs(res.mass_new - rmass) <= 1e-13 * abs(rmass) and abs(res.covered_area - rcov) <= 1e-13 * rcov
     assert np.array_equal(ctx.download_coords(), moved)
     assert ctx.launch_count > 0
+
+
+def test_adapt_step_host_buffers(gpu_ctx_factory, oracle):
+    """mmb_adapt_step_host (pipelined copies, chunked projection) returns the same fields as the separate calls."""
+    from mmesh_b200 import synth
+    for n in (80, 200):                                   # 200: > 2^16 new cells => the chunked projection path
+        m = _mesh1(n)
+        s = synth.shifts_uniform(m, 0.3 * m.h, 30)
+        new_off, new_cell, old_xy, old_idx = synth.pairs_self_and_neighbours(m, m.xy - s)
+        ctx = gpu_ctx_factory(2)
+        _upload(ctx, m)
+        prm = ctx.indicator_init()
+        prm.drop_area = 1e-12
+        ctx.set_params(prm)
+        ctx.upload_pairs(new_off, new_cell, old_xy, old_idx)
+        rng = np.random.default_rng(5)
+        oprm = oracle.Params.from_buffer_copy(bytes(prm))
+        rd = oracle.distance_2d(m.xy, m.segs)
+        rm, rle, rc = oracle.mark(m.xy, rd, m.cells, m.perm, oprm, oracle.distance_max(rd))
+        rv, rs, rn = oracle.trial_validate(m.xy, s, m.cells)
+        rf, rnill = oracle.legality(oracle.move(m.xy, s), None, m.edges)
+        for ncomp in (3, 1):
+            ctx.upload_coords(m.xy)
+            dofs = rng.uniform(size=(m.nc, ncomp)) if ncomp == 3 else rng.uniform(size=m.nc)
+            out = ctx.adapt_step_host(s, ncomp, dofs)
+            ref, rmass, rcov, rnpc = oracle.project(m.xy, m.cells, m.perm, new_off, new_cell, old_xy, old_idx, dofs, m.nc, ncomp, oprm)
+            assert np.array_equal(out["marks"], rm) and np.array_equal(out["longest"], rle)
+            assert np.array_equal(out["valid_fp"], rv) and np.array_equal(out["orient_sign"], rs)
+            assert np.array_equal(out["edge_flags"], rf)
+            assert np.max(np.abs(out["dofs_new"] - ref)) <= 1e-12 * np.max(np.abs(ref))
+            r = out["result"]
+            assert (r.n_refine, r.n_coarsen) == tuple(rc) and r.n_invalid == rn and r.n_illegal == rnill and r.n_pieces == rnpc
+            assert abs(r.mass_new - rmass) <= 1e-13 * abs(rmass) and abs(r.covered_area - rcov) <= 1e-13 * rcov
+            assert np.array_equal(ctx.download_coords(), oracle.move(m.xy, s))
