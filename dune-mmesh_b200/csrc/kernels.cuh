@@ -714,7 +714,7 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 
 // ---- shared-memory Sutherland-Hodgman, organised in convergent passes ------------------------------------------
 // lineIntersectionPoint, polygoncutting.hh:100-114 (iQ = q1 - q2, fq = q1 x q2 hoisted per clip edge)
-__device__ __forceinline__ double2 line_isect(double ax, double ay, double bx, double by, double iQx, double iQy, double fq) {
+__device__ __noinline__ double2 line_isect(double ax, double ay, double bx, double by, double iQx, double iQy, double fq) {
   double dPx = ax - bx, dPy = ay - by;
   const double scale = dPx * iQy - iQx * dPy;
   const double fp = ax * by - ay * bx;
@@ -789,9 +789,8 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
           const int32_t* __restrict__ new_cell, int64_t i_begin, int64_t nnew, const double* __restrict__ old_xy,
           const int32_t* __restrict__ old_idx, const double* __restrict__ dofs_old, double* __restrict__ dofs_new,
           DevParams prm, double* __restrict__ part_mass, double* __restrict__ part_cov, Counters* __restrict__ cnt) {
-  __shared__ double2 sA[4][PROJ_THREADS];
-  __shared__ double2 sB[6][PROJ_THREADS];
-  __shared__ double2 sC[9][PROJ_THREADS];
+  __shared__ double2 sP[6][PROJ_THREADS];      // subject triangle, then output of clip edge 1 (<= 6)
+  __shared__ double2 sQ[9][PROJ_THREADS];      // outputs of clip edges 0 (<= 4) and 2 (<= 9)
   const int tid = threadIdx.x;
   const int64_t gid = (int64_t)blockIdx.x * PROJ_THREADS + tid;
   const int64_t i = i_begin + gid / LPC;           // new cells [i_begin, nnew) of the pair CSR
@@ -853,17 +852,22 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
       const double od = (cy[1] - cy[0]) * (cx[2] - cx[1]) - (cx[1] - cx[0]) * (cy[2] - cy[1]);
       const int o = (fabs(od) < 2147483648.0) ? (int)od : 0;
       const bool sw = o > 0;
-      sB[0][tid] = make_double2(cx[0], cy[0]);
-      sB[1][tid] = sw ? make_double2(cx[2], cy[2]) : make_double2(cx[1], cy[1]);
-      sB[2][tid] = sw ? make_double2(cx[1], cy[1]) : make_double2(cx[2], cy[2]);
-      auto ldA = [&](int k, double& x, double& y) { const double2 v = sA[k][tid]; x = v.x; y = v.y; };
-      auto ldB = [&](int k, double& x, double& y) { const double2 v = sB[k][tid]; x = v.x; y = v.y; };
-      auto stA = [&](int k, double x, double y) { sA[k][tid] = make_double2(x, y); };
-      auto stB = [&](int k, double x, double y) { sB[k][tid] = make_double2(x, y); };
-      auto stC = [&](int k, double x, double y) { sC[k][tid] = make_double2(x, y); };
-      const int nA = clip_stage<3>(ldB, 3, ex[0], ey[0], ex[1], ey[1], prm.clip_eps, stA);
-      const int nB = clip_stage<4>(ldA, nA, ex[1], ey[1], ex[2], ey[2], prm.clip_eps, stB);
-      const int nC = clip_stage<6>(ldB, nB, ex[2], ey[2], ex[0], ey[0], prm.clip_eps, stC);
+      sP[0][tid] = make_double2(cx[0], cy[0]);
+      sP[1][tid] = sw ? make_double2(cx[2], cy[2]) : make_double2(cx[1], cy[1]);
+      sP[2][tid] = sw ? make_double2(cx[1], cy[1]) : make_double2(cx[2], cy[2]);
+      int nC = 3;
+#pragma unroll 1
+      for (int st = 0; st < 3; ++st) {                      // one code instance for the three clip edges
+        const double2* in = (st == 1) ? &sQ[0][tid] : &sP[0][tid];
+        double2* out = (st == 1) ? &sP[0][tid] : &sQ[0][tid];
+        const int a = st, b = st == 2 ? 0 : st + 1;
+        const double q1x = a == 0 ? ex[0] : (a == 1 ? ex[1] : ex[2]), q1y = a == 0 ? ey[0] : (a == 1 ? ey[1] : ey[2]);
+        const double q2x = b == 0 ? ex[0] : (b == 1 ? ex[1] : ex[2]), q2y = b == 0 ? ey[0] : (b == 1 ? ey[1] : ey[2]);
+        nC = clip_stage<6>([&](int k, double& x, double& y) { const double2 v = in[k * PROJ_THREADS]; x = v.x; y = v.y; },
+                           nC, q1x, q1y, q2x, q2y, prm.clip_eps,
+                           [&](int k, double x, double y) { out[k * PROJ_THREADS] = make_double2(x, y); });
+      }
+      auto& sC = sQ;
       // fan (points[0], points[j-1], points[j]), cutsettriangulation.hh:57-61
       double fx = 0, fy = 0, fu = 0, ff1 = 0, ff2 = 0, px = 0, py = 0, pu = 0, pf1 = 0, pf2 = 0;
       for (int j = 0; j < nC; ++j) {
