@@ -213,11 +213,12 @@ def main():
         ctx.adapt_step(None, ncomp=ncomp, want_result=False)
         ctx.scale_shifts(-1.0)                              # next step moves back: the mesh stays in place on average
 
-    for _ in range(args.warmup):
+    for _ in range(args.warmup + (args.warmup & 1)):         # even count: the mesh is back at its start position
         step_resident()
     ctx.synchronize()
     res_check = ctx.adapt_step(None, ncomp=ncomp, want_result=True)
     ctx.scale_shifts(-1.0)
+    step_resident()
     ctx.synchronize()
 
     # ---- timed region: K resident steps, CUDA events on the launching stream, per-kernel events inside ----

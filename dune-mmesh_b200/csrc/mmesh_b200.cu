@@ -839,6 +839,29 @@ int mmb_predicate_batch(mmb_context* ctx, int which, int64_t n, const double* pt
   return MMB_OK;
 }
 
+// asynchronous field transfers on the context's stream (host buffers should be pinned); mmb_synchronize completes them
+int mmb_upload_dofs(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_old_host) {
+  if (!ctx || !dofs_old_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  return stage_dofs(ctx, ncomp, n_old, dofs_old_host);
+}
+int mmb_download_fields(mmb_context* ctx, int ncomp, double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host,
+                        uint8_t* valid_fp_host, int8_t* orient_sign_host, uint8_t* edge_flags_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  const size_t nc = (size_t)ctx->nc;
+  if (marks_host) CK(cudaMemcpyAsync(marks_host, ctx->mark.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (longest_edge_host) CK(cudaMemcpyAsync(longest_edge_host, ctx->longest.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (edge_flags_host && ctx->ne) CK(cudaMemcpyAsync(edge_flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dofs_new_host && ncomp) {
+    REQUIRE(ctx->dofs_new.cap >= nc * ncomp, MMB_ERR_STATE, "no projected DOFs of this ncomp");
+    CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return MMB_OK;
+}
+
 // ---- multi-GPU plumbing: ownership, halo pack/unpack, phased step ------------------------------------------------
 int mmb_set_owned_cells(mmb_context* ctx, int64_t lo, int64_t hi) {
   if (!ctx) return MMB_ERR_INVALID_ARG;

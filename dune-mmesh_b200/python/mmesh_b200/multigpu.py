@@ -134,13 +134,17 @@ def bench_main(args, world, rank, local_rank, METRIC, UNIT, algorithmic_bytes, C
         sm.step(ncomp)
         ctx.scale_shifts(-1.0)
 
-    for _ in range(args.warmup):
+    for _ in range(args.warmup + (args.warmup & 1)):        # even count: the mesh is back at its start position
         step()
     torch.cuda.synchronize()
-    res_check = sm.result()
+    step()
+    torch.cuda.synchronize()
+    res_check = sm.result()                                  # same phase as the single-GPU `check`
+    step()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        time.sleep(0.3)
     ctx.timing_enable(True)
     ctx.timing_reset()
     l0 = ctx.launch_count
@@ -161,6 +165,48 @@ def bench_main(args, world, rank, local_rank, METRIC, UNIT, algorithmic_bytes, C
     ctx.timing_enable(False)
     ctx.timing_reset()
     clk = clocks.stop() if rank == 0 else None
+    # ---- e2e: per-rank HOST buffers (pinned); copies, halo exchange and collectives inside the timed region ----
+    import ctypes
+    L = capi.lib()
+    lnv, lnc, lne = shard.xy.shape[0], shard.cells.shape[0], shard.edges.shape[0]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    sh_h = [pin(s_local), pin(-s_local)]
+    dofs_in = pin(w["dofs"][shard.lcells])
+    dofs_out = torch.empty((lnc, ncomp), dtype=torch.float64).pin_memory()
+    marks_h = torch.empty(lnc, dtype=torch.int8).pin_memory()
+    longest_h = torch.empty(lnc, dtype=torch.uint8).pin_memory()
+    valid_h = torch.empty(lnc, dtype=torch.uint8).pin_memory()
+    orient_h = torch.empty(lnc, dtype=torch.int8).pin_memory()
+    eflag_h = torch.empty(max(lne, 1), dtype=torch.uint8).pin_memory()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def step_e2e(i):
+        ctx._ck(L.mmb_upload_shifts(ctx._h, P(sh_h[i & 1])))
+        ctx._ck(L.mmb_upload_dofs(ctx._h, ctypes.c_int(ncomp), ctypes.c_int64(lnc), P(dofs_in)))
+        sm.step(ncomp)
+        ctx._ck(L.mmb_download_fields(ctx._h, ctypes.c_int(ncomp), P(dofs_out), P(marks_h), P(longest_h), P(valid_h), P(orient_h), P(eflag_h)))
+        vec_h = sm.vec.cpu()                                  # the step's scalars (synchronises the stream)
+        return vec_h
+
+    for i in range(2):
+        step_e2e(i)
+    ke = max(2, min(args.steps, 10)) // 2 * 2
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(ke):
+        step_e2e(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / ke], device="cuda", dtype=torch.float64)
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    io = torch.tensor([lnv * 16 + lnc * ncomp * 8, lnc * ncomp * 8 + 4 * lnc + lne + 128], device="cuda", dtype=torch.float64)
+    dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    e2e = {"value": m.nc / (float(e2e_ms.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(e2e_ms.item()),
+           "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()), "steps": ke,
+           "note": "per rank: owned shifts + old DG-P1 DOFs in (pinned host), halo exchange + 2 all-reduces, marks/flags/new DOFs/scalars out; bytes summed over ranks"}
     halo = torch.tensor([shard.recv_idx.shape[0], shard.lcells.shape[0] - (shard.c1 - shard.c0), shard.lverts.shape[0]],
                         device="cuda", dtype=torch.float64)
     dist.all_reduce(halo, op=dist.ReduceOp.MAX)
@@ -195,7 +241,7 @@ def bench_main(args, world, rank, local_rank, METRIC, UNIT, algorithmic_bytes, C
                 "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                              "frac": dom["frac"], "traffic": None, "scope": "rank 0 shard"},
                 "cpu_baseline": None,
-                "e2e": None, "gpu_launches": int(launches), "clocks": clk, "kernels": kern, "check": res_check,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "kernels": kern, "check": res_check,
                 "setup_s": w["gen_s"], "partition_s": part_s}
         print(json.dumps(line), flush=True)
     ctx.close()

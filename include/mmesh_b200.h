@@ -143,6 +143,12 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
                         double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host, uint8_t* valid_fp_host,
                         int8_t* orient_sign_host, uint8_t* edge_flags_host, mmb_step_result* res);
 
+/* Asynchronous field transfers on the context's stream (pinned host buffers; complete after mmb_synchronize).
+   Used by the sharded step, where collectives sit between the phases. */
+int mmb_upload_dofs(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_old_host);
+int mmb_download_fields(mmb_context* ctx, int ncomp, double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host,
+                        uint8_t* valid_fp_host, int8_t* orient_sign_host, uint8_t* edge_flags_host);
+
 /* ---- multi-GPU plumbing (one context per rank; the collectives themselves are issued by the host, e.g.
    torch.distributed / NCCL, on the buffers exposed by mmb_device_buffer) ------------------------------------------
    The mesh is sharded by contiguous Hilbert ranges of cells (the reference's own scheme is contiguous ranges of the
