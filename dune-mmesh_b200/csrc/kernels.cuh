@@ -90,6 +90,37 @@ __global__ void __launch_bounds__(256) k_scale(double2* __restrict__ s, double a
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Hilbert tiles.  Cells (and edges) arrive in the host's Hilbert order, so the vertices referenced by a tile of
+// TILE consecutive cells cluster in a short index window (98 % inside a TILE-wide window on the 16.8 M benchmark
+// mesh).  Each CTA stages that window in shared memory with coalesced 16-byte loads and gathers from there;
+// references outside the window fall back to a global (L2) load.  The window start is fixed at upload time:
+// median of a 256-index sample of the tile, minus half a window.
+// ------------------------------------------------------------------------------------------------------
+constexpr int TILE = 1024;          // cells (or edges) per CTA = 256 threads x 4
+constexpr int WIN = 1024;           // staged vertices per CTA
+__global__ void __launch_bounds__(256)
+k_tile_windows(const int32_t* __restrict__ first_index, int stride, int64_t n_items, int64_t nv, int32_t* __restrict__ tile_lo) {
+  __shared__ int sv[256];
+  const int64_t base = (int64_t)blockIdx.x * TILE;
+  const int64_t item = base + 4 * (int64_t)threadIdx.x;            // one sample per thread
+  const int a = item < n_items ? first_index[item * stride] : -1;
+  sv[threadIdx.x] = a;
+  __syncthreads();
+  int valid = 0, rank = 0;
+  for (int j = 0; j < 256; ++j) {
+    const int b = sv[j];
+    valid += (b >= 0);
+    rank += (b >= 0) && (b < a || (b == a && j < (int)threadIdx.x));
+  }
+  if (a >= 0 && rank == valid / 2) {
+    long long lo = (long long)a - WIN / 2;
+    if (lo > nv - WIN) lo = nv - WIN;
+    if (lo < 0) lo = 0;
+    tile_lo[blockIdx.x] = (int32_t)lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // K1  trial move + validity, 2-D.  mmesh.hh:1094-1134 (ensureVertexMovement): signedVolume_ <= 0.0 on
 //     x (+) s in TDS vertex order (mmesh.hh:1169-1172 -> CGAL/Cartesian/function_objects.h:918-926), plus the
 //     exact CGAL orientation sign (static filter here, worklist for the fallback kernel).
@@ -97,32 +128,40 @@ __global__ void __launch_bounds__(256) k_scale(double2* __restrict__ s, double a
 template <bool SHIFT>
 __global__ void __launch_bounds__(256)
 k_validate2d(const double2* __restrict__ xy, const double2* __restrict__ sh, const int4* __restrict__ cv0,
-             const int4* __restrict__ cv1, const int4* __restrict__ cv2, int64_t nc4, int64_t nc, int64_t own_lo,
-             int64_t own_hi, uint32_t* __restrict__ valid4, uint32_t* __restrict__ orient4, int32_t* __restrict__ wl,
-             Counters* __restrict__ cnt) {
+             const int4* __restrict__ cv1, const int4* __restrict__ cv2, const int32_t* __restrict__ tile_lo, int64_t nv,
+             int64_t nc4, int64_t nc, int64_t own_lo, int64_t own_hi, uint32_t* __restrict__ valid4,
+             uint32_t* __restrict__ orient4, int32_t* __restrict__ wl, Counters* __restrict__ cnt) {
+  __shared__ double2 sxy[WIN];                              // trial coordinates x (+) s of the tile's vertex window
+  const int lo = tile_lo[blockIdx.x];
+#pragma unroll
+  for (int j = threadIdx.x; j < WIN; j += 256) {
+    const int v = lo + j;
+    if (v < nv) {
+      double2 p = ldg2(xy + v);
+      if (SHIFT) { const double2 q = ldg2(sh + v); p.x = p.x + q.x; p.y = p.y + q.y; }   // mmesh.hh:1427 point = center() + shift
+      sxy[j] = p;
+    }
+  }
+  __syncthreads();
+  auto fetch = [&](int v) -> double2 {
+    const unsigned j = (unsigned)(v - lo);
+    if (j < (unsigned)WIN) return sxy[j];
+    double2 p = ldg2(xy + v);
+    if (SHIFT) { const double2 q = ldg2(sh + v); p.x = p.x + q.x; p.y = p.y + q.y; }
+    return p;
+  };
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned ninv = 0, nnonpos = 0;
   bool need[4] = { false, false, false, false };
   if (g < nc4) {
     const int4 a = __ldg(cv0 + g), b = __ldg(cv1 + g), c = __ldg(cv2 + g);
     const int va[4] = { a.x, a.y, a.z, a.w }, vb[4] = { b.x, b.y, b.z, b.w }, vc[4] = { c.x, c.y, c.z, c.w };
-    double2 P[4], Q[4], R[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { P[j] = ldg2(xy + va[j]); Q[j] = ldg2(xy + vb[j]); R[j] = ldg2(xy + vc[j]); }
-    if (SHIFT) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double2 sp = ldg2(sh + va[j]), sq = ldg2(sh + vb[j]), sr = ldg2(sh + vc[j]);
-        P[j].x = P[j].x + sp.x; P[j].y = P[j].y + sp.y;     // mmesh.hh:1427 point = center() + shift
-        Q[j].x = Q[j].x + sq.x; Q[j].y = Q[j].y + sq.y;
-        R[j].x = R[j].x + sr.x; R[j].y = R[j].y + sr.y;
-      }
-    }
     uint32_t vbits = 0, obits = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      const double2 P = fetch(va[j]), Q = fetch(vb[j]), R = fetch(vc[j]);
       double det;
-      int s = orient2d_filter(P[j].x, P[j].y, Q[j].x, Q[j].y, R[j].x, R[j].y, det);
+      int s = orient2d_filter(P.x, P.y, Q.x, Q.y, R.x, R.y, det);
       const double area = det / 2;                           // Compute_area_2: determinant(...)/2
       const bool ok = !(area <= 0.0);                        // mmesh.hh:1102
       const bool live = 4 * g + j < nc;
@@ -173,28 +212,47 @@ k_exact_orient2d(const double2* __restrict__ xy, const double2* __restrict__ sh,
 template <bool SHIFT>
 __global__ void __launch_bounds__(256)
 k_legality(const double2* __restrict__ xy, const double2* __restrict__ sh, const int4* __restrict__ edges, int64_t ne,
-           uint8_t* __restrict__ flag, int32_t* __restrict__ wl, Counters* __restrict__ cnt) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned nill = 0;
-  bool need = false;
-  if (e < ne) {
-    const int4 q = __ldg(edges + e);
-    uint8_t f = 2;
-    if (q.w >= 0) {
-      double2 A = ldg2(xy + q.x), B = ldg2(xy + q.y), C = ldg2(xy + q.z), D = ldg2(xy + q.w);
-      if (SHIFT) {
-        const double2 sa = ldg2(sh + q.x), sb = ldg2(sh + q.y), sc = ldg2(sh + q.z), sd = ldg2(sh + q.w);
-        A.x = A.x + sa.x; A.y = A.y + sa.y; B.x = B.x + sb.x; B.y = B.y + sb.y;
-        C.x = C.x + sc.x; C.y = C.y + sc.y; D.x = D.x + sd.x; D.y = D.y + sd.y;
-      }
-      const int s = incircle_filter(A.x, A.y, B.x, B.y, C.x, C.y, D.x, D.y);
-      need = (s == SIGN_UNKNOWN);
-      f = (s > 0 && !need) ? 0 : 1;
-      nill += (f == 0);
+           const int32_t* __restrict__ tile_lo, int64_t nv, uint8_t* __restrict__ flag, int32_t* __restrict__ wl,
+           Counters* __restrict__ cnt) {
+  __shared__ double2 sxy[WIN];
+  const int lo = tile_lo[blockIdx.x];
+#pragma unroll
+  for (int j = threadIdx.x; j < WIN; j += 256) {
+    const int v = lo + j;
+    if (v < nv) {
+      double2 p = ldg2(xy + v);
+      if (SHIFT) { const double2 q = ldg2(sh + v); p.x = p.x + q.x; p.y = p.y + q.y; }
+      sxy[j] = p;
     }
-    flag[e] = f;
   }
-  wl_push(need, (int)e, wl, &cnt->wl_incircle);
+  __syncthreads();
+  auto fetch = [&](int v) -> double2 {
+    const unsigned j = (unsigned)(v - lo);
+    if (j < (unsigned)WIN) return sxy[j];
+    double2 p = ldg2(xy + v);
+    if (SHIFT) { const double2 q = ldg2(sh + v); p.x = p.x + q.x; p.y = p.y + q.y; }
+    return p;
+  };
+  unsigned nill = 0;
+  const int64_t e0 = (int64_t)blockIdx.x * TILE + threadIdx.x;       // edges e0, e0+256, e0+512, e0+768: coalesced int4 loads
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t e = e0 + 256 * r;
+    bool need = false;
+    if (e < ne) {
+      const int4 q = __ldg(edges + e);
+      uint8_t f = 2;
+      if (q.w >= 0) {
+        const double2 A = fetch(q.x), B = fetch(q.y), C = fetch(q.z), D = fetch(q.w);
+        const int s = incircle_filter(A.x, A.y, B.x, B.y, C.x, C.y, D.x, D.y);
+        need = (s == SIGN_UNKNOWN);
+        f = (s > 0 && !need) ? 0 : 1;
+        nill += (f == 0);
+      }
+      flag[e] = f;
+    }
+    wl_push(need, (int)e, wl, &cnt->wl_incircle);
+  }
   block_count_add<256>(nill, 0u, &cnt->n_illegal, &cnt->n_illegal);
 }
 template <bool SHIFT>

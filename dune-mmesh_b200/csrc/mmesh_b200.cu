@@ -51,6 +51,7 @@ struct mmb_context {
   DBuf<int4> edges;
   DBuf<int32_t> wl, list_out;
   DBuf<uint32_t> block_count;
+  DBuf<int32_t> tile_lo_cells, tile_lo_edges;
   DBuf<Counters> counters;
   bool has_shift = false, dist_valid = false, mesh_ok = false;
   // bvh
@@ -155,6 +156,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->perm.release(); ctx->valid_fp.release(); ctx->edge_flag.release(); ctx->longest.release();
   ctx->orient.release(); ctx->mark.release(); ctx->imark.release(); ctx->edges.release();
   ctx->wl.release(); ctx->list_out.release(); ctx->block_count.release(); ctx->counters.release();
+  ctx->tile_lo_cells.release(); ctx->tile_lo_edges.release();
   ctx->seg_leaf.release(); ctx->box2.release(); ctx->seg_hint.release(); ctx->ticket.release(); ctx->tri_leaf.release(); ctx->box3.release();
   ctx->new_off.release(); ctx->new_cell.release(); ctx->old_idx.release(); ctx->old_xy.release();
   ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
@@ -242,6 +244,13 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
   if (dim == 2) {
     CK(ctx->edges.ensure(ne + 1)); CK(ctx->edge_flag.ensure(ne + 4));
     if (ne) CK(cudaMemcpyAsync(ctx->edges.p, edges_host, (size_t)ne * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+    // Hilbert tile windows (see kernels.cuh): one per TILE cells / TILE edges
+    const int64_t ntc = (ctx->nc_pad + TILE - 1) / TILE, nte = (ne + TILE - 1) / TILE;
+    CK(ctx->tile_lo_cells.ensure(ntc + 1)); CK(ctx->tile_lo_edges.ensure(nte + 1));
+    CK(cudaMemsetAsync(ctx->tile_lo_cells.p, 0, (ntc + 1) * sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->tile_lo_edges.p, 0, (nte + 1) * sizeof(int32_t), ctx->stream));
+    if (nc) LAUNCH("tile_windows", k_tile_windows, (unsigned)ntc, 256, ctx->cv[0].p, 1, nc, nv, ctx->tile_lo_cells.p);
+    if (ne) LAUNCH("tile_windows", k_tile_windows, (unsigned)nte, 256, (const int32_t*)ctx->edges.p, 4, ne, nv, ctx->tile_lo_edges.p);
   }
   // interface facets: original order (marks) + Morton order (BVH leaves)
   CK(ctx->facets.ensure((size_t)ns * dim + 2)); CK(ctx->facets_sorted.ensure((size_t)ns * dim + 2)); CK(ctx->imark.ensure(ns + 4));
@@ -342,12 +351,12 @@ static int do_validate(mmb_context* ctx, bool with_shift) {
     const int64_t nc4 = ctx->nc_pad / 4;
     if (with_shift)
       LAUNCH("validate2d", k_validate2d<true>, grid_for(nc4, 256), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, nc4, ctx->nc, ctx->own_lo, ctx->own_hi,
-             (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
+             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, ctx->tile_lo_cells.p, ctx->nv, nc4, ctx->nc,
+             ctx->own_lo, ctx->own_hi, (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
     else
       LAUNCH("validate2d", k_validate2d<false>, grid_for(nc4, 256), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, nc4, ctx->nc, ctx->own_lo, ctx->own_hi,
-             (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
+             (const int4*)ctx->cv[0].p, (const int4*)ctx->cv[1].p, (const int4*)ctx->cv[2].p, ctx->tile_lo_cells.p, ctx->nv, nc4, ctx->nc,
+             ctx->own_lo, ctx->own_hi, (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
     if (with_shift)
       LAUNCH("exact_orient2d", k_exact_orient2d<true>, fb, 128, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
              ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->own_lo, ctx->own_hi, ctx->orient.p, c);
@@ -431,8 +440,8 @@ int mmb_marked_cells(mmb_context* ctx, int which, int32_t* cells_host, int64_t c
 // ---- legality -------------------------------------------------------------------------------------------
 static int do_legality(mmb_context* ctx) {
   if (ctx->ne == 0) return MMB_OK;
-  LAUNCH("legality", k_legality<false>, grid_for(ctx->ne, 256), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-         (const int4*)ctx->edges.p, ctx->ne, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p);
+  LAUNCH("legality", k_legality<false>, grid_for(ctx->ne, TILE), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
+         (const int4*)ctx->edges.p, ctx->ne, ctx->tile_lo_edges.p, ctx->nv, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p);
   LAUNCH("exact_incircle", k_exact_incircle<false>, ctx->num_sms * 4, 128, (const double2*)ctx->x.p,
          (const double2*)ctx->shift.p, (const int4*)ctx->edges.p, ctx->wl.p, ctx->edge_flag.p, ctx->counters.p);
   return MMB_OK;
