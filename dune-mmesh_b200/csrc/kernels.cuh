@@ -1237,6 +1237,43 @@ k_trace_skeleton(int64_t nf, const int32_t* __restrict__ inside, const int32_t* 
   skel[f] = __ldg(ug + f);
 }
 
+// MMeshInterfaceGrid::adapt(handle) with FV (P0) data, dune/mmesh/interface/grid.hh:388-415: the longer of (old, new)
+// is the father; old longer => prolongLocal copies the father value, else restrictLocal adds (|old|/|new|) * old.
+__global__ void __launch_bounds__(256)
+k_project_interface_p0(const double* __restrict__ new_len, const long long* __restrict__ new_off, int64_t nnew,
+                       const double* __restrict__ old_len, const int32_t* __restrict__ old_idx,
+                       const double* __restrict__ dofs_old, double* __restrict__ dofs_new) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnew) return;
+  bool initialize = true; double acc = 0.0;
+  const double ln = new_len[i];
+  for (long long p = new_off[i]; p < new_off[i + 1]; ++p) {
+    const double u = __ldg(dofs_old + old_idx[p]);
+    if (old_len[p] > ln) acc = u;
+    else { const double w = old_len[p] / ln; if (initialize) acc = w * u; else acc += w * u; }
+    initialize = false;
+  }
+  dofs_new[i] = acc;
+}
+// LongestEdgeRefinement::refinement (longestedgerefinement.hh:41-57): centre of the longest edge of the listed cells,
+// edge.geometry().center() = origin + 0.5 * (second - first) on the id-ordered corners (DUNE edge numbering)
+__global__ void __launch_bounds__(256)
+k_refinement_points(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1,
+                    const int32_t* __restrict__ cv2, const uint8_t* __restrict__ perm, const uint8_t* __restrict__ longest,
+                    const int32_t* __restrict__ cells, int64_t n, double2* __restrict__ out, int2* __restrict__ edge_vertices) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cells[i];
+  const int v[3] = { cv0[c], cv1[c], cv2[c] };
+  const unsigned p = perm[c];
+  const int k[3] = { v[p & 3], v[(p >> 2) & 3], v[(p >> 4) & 3] };
+  const int e = longest[c];
+  const int ia = e == 2 ? 1 : 0, ib = e == 0 ? 1 : 2;            // edges 0:(0,1) 1:(0,2) 2:(1,2)
+  const double2 a = ldg2(xy + k[ia]), b = ldg2(xy + k[ib]);
+  out[i] = make_double2(a.x + 0.5 * (b.x - a.x), a.y + 0.5 * (b.y - a.y));
+  if (edge_vertices) edge_vertices[i] = make_int2(k[ia], k[ib]);
+}
+
 // halo exchange helpers: owned values -> contiguous send buffer, received values -> halo slots
 __global__ void __launch_bounds__(256)
 k_gather2(const double2* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, double2* __restrict__ dst) {

@@ -680,6 +680,47 @@ int mmb_intersection_volumes(mmb_context* ctx, double* vol_host) {
   return MMB_OK;
 }
 
+int mmb_project_interface_p0(mmb_context* ctx, int64_t nnew, const double* new_len_host, const int64_t* new_off_host,
+                             int64_t npairs, const double* old_len_host, const int32_t* old_idx_host, int64_t n_old,
+                             const double* dofs_old_host, double* dofs_new_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(nnew > 0 && npairs >= 0 && n_old > 0 && new_len_host && new_off_host && dofs_old_host && dofs_new_host &&
+          (npairs == 0 || (old_len_host && old_idx_host)), MMB_ERR_INVALID_ARG, "mmb_project_interface_p0: bad arguments");
+  DBuf<double> nl, ol, dO, dN; DBuf<long long> off; DBuf<int32_t> oi;
+  auto fail = [&](cudaError_t e) { ctx->err = cudaGetErrorString(e); nl.release(); ol.release(); dO.release(); dN.release(); off.release(); oi.release(); return MMB_ERR_CUDA; };
+  cudaError_t e;
+  if ((e = nl.ensure(nnew)) || (e = ol.ensure(npairs + 1)) || (e = dO.ensure(n_old)) || (e = dN.ensure(nnew)) || (e = off.ensure(nnew + 1)) || (e = oi.ensure(npairs + 1))) return fail(e);
+  cudaMemcpyAsync(nl.p, new_len_host, nnew * 8, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(off.p, new_off_host, (nnew + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (npairs) { cudaMemcpyAsync(ol.p, old_len_host, npairs * 8, cudaMemcpyHostToDevice, ctx->stream); cudaMemcpyAsync(oi.p, old_idx_host, npairs * 4, cudaMemcpyHostToDevice, ctx->stream); }
+  cudaMemcpyAsync(dO.p, dofs_old_host, n_old * 8, cudaMemcpyHostToDevice, ctx->stream);
+  LAUNCH("project_interface_p0", k_project_interface_p0, grid_for(nnew, 256), 256, nl.p, off.p, nnew, ol.p, oi.p, dO.p, dN.p);
+  cudaMemcpyAsync(dofs_new_host, dN.p, nnew * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(e);
+  nl.release(); ol.release(); dO.release(); dN.release(); off.release(); oi.release();
+  return MMB_OK;
+}
+int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host, double* points_host, int32_t* edge_vertices_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "refinement points need an uploaded 2-D mesh with marks");
+  REQUIRE(n >= 0 && (n == 0 || (cells_host && points_host)), MMB_ERR_INVALID_ARG, "mmb_refinement_points: bad arguments");
+  if (n == 0) return MMB_OK;
+  CK(ctx->list_out.ensure(n));
+  DBuf<double2> out; DBuf<int2> ev;
+  CK(out.ensure(n)); CK(ev.ensure(n));
+  CK(cudaMemcpyAsync(ctx->list_out.p, cells_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH("refinement_points", k_refinement_points, grid_for(n, 256), 256, (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p,
+         ctx->perm.p, ctx->longest.p, ctx->list_out.p, n, out.p, ev.p);
+  cudaMemcpyAsync(points_host, out.p, n * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream);
+  if (edge_vertices_host) cudaMemcpyAsync(edge_vertices_host, ev.p, n * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  out.release(); ev.release();
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return MMB_ERR_CUDA; }
+  return MMB_OK;
+}
+
 // ---- whole step -----------------------------------------------------------------------------------------
 static int step_core(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host) {
   REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");

@@ -19,7 +19,7 @@ EXPORTS = [
     "mmb_indicator_init", "mmb_move_vertices", "mmb_trial_move_validate", "mmb_invalid_cells", "mmb_legality",
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
-    "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
+    "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
     "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
@@ -273,6 +273,22 @@ class Context:
             out["dofs_new"] = out["dofs_new"].reshape(self.nc, ncomp)
         out["result"] = res
         return out
+
+    def project_interface_p0(self, new_len, new_off, old_len, old_idx, dofs_old):
+        new_len, old_len, dofs_old = _f64(new_len), _f64(old_len), _f64(dofs_old)
+        new_off = np.ascontiguousarray(new_off, np.int64)
+        old_idx = _i32(old_idx)
+        out = np.empty(new_len.shape[0])
+        self._ck(lib().mmb_project_interface_p0(self._h, C.c_int64(new_len.shape[0]), _p(new_len), _p(new_off), C.c_int64(old_idx.shape[0]),
+                                                _p(old_len), _p(old_idx), C.c_int64(dofs_old.shape[0]), _p(dofs_old), _p(out)))
+        return out
+
+    def refinement_points(self, cells):
+        cells = _i32(cells)
+        pts = np.empty((cells.shape[0], 2))
+        ev = np.empty((cells.shape[0], 2), np.int32)
+        self._ck(lib().mmb_refinement_points(self._h, C.c_int64(cells.shape[0]), _p(cells), _p(pts), _p(ev)))
+        return pts, ev
 
     def trace_skeleton_p0(self, inside, outside, u_bulk, u_gamma):
         inside, outside, u_bulk, u_gamma = _i32(inside), _i32(outside), _f64(u_bulk), _f64(u_gamma)

@@ -130,6 +130,15 @@ int mmb_project(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_o
 /* MMeshCachingEntity::intersectionVolume (cachingentity.hh:154-167) for every uploaded pair */
 int mmb_intersection_volumes(mmb_context* ctx, double* vol_host);
 
+/* MMeshInterfaceGrid::adapt(handle) (interface/grid.hh:388-415) for FV (P0) interface data: per new interface element
+   the old children with their lengths; the longer of (old, new) is the father. */
+int mmb_project_interface_p0(mmb_context* ctx, int64_t nnew, const double* new_len_host, const int64_t* new_off_host,
+                             int64_t npairs, const double* old_len_host, const int32_t* old_idx_host, int64_t n_old,
+                             const double* dofs_old_host, double* dofs_new_host);
+/* LongestEdgeRefinement::refinement (longestedgerefinement.hh:41-57) for the listed cells (after mmb_mark_elements):
+   centre of the longest edge and, optionally, its two vertex indices (id order). */
+int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host, double* points_host, int32_t* edge_vertices_host);
+
 /* One whole adapt step on resident data, in the reference's user-loop order (doc/examples/moving.py:231-252):
    markElements (distance + marks) -> ensureVertexMovement (trial validity) -> adapt(handle) projection of the
    uploaded pairs -> moveVertices -> in-circle legality of the moved mesh (input of the next host TDS pass).

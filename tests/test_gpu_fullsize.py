@@ -1,0 +1,96 @@
+"""Parity at BASELINE.json's full size (config 3: 16 777 216 triangles): full-array equality where the oracle is fast
+enough with all host threads, seeded samples where it is not (brute-force distance), and size-independent
+properties (identity projection reproduces the DOFs and conserves mass)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    from mmesh_b200 import synth
+    m = synth.config3()
+    s = synth.shifts_uniform(m, 0.3 * m.h, 30)
+    return m, s
+
+
+def test_full_size_parity(big, gpu_ctx_factory, oracle):
+    from mmesh_b200 import synth
+    m, s = big
+    oracle.set_threads(os.cpu_count() or 1)
+    try:
+        ctx = gpu_ctx_factory(2)
+        ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
+        prm = ctx.indicator_init()
+        oprm = oracle.Params.from_buffer_copy(bytes(prm))
+        # --- distance: seeded sample against the reference's brute-force loop, bit-exact ---
+        d, mx = ctx.distance_update()
+        rng = np.random.default_rng(99)
+        near = np.argsort(d)[:: max(1, m.nv // 1500)][:1500]
+        sample = np.unique(np.concatenate([rng.integers(0, m.nv, 2500), near, [int(np.argmax(d))]])).astype(np.int32)
+        assert np.array_equal(d[sample], oracle.distance_2d_subset(m.xy, sample, m.segs))
+        assert mx == d.max() and np.all(d[m.segs.ravel()] == 0.0)
+        # second call starts from the hints of the first: identical field
+        d2, mx2 = ctx.distance_update()
+        assert np.array_equal(d, d2) and mx2 == mx
+        # --- marks on five contiguous cell ranges (oracle fed with the verified distance field) ---
+        marks, le, counts = ctx.mark_elements(run_distance=False)
+        assert counts[0] == (marks == 1).sum() and counts[1] == (marks == -1).sum()
+        for start in np.linspace(0, m.nc - 8192, 5).astype(int):
+            sl = slice(start, start + 8192)
+            rm, rle, _ = oracle.mark(m.xy, d, m.cells[sl], m.perm[sl], oprm, prm.distProportion * mx)
+            assert np.array_equal(marks[sl], rm) and np.array_equal(le[sl], rle)
+        # --- trial validity and legality: full arrays ---
+        valid, sign, ninv = ctx.trial_move_validate(s)
+        rv, rs, rn = oracle.trial_validate(m.xy, s, m.cells)
+        assert np.array_equal(valid, rv) and np.array_equal(sign, rs) and ninv == rn
+        flags, nill = ctx.legality()
+        rf, rnill = oracle.legality(m.xy, None, m.edges)
+        assert np.array_equal(flags, rf) and nill == rnill
+        # --- identity projection: every cell is its own old child => DOFs reproduced, mass conserved ---
+        ident = np.arange(m.nc, dtype=np.int32)
+        ctx.upload_pairs(np.arange(m.nc + 1, dtype=np.int64), ident, synth.cached_corners(m, m.xy, ident), ident)
+        k = np.stack([np.take_along_axis(m.cells, ((m.perm >> (2 * i)) & 3)[:, None].astype(np.int64), 1)[:, 0] for i in range(3)], 1)
+        pk = m.xy[k]
+        dofs = np.sin(np.pi * pk[..., 0]) * np.sin(np.pi * pk[..., 1]) + 2.0
+        got, mass, cov, npc = ctx.project(3, dofs)
+        assert npc == m.nc and abs(cov - 2.0) < 1e-12
+        assert np.max(np.abs(got - dofs)) <= 1e-12 * np.max(np.abs(dofs))
+        vol = np.abs(synth.cross2(pk[:, 1] - pk[:, 0], pk[:, 2] - pk[:, 0])) * 0.5
+        mass_old = float(np.sum(vol * dofs.mean(axis=1), dtype=np.longdouble))
+        assert abs(mass - mass_old) <= 1e-13 * abs(mass_old)
+        p0 = dofs[:, 0].copy()
+        got0, mass0, _, _ = ctx.project(1, p0)
+        assert np.array_equal(got0, p0 * (vol / vol))          # weight |T|/|K| == 1 exactly for the identity cut
+        # --- real move ---
+        ctx.move_vertices(s)
+        assert np.array_equal(ctx.download_coords(), m.xy + s)
+    finally:
+        oracle.set_threads(1)
+
+
+def test_full_size_projection_vs_oracle(big, gpu_ctx_factory, oracle):
+    """Benchmark pair set (self + face neighbours): DOFs on sampled ranges, piece count and mass on the full set."""
+    from mmesh_b200 import synth
+    m, s = big
+    oracle.set_threads(os.cpu_count() or 1)
+    try:
+        new_off, new_cell, old_xy, old_idx = synth.pairs_self_and_neighbours(m, m.xy - s)
+        ctx = gpu_ctx_factory(2)
+        ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
+        ctx.upload_pairs(new_off, new_cell, old_xy, old_idx)
+        prm = ctx.get_params()
+        oprm = oracle.Params.from_buffer_copy(bytes(prm))
+        rng = np.random.default_rng(3)
+        dofs = rng.uniform(0.5, 1.5, (m.nc, 3))
+        got, mass, cov, npc = ctx.project(3, dofs)
+        ref, rmass, rcov, rnpc = oracle.project(m.xy, m.cells, m.perm, new_off, new_cell, old_xy, old_idx, dofs, m.nc, 3, oprm)
+        assert npc == rnpc
+        assert abs(mass - rmass) <= 1e-13 * abs(rmass) and abs(cov - rcov) <= 1e-13 * rcov
+        scale = np.max(np.abs(ref))
+        assert np.max(np.abs(got - ref)) <= 1e-12 * scale
+    finally:
+        oracle.set_threads(1)

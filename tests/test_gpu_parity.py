@@ -351,3 +351,34 @@ def test_adapt_step_host_buffers(gpu_ctx_factory, oracle):
             assert (r.n_refine, r.n_coarsen) == tuple(rc) and r.n_invalid == rn and r.n_illegal == rnill and r.n_pieces == rnpc
             assert abs(r.mass_new - rmass) <= 1e-13 * abs(rmass) and abs(r.covered_area - rcov) <= 1e-13 * rcov
             assert np.array_equal(ctx.download_coords(), oracle.move(m.xy, s))
+
+
+def test_interface_projection_and_refinement_points(gpu_ctx_factory, oracle):
+    """interface/grid.hh:388-415 (1-D father/child by length) and longestedgerefinement.hh:41-57 (edge midpoints)."""
+    rng = np.random.default_rng(12)
+    nnew, nold = 5000, 7000
+    cnt = rng.integers(1, 4, nnew)
+    new_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    P = int(new_off[-1])
+    new_len = rng.uniform(0.5, 1.5, nnew)
+    old_len = rng.uniform(0.2, 2.0, P)
+    old_idx = rng.integers(0, nold, P).astype(np.int32)
+    dofs = rng.uniform(-1, 1, nold)
+    ctx = gpu_ctx_factory(2)
+    got = ctx.project_interface_p0(new_len, new_off, old_len, old_idx, dofs)
+    assert np.array_equal(got, oracle.project_interface_p0(new_len, new_off, old_len, old_idx, dofs))
+    m = _mesh1(60)
+    _upload(ctx, m)
+    prm = ctx.indicator_init()
+    prm.maxH *= 0.3
+    ctx.set_params(prm)
+    marks, le, counts = ctx.mark_elements(run_distance=True)
+    cells = ctx.marked_cells(+1)
+    assert len(cells) > 0
+    pts, ev = ctx.refinement_points(cells)
+    EV = np.array([[0, 1], [0, 2], [1, 2]])
+    for i, c in enumerate(cells[:2000]):
+        _, _, ec, _ = oracle.cell_geometry_2d(m.xy, m.cells[c], m.perm[c])
+        assert np.array_equal(pts[i], ec[le[c]])
+        k = [int(m.cells[c][(m.perm[c] >> (2 * t)) & 3]) for t in range(3)]
+        assert list(ev[i]) == [k[EV[le[c]][0]], k[EV[le[c]][1]]]
