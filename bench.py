@@ -39,8 +39,10 @@ def algorithmic_bytes(name, nv, nc, ne, ns, npairs, nnew, ncomp):
         "mark2d": nc * (12 + 1 + 2) + nv * (16 + 8),
         "move": nv * 48,
         "scale_shifts": nv * 32,
-        "project_p0": npairs * (48 + 4 + 8) + nnew * (8 + 4 + 12 + 1 + 48 + 8),
-        "project_p1": npairs * (48 + 4 + 24) + nnew * (8 + 4 + 12 + 1 + 48 + 24),
+        # per pair: cached old corners 48 + old index 4; per new cell: CSR offset 8 + cell id 4 + corner ids 12 + perm 1 +
+        # DOF write; old DOFs and the new cells' coordinates once per cell / vertex
+        "project_p0": npairs * (48 + 4) + nnew * (8 + 4 + 12 + 1 + 8) + nc * 8 + nv * 16,
+        "project_p1": npairs * (48 + 4) + nnew * (8 + 4 + 12 + 1 + 24) + nc * 24 + nv * 16,
     }
     return t.get(name)
 
@@ -261,8 +263,16 @@ def main():
                      "frac": (ab / (avg * 1e-3) / 1e9 / peak) if ab else None})
     kern.sort(key=lambda k: -k["share"])
     dom = kern[0]
+    traffic = None
+    try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if tj.get("cells") == nc:
+            traffic = tj["kernels"].get(dom["kernel"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": None, "peak_source": peak_src}
+                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "note": "project_p1 is fp64-pipe/issue bound (ncu: fp64 pipe 34 %, issue 56 %, 19/32 active lanes), not HBM bound; see DESIGN.md section 4"}
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
     e2e = None
