@@ -329,83 +329,23 @@ k_pred_exact(int which, const double* __restrict__ pts, const int32_t* __restric
 // ------------------------------------------------------------------------------------------------------
 struct SegLeaf { double c0x, c0y, c1x, c1y, n0, n1; };   // facet corners (AffineGeometry::corner) + Plane normal
 
-// Bounding-volume tree over the facets: implicit heap, node i in [1, 2L), children 2i / 2i+1, leaves at L + s.  Leaf
-// order is chosen at upload: the host's order when consecutive facets are chained (interface-element iteration
-// order follows the polylines), else Morton order of the midpoints.  A node's volume is a CAPSULE: all facets below
-// it lie within `rad` of the axis set S = { a + sigma t : sigma in [0, len] } (fp32 parameters).  Along a polyline
-// run the capsule is the chord plus the sagitta, far tighter than an axis-aligned box, which is what lets distant
-// vertices discard all but a handful of facets.  Per-facet arithmetic stays fp64 and identical to the reference;
-// the tree only decides what may be skipped.
-struct __align__(16) Cap { float ax, ay, tx, ty, len, rad, p0, p1; };
-
-// distance (double) from point e to the axis set of c, evaluated with c's float parameters
-__device__ __forceinline__ double cap_axis_dist(const Cap& c, double ex, double ey) {
-  const double wx = ex - (double)c.ax, wy = ey - (double)c.ay;
-  double s = wx * (double)c.tx + wy * (double)c.ty;
-  s = fmin(fmax(s, 0.0), (double)c.len);
-  const double qx = wx - s * (double)c.tx, qy = wy - s * (double)c.ty;
-  return sqrt(qx * qx + qy * qy);
-}
-__device__ __forceinline__ Cap cap_from_axis(double px, double py, double qx, double qy) {
-  Cap c;
-  c.ax = (float)px; c.ay = (float)py;
-  const float dx = (float)(qx - (double)c.ax), dy = (float)(qy - (double)c.ay);
-  const float l = sqrtf(dx * dx + dy * dy);
-  c.len = l;
-  c.tx = l > 0.f ? dx / l : 1.f; c.ty = l > 0.f ? dy / l : 0.f;
-  c.rad = 0.f; c.p0 = 0.f; c.p1 = 0.f;
-  return c;
-}
-__device__ __forceinline__ float cap_round_up(double r, const Cap& c) {
-  // slack for the double evaluation above and for the non-unit float tangent
-  const double rr = r * (1.0 + 1e-6) + 1e-7 * (fabs((double)c.ax) + fabs((double)c.ay) + (double)c.len) + 1e-300;
-  return __double2float_ru(rr);
-}
-__device__ __forceinline__ Cap cap_empty() {
-  Cap c; c.ax = c.ay = 0.f; c.tx = 1.f; c.ty = 0.f; c.len = 0.f; c.rad = -INFINITY; c.p0 = c.p1 = 0.f; return c;
-}
-// parent capsule of two children: axis = the farthest pair among the four child axis endpoints; radius = max over
-// those endpoints of (distance to the parent axis + child radius) -- the distance to a convex set is convex along
-// each child axis, so its maximum sits at an endpoint.
-__device__ __forceinline__ Cap cap_merge(const Cap& l, const Cap& r) {
-  if (!(l.rad >= 0.f)) return r;
-  if (!(r.rad >= 0.f)) return l;
-  const double ex[4] = { (double)l.ax, (double)l.ax + (double)l.len * (double)l.tx, (double)r.ax, (double)r.ax + (double)r.len * (double)r.tx };
-  const double ey[4] = { (double)l.ay, (double)l.ay + (double)l.len * (double)l.ty, (double)r.ay, (double)r.ay + (double)r.len * (double)r.ty };
-  int bi = 0, bj = 1; double bd = -1.0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = i + 1; j < 4; ++j) {
-      const double d = (ex[i] - ex[j]) * (ex[i] - ex[j]) + (ey[i] - ey[j]) * (ey[i] - ey[j]);
-      if (d > bd) { bd = d; bi = i; bj = j; }
-    }
-  Cap c = cap_from_axis(ex[bi], ey[bi], ex[bj], ey[bj]);
-  double rad = 0.0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) rad = fmax(rad, cap_axis_dist(c, ex[i], ey[i]) + (double)(i < 2 ? l.rad : r.rad));
-  c.rad = cap_round_up(rad, c);
-  return c;
-}
-__device__ __forceinline__ Cap ld_cap(const Cap* p) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  Cap c; c.ax = a.x; c.ay = a.y; c.tx = a.z; c.ty = a.w; c.len = b.x; c.rad = b.y; c.p0 = 0.f; c.p1 = 0.f; return c;
-}
-__device__ __forceinline__ Cap ld_cap_cg(const Cap* p) {
-  const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
-  Cap c; c.ax = a.x; c.ay = a.y; c.tx = a.z; c.ty = a.w; c.len = b.x; c.rad = b.y; c.p0 = 0.f; c.p1 = 0.f; return c;
+// AABB tree over the facets in Morton order of their (upload-time) midpoints: implicit heap, node i in [1, 2L),
+// children 2i / 2i+1, leaves at L + s.  Boxes are float4 (minx, miny, maxx, maxy) rounded OUTWARD, so every fp32
+// test below is a rigorous lower bound; the per-facet arithmetic stays fp64 and identical to the reference.
+__device__ __forceinline__ float4 box_merge(float4 a, float4 b) {
+  return make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 // One launch refits the whole tree: each block reduces 256 leaves in shared memory (8 levels); the block that
 // finishes last (atomic ticket) reduces the remaining top levels.
 __global__ void __launch_bounds__(256)
 k_bvh_build2d(const double2* __restrict__ xy, const int2* __restrict__ segs_sorted, int ns, int L,
-              SegLeaf* __restrict__ leaf, Cap* __restrict__ box, unsigned* __restrict__ ticket) {
-  __shared__ Cap sb[512];
+              SegLeaf* __restrict__ leaf, float4* __restrict__ box, unsigned* __restrict__ ticket) {
+  __shared__ float4 sb[512];
   __shared__ bool last;
   const int t = threadIdx.x;
   const int W = L < 256 ? L : 256;                       // leaves per block (power of two)
   const int i = blockIdx.x * W + t;
-  Cap b = cap_empty();
+  float4 b = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
   if (t < W && i < ns) {
     const int2 s = segs_sorted[i];
     const double2 v0 = ldg2(xy + s.x), v1 = ldg2(xy + s.y);
@@ -419,17 +359,18 @@ k_bvh_build2d(const double2* __restrict__ xy, const int2* __restrict__ segs_sort
     double nn = 0.0; nn += n0 * n0; nn += n1 * n1; nn = sqrt(nn);
     f.n0 = n0 / nn; f.n1 = n1 / nn;
     leaf[i] = f;
-    b = cap_from_axis(f.c0x, f.c0y, f.c1x, f.c1y);
-    b.rad = cap_round_up(fmax(cap_axis_dist(b, f.c0x, f.c0y), cap_axis_dist(b, f.c1x, f.c1y)), b);
+    b = make_float4(__double2float_rd(fmin(f.c0x, f.c1x)), __double2float_rd(fmin(f.c0y, f.c1y)),
+                    __double2float_ru(fmax(f.c0x, f.c1x)), __double2float_ru(fmax(f.c0y, f.c1y)));
   }
   if (t < W) { sb[W + t] = b; box[L + i] = b; }
   const int g0 = L / W + blockIdx.x;                     // global index of this block's subtree root
-  for (int w = W >> 1; w >= 1; w >>= 1) {
+  for (int w = W >> 1, d = 1; w >= 1; w >>= 1, ++d) {
     __syncthreads();
     if (t < w) {
-      const Cap m = cap_merge(sb[2 * (w + t)], sb[2 * (w + t) + 1]);
+      const float4 m = box_merge(sb[2 * (w + t)], sb[2 * (w + t) + 1]);
       sb[w + t] = m;
-      int lev = 0; for (int x = w; x > 1; x >>= 1) ++lev;   // local node (w + t) sits `lev` levels below the subtree root
+      // local node (w + t) sits `lev` levels below the subtree root, offset t inside its level
+      int lev = 0; for (int x = w; x > 1; x >>= 1) ++lev;
       box[((size_t)g0 << lev) + t] = m;
     }
   }
@@ -441,8 +382,11 @@ k_bvh_build2d(const double2* __restrict__ xy, const int2* __restrict__ segs_sort
   if (!last) return;
   const int nb = L / W;                                  // top tree: leaves are the nb subtree roots at [nb, 2nb)
   for (int w = nb >> 1; w >= 1; w >>= 1) {
-    for (int j = w + t; j < 2 * w; j += 256) box[j] = cap_merge(ld_cap_cg(box + 2 * j), ld_cap_cg(box + 2 * j + 1));
-    __threadfence();
+    for (int j = w + t; j < 2 * w; j += 256) {
+      const float4 a = __ldcg(box + 2 * j), c = __ldcg(box + 2 * j + 1);
+      box[j] = box_merge(a, c);
+    }
+    __threadfence_block();
     __syncthreads();
   }
   if (t == 0) *ticket = 0;
@@ -464,54 +408,43 @@ __device__ __forceinline__ double seg_distance(const SegLeaf& f, double px, doub
 }
 struct DistQuery {
   double px, py, best, diag;
-  float pxf, pyf, perr, Tf;
+  float pxlo, pxhi, pylo, pyhi, T2f;
   int arg;
-#ifdef MMB_COUNT_VISITS
-  unsigned nvis = 0, nleaf = 0, ndfs = 0;
-#endif
-  // conservative cull threshold: a node whose lower bound exceeds T cannot hold a facet whose *computed* distance is
-  // below `best` (computed and true distance differ by O(1e-15 (d + len)); diag >= any facet length)
-  __device__ __forceinline__ void set_threshold() { Tf = __double2float_ru(best + 1e-12 * (best + diag)); }
-  // fp32 lower bound of the distance from the query point to anything inside the capsule: |q| below is the distance
-  // to SOME axis point (>= the true axis distance), evaluated with a 2e-6 relative allowance for rounding, the
-  // float copy of the point and the non-unit float tangent
-  __device__ __forceinline__ float lb(const Cap& c) const {
-    const float wx = pxf - c.ax, wy = pyf - c.ay;
-    float s = wx * c.tx + wy * c.ty;
-    s = fminf(fmaxf(s, 0.f), c.len);
-    const float qx = wx - s * c.tx, qy = wy - s * c.ty;
-    const float d = sqrtf(qx * qx + qy * qy);
-    return d - c.rad - (2e-6f * (fabsf(wx) + fabsf(wy) + c.len) + perr);
+  // conservative cull threshold: a node whose box distance exceeds T cannot hold a facet whose *computed* distance
+  // is below `best` (computed and true distance differ by O(1e-15 (d + len)); diag >= any facet length)
+  __device__ __forceinline__ void set_threshold() {
+    const double T = best + 1e-12 * (best + diag);
+    T2f = __double2float_ru(T * T * (1.0 + 1e-12));
+  }
+  // rigorous fp32 lower bound of the squared distance from the query point to a (outward-rounded) box
+  __device__ __forceinline__ float lb2(const float4 b) const {
+    const float dx = fmaxf(fmaxf(__fsub_rd(b.x, pxhi), __fsub_rd(pxlo, b.z)), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(b.y, pyhi), __fsub_rd(pylo, b.w)), 0.f);
+    return __fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy));
   }
   __device__ __forceinline__ void eval_leaf(const SegLeaf* __restrict__ leaf, int s) {
-#ifdef MMB_COUNT_VISITS
-    ++nleaf;
-#endif
     const SegLeaf f = leaf[s];
     const double d = seg_distance(f, px, py);
     if (d < best) { best = d; arg = s; set_threshold(); }          // distance.hh:137-138
   }
   // nearest-first depth-first search of the subtree rooted at `root`
-  __device__ __forceinline__ void dfs(const SegLeaf* __restrict__ leaf, const Cap* __restrict__ box, int ns, int L, int root) {
-    int stack[32]; float sd[32]; int sp = 0;
+  __device__ __forceinline__ void dfs(const SegLeaf* __restrict__ leaf, const float4* __restrict__ box, int ns, int L, int root) {
+    int stack[32]; float sd2[32]; int sp = 0;
     int node = root;
     for (;;) {
       if (node >= L) {
         if (node - L < ns) eval_leaf(leaf, node - L);
         node = 0;
       } else {
-#ifdef MMB_COUNT_VISITS
-        ++nvis;
-#endif
-        const float dl = lb(ld_cap(box + 2 * node)), dr = lb(ld_cap(box + 2 * node + 1));
+        const float dl = lb2(__ldg(box + 2 * node)), dr = lb2(__ldg(box + 2 * node + 1));
         const bool lf = dl <= dr;
         const float dn = lf ? dl : dr, df = lf ? dr : dl;
         const int nn = 2 * node + (lf ? 0 : 1), nf = 2 * node + (lf ? 1 : 0);
-        if (dn > Tf) node = 0;
-        else { if (!(df > Tf)) { stack[sp] = nf; sd[sp] = df; ++sp; } node = nn; }
+        if (dn > T2f) node = 0;
+        else { if (!(df > T2f)) { stack[sp] = nf; sd2[sp] = df; ++sp; } node = nn; }
       }
       if (node == 0) {
-        while (sp > 0) { --sp; if (!(sd[sp] > Tf)) { node = stack[sp]; break; } }
+        while (sp > 0) { --sp; if (!(sd2[sp] > T2f)) { node = stack[sp]; break; } }
         if (node == 0) break;
       }
     }
@@ -522,7 +455,7 @@ struct DistQuery {
 // that path partition all other leaves, so the result is the minimum over ALL facets, like distance.hh:42-59.
 __global__ void __launch_bounds__(256)
 k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restrict__ leaf,
-             const Cap* __restrict__ box, int ns, int L, double* __restrict__ dist, int32_t* __restrict__ hint,
+             const float4* __restrict__ box, int ns, int L, double* __restrict__ dist, int32_t* __restrict__ hint,
              Counters* __restrict__ cnt) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = v < nv && ns > 0;
@@ -531,10 +464,10 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
   if (live) {
     const double2 p = ldg2(xy + v);
     q.px = p.x; q.py = p.y;
-    q.pxf = (float)p.x; q.pyf = (float)p.y;
-    q.perr = 2e-7f * (fabsf(q.pxf) + fabsf(q.pyf)) + 1e-37f;
-    const Cap root = ld_cap(box + 1);
-    q.diag = (double)root.len + 2.0 * (double)root.rad;         // every facet lies inside the root capsule
+    q.pxlo = __double2float_rd(p.x); q.pxhi = __double2float_ru(p.x);
+    q.pylo = __double2float_rd(p.y); q.pyhi = __double2float_ru(p.y);
+    const float4 root = __ldg(box + 1);
+    q.diag = ((double)root.z - (double)root.x) + ((double)root.w - (double)root.y);
     q.set_threshold();
   }
   int h = live ? hint[v] : 0;
@@ -550,19 +483,10 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
     q.eval_leaf(leaf, h);
     for (int node = L + h; node > 1; node >>= 1) {
       const int sib = node ^ 1;
-      if (!(q.lb(ld_cap(box + sib)) > q.Tf)) {
-#ifdef MMB_COUNT_VISITS
-        ++q.ndfs;
-#endif
-        q.dfs(leaf, box, ns, L, sib);
-      }
+      if (!(q.lb2(__ldg(box + sib)) > q.T2f)) q.dfs(leaf, box, ns, L, sib);
     }
     hint[v] = q.arg;
   }
-#ifdef MMB_COUNT_VISITS
-  { unsigned a = warp_sum(q.nvis), b = warp_sum(q.nleaf), c = warp_sum(q.ndfs);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt->pad_[1], (unsigned long long)a); atomicAdd(&cnt->minmax_bits[0], (unsigned long long)b); atomicAdd(&cnt->minmax_bits[1], (unsigned long long)c); } }
-#endif
   if (v < nv) dist[v] = q.best;
   // Distance::maximum (distance.hh:118-123): max starting from 0.0; non-negative doubles order like integers
   unsigned long long bits = (v < nv) ? (unsigned long long)__double_as_longlong(q.best) : 0ull;

@@ -56,7 +56,7 @@ struct mmb_context {
   bool has_shift = false, dist_valid = false, mesh_ok = false;
   // bvh
   int L = 1;
-  DBuf<SegLeaf> seg_leaf; DBuf<Cap> box2; DBuf<int32_t> seg_hint; DBuf<unsigned> ticket;
+  DBuf<SegLeaf> seg_leaf; DBuf<float4> box2; DBuf<int32_t> seg_hint; DBuf<unsigned> ticket;
   DBuf<TriLeaf> tri_leaf; DBuf<double> box3;
   // projection
   int64_t nnew = 0, npairs = 0, n_old = 0;
@@ -270,15 +270,7 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
     std::vector<std::pair<uint64_t, int32_t>> keyed(ns);
     for (int64_t s = 0; s < ns; ++s)
       keyed[s] = { dim == 2 ? morton2(mid[2 * s], mid[2 * s + 1], lo, inv) : morton3(&mid[3 * s], lo, inv), (int32_t)s };
-    // 2-D: keep the host's order when it already walks the interface polylines (consecutive facets share a vertex);
-    // contiguous runs give the tightest capsules.  Otherwise (and in 3-D) sort by Morton code.
-    int64_t chained = 0;
-    if (dim == 2) for (int64_t s = 1; s < ns; ++s) {
-      const int32_t a0 = facets_host[2 * s - 2], a1 = facets_host[2 * s - 1], b0 = facets_host[2 * s], b1 = facets_host[2 * s + 1];
-      chained += (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1);
-    }
-    const bool keep_order = dim == 2 && ns > 1 && chained * 10 >= (ns - 1) * 9 && !getenv("MMB_BVH_MORTON");
-    if (!keep_order) std::sort(keyed.begin(), keyed.end());
+    std::sort(keyed.begin(), keyed.end());
     std::vector<int32_t> sorted((size_t)ns * dim);
     for (int64_t s = 0; s < ns; ++s)
       for (int c = 0; c < dim; ++c) sorted[s * dim + c] = facets_host[(size_t)keyed[s].second * dim + c];
@@ -486,12 +478,6 @@ static int do_distance(mmb_context* ctx) {
     LAUNCH("distance3d", k_distance3d, grid_for(ctx->nv, 256), 256, ctx->x.p, ctx->nv, ctx->tri_leaf.p, ctx->box3.p, ns, L,
            ctx->dist.p, ctx->counters.p);
   }
-#ifdef MMB_COUNT_VISITS
-  { Counters h; cudaStreamSynchronize(ctx->stream); cudaMemcpy(&h, ctx->counters.p, sizeof h, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[visits] per vertex: internal %.2f  leaf evals %.2f  dfs calls %.2f\n", (double)h.pad_[1] / ctx->nv,
-            (double)h.minmax_bits[0] / ctx->nv, (double)h.minmax_bits[1] / ctx->nv);
-    cudaMemset(&ctx->counters.p->pad_[1], 0, 8); cudaMemset(ctx->counters.p->minmax_bits, 0, 16); }
-#endif
   ctx->dist_valid = true;
   return MMB_OK;
 }
