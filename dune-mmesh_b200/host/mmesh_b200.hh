@@ -34,6 +34,7 @@ struct Snapshot {
   std::vector<std::array<int32_t, 4>> edges;        // (a,b,c,d), 2-D only
   std::vector<std::array<int32_t, dim>> facets;     // interface facets
   std::vector<uint8_t> vflags;                      // bit0 isInterface, bit1 boundaryFlag == 1 (host-side use only)
+  std::vector<int32_t> interfaceVertices;           // interface leaf vertex index -> bulk vertex index (interface/indexsets.hh:238-277)
 };
 
 template <int dim> class MMesh;
@@ -133,6 +134,31 @@ class MMesh {
   }
   const std::vector<int32_t>& removed() const { return removed_; }
 
+  //! mmesh.hh:1407-1416: shifts are indexed by the interface grid's leaf vertex index
+  void moveInterface(const std::vector<Coordinate>& ishifts) {
+    scatterInterfaceShifts(ishifts);
+    check(mmb_move_vertices(ctx_, full_[0].data()));
+  }
+  //! Numeric part of mmesh.hh:920-1088: the current mesh must be valid (:926-930, GridError otherwise); cells that
+  //! invert under the interface movement are returned (the host decides between vertex removal and the
+  //! interface-constrained branch :963-1078, which needs the TDS).
+  std::vector<int32_t> ensureInterfaceMovement(const std::vector<Coordinate>& ishifts) {
+    std::vector<Coordinate> zero(snap_->x.size(), Coordinate{});
+    int64_t ninv = 0;
+    int rc = mmb_trial_move_validate(ctx_, zero[0].data(), nullptr, nullptr, &ninv);
+    if (rc == MMB_ERR_INVALID_CELL_3D || (rc == MMB_OK && ninv > 0))
+      throw GridError("A cell has a negative volume! Maybe the interface has been moved too far?");   // mmesh.hh:928
+    check(rc);
+    scatterInterfaceShifts(ishifts);
+    rc = mmb_trial_move_validate(ctx_, full_[0].data(), nullptr, nullptr, &ninv);
+    if (rc == MMB_ERR_INVALID_CELL_3D)
+      throw GridError("Interface could not be moved, because the removal of vertices is not supported in 3D!");   // mmesh.hh:939
+    check(rc);
+    std::vector<int32_t> bad((std::size_t)ninv);
+    if (ninv > 0) check(mmb_invalid_cells(ctx_, bad.data(), ninv, &ninv));
+    return bad;
+  }
+
   //! mmesh.hh:736-751 (bulk loop on the device, interface loop on the device, counters like :725-731)
   bool markElements() {
     indicator_.push();
@@ -199,6 +225,12 @@ class MMesh {
   }
 
  private:
+  void scatterInterfaceShifts(const std::vector<Coordinate>& ishifts) {
+    if (!snap_ || ishifts.size() != snap_->interfaceVertices.size())
+      throw InvalidStateException("shifts.size() != number of interface vertices");           // assert at mmesh.hh:921,1409
+    full_.assign(snap_->x.size(), Coordinate{});
+    for (std::size_t i = 0; i < ishifts.size(); ++i) full_[(std::size_t)snap_->interfaceVertices[i]] = ishifts[i];
+  }
   void requireSize(const std::vector<Coordinate>& s) const {                          // asserts at mmesh.hh:1095,1423
     if (!snap_ || s.size() != snap_->x.size()) throw InvalidStateException("shifts.size() != number of vertices");
   }
@@ -208,6 +240,7 @@ class MMesh {
   std::vector<int8_t> marks_, imarks_;
   std::vector<uint8_t> longest_, valid_;
   std::vector<int32_t> removed_;
+  std::vector<Coordinate> full_;
   int64_t refineMarked_ = 0, coarsenMarked_ = 0;
 };
 

@@ -48,6 +48,12 @@ int main(int argc, char** argv) {
     std::printf("\n");
     grid.postAdapt();
     std::printf("preAdapt %d\n", (int)grid.preAdapt());
+    // interface movement (mmesh.hh:920-1088, :1407-1416): the moved mesh above may contain inverted cells, so the
+    // pre-check of ensureInterfaceMovement must throw GridError exactly when the oracle sees an invalid cell
+    for (std::size_t v = 0; v < nv; ++v) if (s.vflags[v] & 1) s.interfaceVertices.push_back((int32_t)v);
+    std::vector<GlobalCoordinate<2>> ish(s.interfaceVertices.size(), GlobalCoordinate<2>{ 0.0, 1e-3 });
+    try { auto bad = grid.ensureInterfaceMovement(ish); std::printf("ifmove ok %zu\n", bad.size()); }
+    catch (const GridError&) { std::printf("ifmove GridError\n"); }
     // wrong-sized shifts are an error, as the assert at mmesh.hh:1095
     shifts.pop_back();
     try { grid.moveVertices(shifts); std::printf("sizecheck missing\n"); }

@@ -65,3 +65,6 @@ def test_host_class_user_loop(oracle, tmp_path):
     legal, _ = oracle.legality(oracle.move(m.xy, s), None, m.edges)
     assert np.array_equal(np.array(lines["legal"], int), legal)
     assert lines["preAdapt"] == ["0"] and lines["sizecheck"] == ["ok"]
+    # after the (large) move the mesh has inverted cells => ensureInterfaceMovement's pre-check throws (mmesh.hh:926-930)
+    _, _, ninv_moved = oracle.trial_validate(oracle.move(m.xy, s), None, m.cells)
+    assert lines["ifmove"][0] == ("GridError" if ninv_moved > 0 else "ok")
