@@ -658,6 +658,7 @@ int mmb_project(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_o
   REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "projection needs an uploaded 2-D mesh");
   TRY(stage_dofs(ctx, ncomp, n_old, dofs_old_host));
   CK(cudaMemsetAsync(&ctx->counters.p->n_pieces, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->mass_new, 0, 2 * sizeof(double), ctx->stream));      // nnew == 0 leaves them at zero
   TRY(do_project(ctx, ncomp));
   if (dofs_new_host) CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, (size_t)ctx->nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaGetLastError());

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # dune-mmesh_b200/
-_SO = os.path.join(_PKG, "lib", "libmmesh_b200.so")
+_SO = os.environ.get("MMB_LIB") or os.path.join(_PKG, "lib", "libmmesh_b200.so")   # MMB_LIB: instrumented debug builds
 
 MMB_OK, MMB_ERR_INVALID_ARG, MMB_ERR_CUDA, MMB_ERR_NCCL, MMB_ERR_INVALID_CELL_3D, MMB_ERR_CAPACITY, MMB_ERR_STATE = range(7)
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "NCCL error", 4: "invalid 3-D cell", 5: "capacity", 6: "state"}

@@ -382,3 +382,48 @@ def test_interface_projection_and_refinement_points(gpu_ctx_factory, oracle):
         assert np.array_equal(pts[i], ec[le[c]])
         k = [int(m.cells[c][(m.perm[c] >> (2 * t)) & 3]) for t in range(3)]
         assert list(ev[i]) == [k[EV[le[c]][0]], k[EV[le[c]][1]]]
+
+
+def test_projection_ragged_csr(gpu_ctx_factory, oracle):
+    """Ragged pair lists: new cells with 0..9 old children (more than one round of the per-cell loop), arbitrary old
+    triangles (clockwise ones too, degenerate ones, far-away ones), non-contiguous new cells; and an empty pair set."""
+    from mmesh_b200 import synth
+    m = _mesh1(40)
+    rng = np.random.default_rng(21)
+    ctx = gpu_ctx_factory(2)
+    _upload(ctx, m)
+    new_cell = np.sort(rng.choice(m.nc, size=m.nc // 3, replace=False)).astype(np.int32)
+    cnt = rng.integers(0, 10, new_cell.shape[0])
+    new_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    P = int(new_off[-1])
+    ctr = m.xy[m.cells[np.repeat(new_cell, cnt)]].mean(axis=1)
+    old = ctr[:, None, :] + rng.uniform(-1.5 * m.h, 1.5 * m.h, size=(P, 3, 2))
+    old[::17, 2] = 0.5 * (old[::17, 0] + old[::17, 1])            # degenerate (zero area) old cells
+    old[::23] += 0.4                                              # far away: empty intersection
+    old_xy = old.reshape(P, 6)
+    old_idx = rng.integers(0, 500, P).astype(np.int32)
+    ctx.upload_pairs(new_off, new_cell, old_xy, old_idx)
+    prm = ctx.get_params()
+    prm.drop_area = 1e-9
+    ctx.set_params(prm)
+    oprm = oracle.Params.from_buffer_copy(bytes(prm))
+    for ncomp in (1, 3):
+        dofs = rng.uniform(-1, 1, (500, ncomp)) if ncomp == 3 else rng.uniform(-1, 1, 500)
+        ctx.project(ncomp, dofs * 0 + 7.0, download=False)        # stale values must not leak into untouched cells... 
+        got, mass, cov, npc = ctx.project(ncomp, dofs)
+        ref, rmass, rcov, rnpc = oracle.project(m.xy, m.cells, m.perm, new_off, new_cell, old_xy, old_idx, dofs, m.nc, ncomp, oprm)
+        sel = new_cell
+        assert npc == rnpc
+        g, r = (got[sel], ref[sel])
+        assert np.max(np.abs(g - r)) <= 1e-12 * max(1.0, np.max(np.abs(r)))
+        if ncomp == 1:
+            assert np.array_equal(g, r)
+        assert abs(mass - rmass) <= 1e-13 * max(abs(rmass), 1e-300) + 1e-18 and abs(cov - rcov) <= 1e-13 * rcov
+    vols = ctx.intersection_volumes()
+    ref_v = np.array([oracle.intersection_volume(old_xy[p], m.xy[m.cells[new_cell[i]]].reshape(6))
+                      for i in range(new_cell.shape[0]) for p in range(new_off[i], new_off[i + 1])])
+    assert np.array_equal(vols, ref_v)
+    # empty pair set
+    ctx.upload_pairs(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros((0, 6)), np.zeros(0, np.int32))
+    _, mass, cov, npc = ctx.project(1, np.ones(4))
+    assert (mass, cov, npc) == (0.0, 0.0, 0)
