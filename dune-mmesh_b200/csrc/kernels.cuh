@@ -1129,15 +1129,32 @@ k_mark3d(const double* __restrict__ x, const double* __restrict__ dist, const in
   }
   block_count_add<256>(nref, 0u, &cnt->n_refine, &cnt->n_coarsen);
 }
-// 3-D facet leaves: 7 sample points (3 corners, 3 edge midpoints, centre), distance.hh:157-173
+// 3-D facet leaves: 7 sample points (3 corners, 3 edge midpoints, centre), distance.hh:157-173.  Same tree machinery as
+// in 2-D: fp32 boxes rounded outward (two float4 per node), one-launch refit, hint-seeded leaf->root walk.
 struct TriLeaf { double pt[7][3]; };
+struct Box3 { float4 lo, hi; };
+__device__ __forceinline__ Box3 box3_merge(const Box3& a, const Box3& b) {
+  Box3 m;
+  m.lo = make_float4(fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z), 0.f);
+  m.hi = make_float4(fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z), 0.f);
+  return m;
+}
+__device__ __forceinline__ Box3 ld_box3(const Box3* p) {
+  Box3 b; b.lo = __ldg(&p->lo); b.hi = __ldg(&p->hi); return b;
+}
+__device__ __forceinline__ Box3 ld_box3_cg(const Box3* p) {
+  Box3 b; b.lo = __ldcg(&p->lo); b.hi = __ldcg(&p->hi); return b;
+}
 __global__ void __launch_bounds__(256)
-k_tri_prepare(const double* __restrict__ x, const int32_t* __restrict__ tris_sorted, int ns, int L,
-              TriLeaf* __restrict__ leaf, double* __restrict__ box /* [2L][6] */) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= L) return;
-  double b[6] = { INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY };
-  if (i < ns) {
+k_bvh_build3d(const double* __restrict__ x, const int32_t* __restrict__ tris_sorted, int ns, int L,
+              TriLeaf* __restrict__ leaf, Box3* __restrict__ box, unsigned* __restrict__ ticket) {
+  __shared__ Box3 sb[512];
+  __shared__ bool last;
+  const int t = threadIdx.x;
+  const int W = L < 256 ? L : 256;
+  const int i = blockIdx.x * W + t;
+  Box3 b; b.lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f); b.hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+  if (t < W && i < ns) {
     const double* a = x + 3 * (int64_t)tris_sorted[3 * i];
     const double* bb = x + 3 * (int64_t)tris_sorted[3 * i + 1];
     const double* cc = x + 3 * (int64_t)tris_sorted[3 * i + 2];
@@ -1146,78 +1163,126 @@ k_tri_prepare(const double* __restrict__ x, const int32_t* __restrict__ tris_sor
     for (int k = 0; k < 3; ++k) {
       const double j0 = bb[k] - a[k], j1 = cc[k] - a[k];
       c[0][k] = a[k];
-      c[1][k] = (a[k] + 1.0 * j0) + 0.0 * j1;
+      c[1][k] = (a[k] + 1.0 * j0) + 0.0 * j1;            // AffineGeometry::corner
       c[2][k] = (a[k] + 0.0 * j0) + 1.0 * j1;
-      ctr[k] = (a[k] + third * j0) + third * j1;
+      ctr[k] = (a[k] + third * j0) + third * j1;         // center() = global(1/3, 1/3)
     }
     TriLeaf f;
-    for (int t = 0; t < 3; ++t) {
-      const int t2 = (t + 1) % 3;
-      for (int k = 0; k < 3; ++k) { f.pt[2 * t][k] = c[t][k]; f.pt[2 * t + 1][k] = 0.5 * (c[t][k] + c[t2][k]); }
+    for (int tt = 0; tt < 3; ++tt) {
+      const int t2 = (tt + 1) % 3;
+      for (int k = 0; k < 3; ++k) { f.pt[2 * tt][k] = c[tt][k]; f.pt[2 * tt + 1][k] = 0.5 * (c[tt][k] + c[t2][k]); }
     }
     for (int k = 0; k < 3; ++k) f.pt[6][k] = ctr[k];
     leaf[i] = f;
-    for (int t = 0; t < 7; ++t) for (int k = 0; k < 3; ++k) { b[k] = fmin(b[k], f.pt[t][k]); b[3 + k] = fmax(b[3 + k], f.pt[t][k]); }
+    double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int tt = 0; tt < 7; ++tt) for (int k = 0; k < 3; ++k) { lo[k] = fmin(lo[k], f.pt[tt][k]); hi[k] = fmax(hi[k], f.pt[tt][k]); }
+    b.lo = make_float4(__double2float_rd(lo[0]), __double2float_rd(lo[1]), __double2float_rd(lo[2]), 0.f);
+    b.hi = make_float4(__double2float_ru(hi[0]), __double2float_ru(hi[1]), __double2float_ru(hi[2]), 0.f);
   }
-  for (int k = 0; k < 6; ++k) box[6 * (int64_t)(L + i) + k] = b[k];
-}
-__global__ void __launch_bounds__(1024) k_bvh_upper3(int L, double* __restrict__ box) {
-  for (int lvl = L >> 1; lvl >= 1; lvl >>= 1) {
-    for (int i = lvl + threadIdx.x; i < 2 * lvl; i += blockDim.x) {
-      const double* a = box + 6 * (int64_t)(2 * i); const double* b = a + 6;
-      for (int k = 0; k < 3; ++k) { box[6 * (int64_t)i + k] = fmin(a[k], b[k]); box[6 * (int64_t)i + 3 + k] = fmax(a[3 + k], b[3 + k]); }
+  if (t < W) { sb[W + t] = b; box[L + i] = b; }
+  const int g0 = L / W + blockIdx.x;
+  for (int w = W >> 1; w >= 1; w >>= 1) {
+    __syncthreads();
+    if (t < w) {
+      const Box3 m = box3_merge(sb[2 * (w + t)], sb[2 * (w + t) + 1]);
+      sb[w + t] = m;
+      int lev = 0; for (int xx = w; xx > 1; xx >>= 1) ++lev;
+      box[((size_t)g0 << lev) + t] = m;
     }
+  }
+  if (L <= W) return;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  const int nb = L / W;
+  for (int w = nb >> 1; w >= 1; w >>= 1) {
+    for (int j = w + t; j < 2 * w; j += 256) box[j] = box3_merge(ld_box3_cg(box + 2 * j), ld_box3_cg(box + 2 * j + 1));
+    __threadfence();
     __syncthreads();
   }
+  if (t == 0) *ticket = 0;
 }
-__device__ __forceinline__ double box_dist2_3(const double* __restrict__ b, const double* p) {
-  double s = 0.0;
+struct DistQuery3 {
+  double p[3], best2;
+  float plo[3], phi[3], T2f;
+  int arg;
+  // squared quantities are compared exactly like distance.hh:160-171; a node is skipped only if its fp32 lower bound
+  // exceeds best2 (1 + 1e-12): computed squared norms carry a relative error of a few ulps
+  __device__ __forceinline__ void set_threshold() { T2f = __double2float_ru(best2 * (1.0 + 1e-12)); }
+  __device__ __forceinline__ float lb2(const Box3& b) const {
+    const float dx = fmaxf(fmaxf(__fsub_rd(b.lo.x, phi[0]), __fsub_rd(plo[0], b.hi.x)), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(b.lo.y, phi[1]), __fsub_rd(plo[1], b.hi.y)), 0.f);
+    const float dz = fmaxf(fmaxf(__fsub_rd(b.lo.z, phi[2]), __fsub_rd(plo[2], b.hi.z)), 0.f);
+    return __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
+  }
+  __device__ __forceinline__ void eval_leaf(const TriLeaf* __restrict__ leaf, int s) {
+    const TriLeaf& f = leaf[s];
+    bool better = false;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { const double d = fmax(fmax(__ldg(b + k) - p[k], p[k] - __ldg(b + 3 + k)), 0.0); s += d * d; }
-  return s;
-}
-__global__ void __launch_bounds__(256)
-k_distance3d(const double* __restrict__ x, int64_t nv, const TriLeaf* __restrict__ leaf, const double* __restrict__ box,
-             int ns, int L, double* __restrict__ dist, Counters* __restrict__ cnt) {
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double best = 1e100;
-  if (v < nv && ns > 0) {
-    double p[3]; load3(x, nullptr, (int)v, false, p);
-    // the reference takes sqrt(min of squared norms) per facet, then the min over facets: sqrt is monotone, so
-    // minimise the squared value over all facets and take one sqrt -- identical bits.
-    double best2 = 1e100;       // distance.hh:160 initial value (squared quantities are compared against it too)
-    double T2 = best2;
-    int stack[40]; double sd2[40]; int sp = 0; int node = 1;
+    for (int t = 0; t < 7; ++t) {
+      double n2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const double d = p[k] - __ldg(&f.pt[t][k]); n2 += d * d; }
+      if (n2 < best2) { best2 = n2; better = true; }
+    }
+    if (better) { arg = s; set_threshold(); }
+  }
+  __device__ __forceinline__ void dfs(const TriLeaf* __restrict__ leaf, const Box3* __restrict__ box, int ns, int L, int root) {
+    int stack[32]; float sd2[32]; int sp = 0;
+    int node = root;
     for (;;) {
       if (node >= L) {
-        const int s = node - L;
-        if (s < ns) {
-          const TriLeaf& f = leaf[s];
-#pragma unroll
-          for (int t = 0; t < 7; ++t) {
-            double n2 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { const double d = p[k] - f.pt[t][k]; n2 += d * d; }
-            if (n2 < best2) best2 = n2;
-          }
-          T2 = best2 * (1.0 + 1e-12);
-        }
+        if (node - L < ns) eval_leaf(leaf, node - L);
         node = 0;
       } else {
-        const double dl = box_dist2_3(box + 6 * (int64_t)(2 * node), p), dr = box_dist2_3(box + 6 * (int64_t)(2 * node + 1), p);
+        const float dl = lb2(ld_box3(box + 2 * node)), dr = lb2(ld_box3(box + 2 * node + 1));
         const bool lf = dl <= dr;
-        const double dn = lf ? dl : dr, df = lf ? dr : dl;
+        const float dn = lf ? dl : dr, df = lf ? dr : dl;
         const int nn = 2 * node + (lf ? 0 : 1), nf = 2 * node + (lf ? 1 : 0);
-        if (dn > T2) node = 0;
-        else { if (!(df > T2)) { stack[sp] = nf; sd2[sp] = df; ++sp; } node = nn; }
+        if (dn > T2f) node = 0;
+        else { if (!(df > T2f)) { stack[sp] = nf; sd2[sp] = df; ++sp; } node = nn; }
       }
       if (node == 0) {
-        while (sp > 0) { --sp; if (!(sd2[sp] > T2)) { node = stack[sp]; break; } }
+        while (sp > 0) { --sp; if (!(sd2[sp] > T2f)) { node = stack[sp]; break; } }
         if (node == 0) break;
       }
     }
-    best = sqrt(best2);
-    if (best > 1e100) best = 1e100;
+  }
+};
+__global__ void __launch_bounds__(256)
+k_distance3d(const double* __restrict__ x, int64_t nv, const TriLeaf* __restrict__ leaf, const Box3* __restrict__ box,
+             int ns, int L, double* __restrict__ dist, int32_t* __restrict__ hint, Counters* __restrict__ cnt) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = v < nv && ns > 0;
+  DistQuery3 q;
+  q.best2 = 1e100; q.arg = -1;                             // distance.hh:160 initial value
+  if (live) {
+    load3(x, nullptr, (int)v, false, q.p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { q.plo[k] = __double2float_rd(q.p[k]); q.phi[k] = __double2float_ru(q.p[k]); }
+    q.set_threshold();
+  }
+  int h = live ? hint[v] : 0;
+  if (h >= ns) h = -1;
+  const unsigned cold = __ballot_sync(0xffffffffu, live && h < 0);
+  if (cold) {
+    const int leader = __ffs(cold) - 1;
+    if ((threadIdx.x & 31) == leader) q.dfs(leaf, box, ns, L, 1);
+    const int seed = __shfl_sync(0xffffffffu, q.arg, leader);
+    if (live && h < 0) h = seed;
+  }
+  double best = 1e100;
+  if (live) {
+    q.eval_leaf(leaf, h);
+    for (int node = L + h; node > 1; node >>= 1) {
+      const int sib = node ^ 1;
+      if (!(q.lb2(ld_box3(box + sib)) > q.T2f)) q.dfs(leaf, box, ns, L, sib);
+    }
+    hint[v] = q.arg;
+    // sqrt is monotone: sqrt(min over facets of the squared minimum) == min over facets of sqrt(...) bit for bit
+    best = sqrt(q.best2);
   }
   if (v < nv) dist[v] = best;
   unsigned long long bits = (v < nv) ? (unsigned long long)__double_as_longlong(best) : 0ull;

@@ -57,7 +57,7 @@ struct mmb_context {
   // bvh
   int L = 1;
   DBuf<SegLeaf> seg_leaf; DBuf<float4> box2; DBuf<int32_t> seg_hint; DBuf<unsigned> ticket;
-  DBuf<TriLeaf> tri_leaf; DBuf<double> box3;
+  DBuf<TriLeaf> tri_leaf; DBuf<Box3> box3;
   // projection
   int64_t nnew = 0, npairs = 0, n_old = 0;
   DBuf<long long> new_off; DBuf<int32_t> new_cell, old_idx; DBuf<double> old_xy, dofs_old, dofs_new, part_a, part_b, pair_vol;
@@ -282,7 +282,11 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
     CK(cudaMemsetAsync(ctx->seg_hint.p, 0xFF, (size_t)nv * sizeof(int32_t), ctx->stream));    // -1: no hint yet
     CK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
   }
-  else { CK(ctx->tri_leaf.ensure(L)); CK(ctx->box3.ensure(12 * (size_t)L)); }
+  else {
+    CK(ctx->tri_leaf.ensure(L)); CK(ctx->box3.ensure(2 * (size_t)L)); CK(ctx->seg_hint.ensure(nv)); CK(ctx->ticket.ensure(1));
+    CK(cudaMemsetAsync(ctx->seg_hint.p, 0xFF, (size_t)nv * sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   ctx->has_shift = false; ctx->dist_valid = false; ctx->mesh_ok = true;
@@ -472,11 +476,11 @@ static int do_distance(mmb_context* ctx) {
            ctx->box2.p, ns, L, ctx->dist.p, ctx->seg_hint.p, ctx->counters.p);
   } else {
     if (ns) {
-      LAUNCH("tri_prepare", k_tri_prepare, grid_for(L, 256), 256, ctx->x.p, ctx->facets_sorted.p, ns, L, ctx->tri_leaf.p, ctx->box3.p);
-      LAUNCH("bvh_upper3", k_bvh_upper3, 1, 1024, L, ctx->box3.p);
+      LAUNCH("bvh_build3d", k_bvh_build3d, L < 256 ? 1 : L / 256, 256, ctx->x.p, ctx->facets_sorted.p, ns, L, ctx->tri_leaf.p,
+             ctx->box3.p, ctx->ticket.p);
     }
     LAUNCH("distance3d", k_distance3d, grid_for(ctx->nv, 256), 256, ctx->x.p, ctx->nv, ctx->tri_leaf.p, ctx->box3.p, ns, L,
-           ctx->dist.p, ctx->counters.p);
+           ctx->dist.p, ctx->seg_hint.p, ctx->counters.p);
   }
   ctx->dist_valid = true;
   return MMB_OK;
