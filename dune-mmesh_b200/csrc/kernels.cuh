@@ -1350,6 +1350,15 @@ k_scatter2(double2* __restrict__ dst, const int32_t* __restrict__ idx, int64_t n
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[idx[i]] = src[i];
 }
+// scatter of packed DOF blocks (ncomp doubles each) to their cell slots: the few old DOFs a projection chunk needs from
+// outside its own index range are uploaded first through a packed staging buffer
+__global__ void __launch_bounds__(256)
+k_scatter_dofs(double* __restrict__ dst, const int32_t* __restrict__ idx, int64_t n, int ncomp, const double* __restrict__ src) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * ncomp) return;
+  const int64_t e = i / ncomp; const int c = (int)(i - e * ncomp);
+  dst[(int64_t)idx[e] * ncomp + c] = src[i];
+}
 // the additive scalars of a step as one double vector (counts < 2^53 are exact), ready for a single all-reduce
 __global__ void k_reduce_vector(const Counters* __restrict__ c, double* __restrict__ v) {
   if (threadIdx.x == 0) {

@@ -63,6 +63,9 @@ struct mmb_context {
   DBuf<long long> new_off; DBuf<int32_t> new_cell, old_idx; DBuf<double> old_xy, dofs_old, dofs_new, part_a, part_b, pair_vol;
   int dofs_ncomp = 0;
   std::vector<int64_t> chunk_i; std::vector<int32_t> chunk_cell_lo, chunk_cell_hi; bool chunks_ok = false;
+  // pipelined DOF upload: chunk k reads old DOFs from its home index range [dof_lo[k], dof_lo[k+1]) plus a few remote ones
+  bool dof_pipe_ok = false; std::vector<int64_t> dof_lo; std::vector<int32_t> remote_idx; DBuf<int32_t> d_remote_idx;
+  DBuf<double> d_remote_stage; double* h_remote_stage = nullptr; size_t h_remote_cap = 0;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr; std::vector<cudaEvent_t> pipe_ev;
   // 3-D trace
   DBuf<int32_t> tr_in, tr_out; DBuf<double> tr_u, tr_ug, tr_a, tr_b, tr_c;
@@ -164,6 +167,8 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->tr_a.release(); ctx->tr_b.release(); ctx->tr_c.release(); ctx->pred_pts.release(); ctx->pred_sign.release();
   ctx->halo_send_idx.release(); ctx->halo_recv_idx.release(); ctx->halo_send.release(); ctx->halo_recv.release(); ctx->reduce_vec.release();
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->h_remote_stage) cudaFreeHost(ctx->h_remote_stage);
+  ctx->d_remote_idx.release(); ctx->d_remote_stage.release();
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
@@ -608,6 +613,31 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
     ctx->chunk_cell_lo.push_back(new_cell_host[ctx->chunk_i[k]]);
     ctx->chunk_cell_hi.push_back(new_cell_host[ctx->chunk_i[k + 1] - 1]);
   }
+  // Can the old DOFs be uploaded range by range behind the projection?  Split the old index space into C equal ranges;
+  // chunk k's home range is range k.  Every reference outside the home range goes to a (unique, small) remote list that
+  // is uploaded first.  If the numbering of old and new cells is unrelated the remote list is large -> monolithic upload.
+  ctx->dof_pipe_ok = false; ctx->dof_lo.clear(); ctx->remote_idx.clear();
+  if (ctx->chunks_ok && C > 1 && npairs > 0) {
+    int64_t n_idx = 0;
+    for (int64_t p = 0; p < npairs; ++p) n_idx = std::max<int64_t>(n_idx, old_idx_host[p] + 1);
+    for (int k = 0; k <= C; ++k) ctx->dof_lo.push_back(n_idx * k / C);
+    std::vector<uint8_t> seen((size_t)n_idx, 0);
+    bool ok = true;
+    for (int k = 0; k < C && ok; ++k) {
+      const int64_t lo = ctx->dof_lo[k], hi = ctx->dof_lo[k + 1];
+      for (int64_t p = new_off_host[ctx->chunk_i[k]]; p < new_off_host[ctx->chunk_i[k + 1]]; ++p) {
+        const int32_t o = old_idx_host[p];
+        if ((o < lo || o >= hi) && !seen[(size_t)o]) { seen[(size_t)o] = 1; ctx->remote_idx.push_back(o); }
+      }
+      ok = (int64_t)ctx->remote_idx.size() * 16 <= n_idx;
+    }
+    if (ok) {
+      CK(ctx->d_remote_idx.ensure(ctx->remote_idx.size() + 1));
+      if (!ctx->remote_idx.empty())
+        CK(cudaMemcpy(ctx->d_remote_idx.p, ctx->remote_idx.data(), ctx->remote_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      ctx->dof_pipe_ok = true;
+    } else ctx->remote_idx.clear();
+  }
   return MMB_OK;
 }
 #define PROJ_ARGS (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p, ctx->new_off.p, ctx->new_cell.p, \
@@ -779,7 +809,7 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
   REQUIRE(ncomp == 0 || ncomp == 1 || ncomp == 3, MMB_ERR_INVALID_ARG, "ncomp must be 0, 1 (P0) or 3 (DG-P1)");
   REQUIRE(shifts_host || ctx->has_shift, MMB_ERR_STATE, "shifts == NULL but no resident shifts");
   if (!ctx->s_h2d) { CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)); }
-  while (ctx->pipe_ev.size() < 24) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->pipe_ev.push_back(e); }
+  while (ctx->pipe_ev.size() < 32) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->pipe_ev.push_back(e); }
   cudaStream_t S0 = ctx->stream, S1 = ctx->s_h2d, S2 = ctx->s_d2h;
   cudaEvent_t* ev = ctx->pipe_ev.data();
   const size_t nc = (size_t)ctx->nc;
@@ -795,8 +825,33 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
   if (shifts_host) CK(cudaMemcpyAsync(ctx->shift.p, shifts_host, (size_t)ctx->nv * ctx->dim * sizeof(double), cudaMemcpyHostToDevice, S1));
   ctx->has_shift = true;
   CK(cudaEventRecord(ev[1], S1));
+  const bool pipe_dofs = ncomp && dofs_old_host && dofs_new_host && ctx->nnew && ctx->chunks_ok && ctx->dof_pipe_ok &&
+                         (ctx->dof_lo.empty() || ctx->dof_lo.back() <= n_old);
   if (ncomp && dofs_old_host) {
-    CK(cudaMemcpyAsync(ctx->dofs_old.p, dofs_old_host, (size_t)n_old * ncomp * sizeof(double), cudaMemcpyHostToDevice, S1));
+    if (pipe_dofs) {
+      // remote DOFs first (packed on the host, scattered on the device), then one index range per projection chunk
+      const size_t nr = ctx->remote_idx.size();
+      if (nr) {
+        if (ctx->h_remote_cap < nr * ncomp) {
+          if (ctx->h_remote_stage) cudaFreeHost(ctx->h_remote_stage);
+          CK(cudaMallocHost((void**)&ctx->h_remote_stage, nr * 3 * sizeof(double))); ctx->h_remote_cap = nr * 3;
+        }
+        CK(ctx->d_remote_stage.ensure(nr * 3));
+        for (size_t r = 0; r < nr; ++r)
+          for (int c = 0; c < ncomp; ++c) ctx->h_remote_stage[r * ncomp + c] = dofs_old_host[(size_t)ctx->remote_idx[r] * ncomp + c];
+        CK(cudaMemcpyAsync(ctx->d_remote_stage.p, ctx->h_remote_stage, nr * ncomp * sizeof(double), cudaMemcpyHostToDevice, S1));
+        { LaunchScope ls_(ctx, "scatter_dofs");
+          k_scatter_dofs<<<grid_for((int64_t)nr * ncomp, 256), 256, 0, S1>>>(ctx->dofs_old.p, ctx->d_remote_idx.p, (int64_t)nr, ncomp, ctx->d_remote_stage.p); }
+      }
+      const int C = (int)ctx->chunk_cell_lo.size();
+      for (int k = 0; k < C; ++k) {
+        const size_t lo = (size_t)ctx->dof_lo[k], hi = k == C - 1 ? (size_t)n_old : (size_t)ctx->dof_lo[k + 1];
+        if (hi > lo) CK(cudaMemcpyAsync(ctx->dofs_old.p + lo * ncomp, dofs_old_host + lo * ncomp, (hi - lo) * ncomp * sizeof(double), cudaMemcpyHostToDevice, S1));
+        CK(cudaEventRecord(ev[16 + k], S1));
+      }
+    } else {
+      CK(cudaMemcpyAsync(ctx->dofs_old.p, dofs_old_host, (size_t)n_old * ncomp * sizeof(double), cudaMemcpyHostToDevice, S1));
+    }
     ctx->n_old = n_old; ctx->dofs_ncomp = ncomp;
   }
   CK(cudaEventRecord(ev[2], S1));
@@ -818,13 +873,14 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
   if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, nc, cudaMemcpyDeviceToHost, S2));
   if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, nc, cudaMemcpyDeviceToHost, S2));
   if (ncomp && ctx->nnew) {
-    CK(cudaStreamWaitEvent(S0, ev[2], 0));                         // old DOFs have landed
+    if (!pipe_dofs) CK(cudaStreamWaitEvent(S0, ev[2], 0));         // old DOFs have landed (monolithic upload)
     const bool chunked = ctx->chunks_ok && dofs_new_host;
     const int C = chunked ? (int)ctx->chunk_cell_lo.size() : 1;
     int pb = 0;
     for (int k = 0; k < C; ++k) {
       const int64_t i0 = chunked ? ctx->chunk_i[k] : 0, i1 = chunked ? ctx->chunk_i[k + 1] : ctx->nnew;
       int nb = 0;
+      if (pipe_dofs) CK(cudaStreamWaitEvent(S0, ev[16 + k], 0));   // this chunk's home range (and the remote DOFs) have landed
       TRY(project_range(ctx, ncomp, i0, i1, pb, &nb));
       pb += nb;
       if (dofs_new_host) {

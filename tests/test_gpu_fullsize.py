@@ -92,5 +92,11 @@ def test_full_size_projection_vs_oracle(big, gpu_ctx_factory, oracle):
         assert abs(mass - rmass) <= 1e-13 * abs(rmass) and abs(cov - rcov) <= 1e-13 * rcov
         scale = np.max(np.abs(ref))
         assert np.max(np.abs(got - ref)) <= 1e-12 * scale
+        # the pipelined host-buffer step (chunked DOF upload / projection / download) returns the very same DOFs
+        out = ctx.adapt_step_host(s, 3, dofs)
+        assert np.array_equal(out["dofs_new"], got)
+        assert out["result"].n_pieces == rnpc and abs(out["result"].mass_new - rmass) <= 1e-13 * abs(rmass)
+        rv, rs, rn = oracle.trial_validate(m.xy, s, m.cells)
+        assert np.array_equal(out["valid_fp"], rv) and np.array_equal(out["orient_sign"], rs)
     finally:
         oracle.set_threads(1)
