@@ -1030,24 +1030,39 @@ int mmb_step_phase_distance(mmb_context* ctx) {
   CK(cudaGetLastError());
   return MMB_OK;
 }
-// phase B: everything after the global max distance is known; leaves the additive scalars in the reduce vector
-int mmb_step_phase_rest(mmb_context* ctx, int ncomp) {
-  if (!ctx) return MMB_ERR_INVALID_ARG;
+// phases after the distance update.  which = 1: trial validity + projection (independent of the global max distance, so
+// the MAX all-reduce can run concurrently); 2: marks (need the global max); 3: moveVertices + legality + the reduce
+// vector; 0: all three in the reference order (marks first).
+int mmb_step_phase(mmb_context* ctx, int which, int ncomp) {
+  if (!ctx || which < 0 || which > 3) return MMB_ERR_INVALID_ARG;
   REQUIRE(ctx->mesh_ok && ctx->has_shift, MMB_ERR_STATE, "no mesh / shifts");
-  if (ncomp) TRY(stage_dofs(ctx, ncomp, 0, nullptr));
-  TRY(do_mark(ctx));
-  if (ctx->dim == 2 && ctx->ns)
-    LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
-           (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
-  TRY(do_validate(ctx, true));
-  if (ncomp) TRY(do_project(ctx, ncomp));
-  TRY(do_move(ctx));
-  if (ctx->dim == 2) TRY(do_legality(ctx));
-  CK(ctx->reduce_vec.ensure(16));
-  LAUNCH("reduce_vector", k_reduce_vector, 1, 32, ctx->counters.p, ctx->reduce_vec.p);
+  auto marks = [&]() -> int {
+    TRY(do_mark(ctx));
+    if (ctx->dim == 2 && ctx->ns)
+      LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
+             (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
+    return MMB_OK;
+  };
+  auto validate_project = [&]() -> int {
+    if (ncomp) TRY(stage_dofs(ctx, ncomp, 0, nullptr));
+    TRY(do_validate(ctx, true));
+    if (ncomp) TRY(do_project(ctx, ncomp));
+    return MMB_OK;
+  };
+  auto move_legality = [&]() -> int {
+    TRY(do_move(ctx));
+    if (ctx->dim == 2) TRY(do_legality(ctx));
+    CK(ctx->reduce_vec.ensure(16));
+    LAUNCH("reduce_vector", k_reduce_vector, 1, 32, ctx->counters.p, ctx->reduce_vec.p);
+    return MMB_OK;
+  };
+  if (which == 0 || which == 2) TRY(marks());
+  if (which == 0 || which == 1) TRY(validate_project());
+  if (which == 0 || which == 3) TRY(move_legality());
   CK(cudaGetLastError());
   return MMB_OK;
 }
+int mmb_step_phase_rest(mmb_context* ctx, int ncomp) { return mmb_step_phase(ctx, 0, ncomp); }
 
 // ---- timing ---------------------------------------------------------------------------------------------
 int mmb_timing_enable(mmb_context* ctx, int on) { if (!ctx) return MMB_ERR_INVALID_ARG; ctx->timing = on != 0; return MMB_OK; }

@@ -20,7 +20,7 @@ EXPORTS = [
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
     "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
-    "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
+    "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
 
@@ -330,6 +330,9 @@ class Context:
 
     def step_phase_rest(self, ncomp):
         self._ck(lib().mmb_step_phase_rest(self._h, C.c_int(ncomp)))
+
+    def step_phase(self, which, ncomp):
+        self._ck(lib().mmb_step_phase(self._h, C.c_int(which), C.c_int(ncomp)))
 
     # ---- instrumentation ----
     def timing_enable(self, on=True):

@@ -70,12 +70,26 @@ class ShardedMesh:
         self.ctx.halo_unpack_shifts()
 
     def step(self, ncomp):
-        """markElements -> ensureVertexMovement -> adapt(handle) -> moveVertices -> legality on this shard."""
-        dist, torch = self.dist, self.torch
-        self.exchange_shifts()                                   # halo vertex exchange (owned shifts -> halos)
-        self.ctx.step_phase_distance()
-        dist.all_reduce(self.maxword, op=dist.ReduceOp.MAX)      # Distance::maximum() over all ranks
-        self.ctx.step_phase_rest(ncomp)
+        """markElements -> ensureVertexMovement -> adapt(handle) -> moveVertices -> legality on this shard.
+        The halo exchange runs while the distance field is computed (it does not need the shifts); the MAX
+        all-reduce runs while validity + projection are computed (they do not need the global max distance)."""
+        dist = self.dist
+        nccl = dist.get_backend() == "nccl"
+        self.ctx.halo_pack_shifts()
+        if nccl:
+            w1 = dist.all_to_all_single(self.recv, self.send, output_split_sizes=[int(c) for c in self.sh.recv_counts],
+                                        input_split_sizes=[int(c) for c in self.sh.send_counts], async_op=True)
+            self.ctx.step_phase_distance()
+            w1.wait()
+        else:
+            exchange_rows(dist, self.send, self.recv, self.sh.send_counts, self.sh.recv_counts, self.sh.rank, self.sh.world)
+            self.ctx.step_phase_distance()
+        self.ctx.halo_unpack_shifts()                            # halo vertex exchange (owned shifts -> halos)
+        w2 = dist.all_reduce(self.maxword, op=dist.ReduceOp.MAX, async_op=True)      # Distance::maximum() over all ranks
+        self.ctx.step_phase(1, ncomp)                            # trial validity + projection
+        w2.wait()
+        self.ctx.step_phase(2, ncomp)                            # marks (need the global max)
+        self.ctx.step_phase(3, ncomp)                            # move + legality + reduce vector
         dist.all_reduce(self.vec, op=dist.ReduceOp.SUM)          # counts + mass in one small vector
 
     def result(self):

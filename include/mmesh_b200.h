@@ -174,6 +174,9 @@ int mmb_halo_unpack_shifts(mmb_context* ctx);    /* recv buffer -> resident shif
 int mmb_device_buffer(mmb_context* ctx, int which, void** device_ptr, int64_t* bytes);
 int mmb_step_phase_distance(mmb_context* ctx);            /* counters = 0; Distance::update on the local vertices */
 int mmb_step_phase_rest(mmb_context* ctx, int ncomp);     /* mark -> validate -> project -> move -> legality */
+/* the same split so that collectives overlap compute: which = 1 validity + projection (no dependence on the global max
+   distance: run it while the MAX all-reduce is in flight), 2 marks, 3 move + legality + reduce vector, 0 = all */
+int mmb_step_phase(mmb_context* ctx, int which, int ncomp);
 
 /* ---- 3-D extras -------------------------------------------------------------------------------------- */
 /* P0 interface-coupled transfer (dune/python/mmesh/pyskeletontrace.hh:42-64,133-160):
