@@ -147,7 +147,7 @@ def run_reference_arm(args):
     m = w["mesh"]
     prm = O.indicator_init_2d(m.xy, m.edges, m.segs, O.Params.default())
     threads = os.cpu_count() or 1
-    sample = min(m.nc, args.cpu_sample)
+    sample = min(m.nc, 8 * args.cpu_sample)               # all host threads: a larger bounded sample than the 1-core baseline
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_step(O, w, sample, prm, threads)
     ts = [cpu_reference_step(O, w, sample, prm, threads) for _ in range(max(1, min(args.steps, 3)))]
