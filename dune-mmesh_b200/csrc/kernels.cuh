@@ -849,6 +849,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
           DevParams prm, double* __restrict__ part_mass, double* __restrict__ part_cov, Counters* __restrict__ cnt) {
   __shared__ double2 sP[6][PROJ_THREADS];      // subject triangle, then output of clip edge 1 (<= 6)
   __shared__ double2 sQ[9][PROJ_THREADS];      // outputs of clip edges 0 (<= 4) and 2 (<= 9)
+  __shared__ double2 sE[4][PROJ_THREADS];      // the new cell's TDS-order corners e0, e1, e2, e0: clip edge st = (sE[st], sE[st+1])
   const int tid = threadIdx.x;
   const int64_t gid = (int64_t)blockIdx.x * PROJ_THREADS + tid;
   const int64_t i = i_begin + gid / LPC;           // new cells [i_begin, nnew) of the pair CSR
@@ -876,6 +877,8 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
     }
     if (NCOMP == 3) gK = aff2_make(kx[0] - orgx, ky[0] - orgy, kx[1] - orgx, ky[1] - orgy, kx[2] - orgx, ky[2] - orgy);
   }
+  sE[0][tid] = make_double2(ex[0], ey[0]); sE[1][tid] = make_double2(ex[1], ey[1]);
+  sE[2][tid] = make_double2(ex[2], ey[2]); sE[3][tid] = make_double2(ex[0], ey[0]);
   double acc0 = 0.0; bool initialize = true;     // P0 running value (reference order)
   double R1 = 0.0, R2 = 0.0, U = 0.0;            // P1 totals over pairs
   long long maxr = live ? (p1 - p0 + LPC - 1) / LPC : 0;
@@ -918,9 +921,8 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
       for (int st = 0; st < 3; ++st) {                      // one code instance for the three clip edges
         const double2* in = (st == 1) ? &sQ[0][tid] : &sP[0][tid];
         double2* out = (st == 1) ? &sP[0][tid] : &sQ[0][tid];
-        const int a = st, b = st == 2 ? 0 : st + 1;
-        const double q1x = a == 0 ? ex[0] : (a == 1 ? ex[1] : ex[2]), q1y = a == 0 ? ey[0] : (a == 1 ? ey[1] : ey[2]);
-        const double q2x = b == 0 ? ex[0] : (b == 1 ? ex[1] : ex[2]), q2y = b == 0 ? ey[0] : (b == 1 ? ey[1] : ey[2]);
+        const double2 q1 = sE[st][tid], q2 = sE[st + 1][tid];
+        const double q1x = q1.x, q1y = q1.y, q2x = q2.x, q2y = q2.y;
         nC = clip_stage<6>([&](int k, double& x, double& y) { const double2 v = in[k * PROJ_THREADS]; x = v.x; y = v.y; },
                            nC, q1x, q1y, q2x, q2y, prm.clip_eps,
                            [&](int k, double x, double y) { out[k * PROJ_THREADS] = make_double2(x, y); });
