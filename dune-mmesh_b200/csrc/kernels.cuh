@@ -850,6 +850,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
   __shared__ double2 sP[6][PROJ_THREADS];      // subject triangle, then output of clip edge 1 (<= 6)
   __shared__ double2 sQ[9][PROJ_THREADS];      // outputs of clip edges 0 (<= 4) and 2 (<= 9)
   __shared__ double2 sE[4][PROJ_THREADS];      // the new cell's TDS-order corners e0, e1, e2, e0: clip edge st = (sE[st], sE[st+1])
+  __shared__ double2 sG[3][PROJ_THREADS];      // the new cell's inverse affine map (origin, J^-T rows), used by the fan only
   const int tid = threadIdx.x;
   const int64_t gid = (int64_t)blockIdx.x * PROJ_THREADS + tid;
   const int64_t i = i_begin + gid / LPC;           // new cells [i_begin, nnew) of the pair CSR
@@ -860,7 +861,6 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
   unsigned npc = 0;
   int K = 0; long long p0 = 0, p1 = 0;
   double ex[3] = { 0, 0, 0 }, ey[3] = { 0, 0, 0 }, kx[3], ky[3], orgx = 0.0, orgy = 0.0, volK = 1.0;
-  Aff2 gK;
   if (live) {
     K = new_cell[i]; p0 = new_off[i]; p1 = new_off[i + 1];
     const int v[3] = { __ldg(cv0 + K), __ldg(cv1 + K), __ldg(cv2 + K) };
@@ -875,7 +875,10 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
 #pragma unroll
       for (int t = 0; t < 3; ++t) { ex[t] -= orgx; ey[t] -= orgy; }
     }
-    if (NCOMP == 3) gK = aff2_make(kx[0] - orgx, ky[0] - orgy, kx[1] - orgx, ky[1] - orgy, kx[2] - orgx, ky[2] - orgy);
+    if (NCOMP == 3) {
+      const Aff2 gK = aff2_make(kx[0] - orgx, ky[0] - orgy, kx[1] - orgx, ky[1] - orgy, kx[2] - orgx, ky[2] - orgy);
+      sG[0][tid] = make_double2(gK.ox, gK.oy); sG[1][tid] = make_double2(gK.i00, gK.i01); sG[2][tid] = make_double2(gK.i10, gK.i11);
+    }
   }
   sE[0][tid] = make_double2(ex[0], ey[0]); sE[1][tid] = make_double2(ex[1], ey[1]);
   sE[2][tid] = make_double2(ex[2], ey[2]); sE[3][tid] = make_double2(ex[0], ey[0]);
@@ -902,13 +905,6 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
 #pragma unroll
         for (int t = 0; t < 3; ++t) { cx[t] -= orgx; cy[t] -= orgy; }
       }
-      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-      Aff2 gO;
-      {
-        const double* uo = dofs_old + (int64_t)NCOMP * __ldg(old_idx + pr);
-        u0 = __ldg(uo);
-        if (NCOMP == 3) { u1 = __ldg(uo + 1); u2 = __ldg(uo + 2); gO = aff2_make(cx[0], cy[0], cx[1], cy[1], cx[2], cy[2]); }
-      }
       // cutsettriangulation.hh:46-49: orientation value truncated to int
       const double od = (cy[1] - cy[0]) * (cx[2] - cx[1]) - (cx[1] - cx[0]) * (cy[2] - cy[1]);
       const int o = (fabs(od) < 2147483648.0) ? (int)od : 0;
@@ -928,6 +924,20 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
                            [&](int k, double x, double y) { out[k * PROJ_THREADS] = make_double2(x, y); });
       }
       auto& sC = sQ;
+      if (nC >= 3) {                                        // cutsettriangulation.hh:55 `if (points.size() < 3) return;`
+      // old DOFs and the old cell's geometry are needed only now (about every second neighbour pair is empty)
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      Aff2 gO, gK;
+      {
+        const double* uo = dofs_old + (int64_t)NCOMP * __ldg(old_idx + pr);
+        u0 = __ldg(uo);
+        if (NCOMP == 3) {
+          u1 = __ldg(uo + 1); u2 = __ldg(uo + 2);
+          gO = aff2_make(cx[0], cy[0], cx[1], cy[1], cx[2], cy[2]);
+          const double2 g0 = sG[0][tid], g1 = sG[1][tid], g2 = sG[2][tid];
+          gK.ox = g0.x; gK.oy = g0.y; gK.i00 = g1.x; gK.i01 = g1.y; gK.i10 = g2.x; gK.i11 = g2.y; gK.vol = 0.0;
+        }
+      }
       // fan (points[0], points[j-1], points[j]), cutsettriangulation.hh:57-61
       double fx = 0, fy = 0, fu = 0, ff1 = 0, ff2 = 0, px = 0, py = 0, pu = 0, pf1 = 0, pf2 = 0;
       for (int j = 0; j < nC; ++j) {
@@ -954,14 +964,15 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
               const double s1 = ff1 + pf1 + f1, s2 = ff2 + pf2 + f2;
               const double d1 = fu * ff1 + pu * pf1 + uj * f1;
               const double d2 = fu * ff2 + pu * pf2 + uj * f2;
-              const double w12 = aT / 12;
+              const double w12 = aT * (1.0 / 12.0);
               r1 += w12 * (su * s1 + d1);
               r2 += w12 * (su * s2 + d2);
-              u += (aT / 3) * su;
+              u += (aT * (1.0 / 3.0)) * su;
             }
           }
         }
         px = P.x; py = P.y; pu = uj; pf1 = f1; pf2 = f2;
+      }
       }
     }
     if (NCOMP == 3) {

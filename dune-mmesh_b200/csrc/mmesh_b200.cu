@@ -659,7 +659,8 @@ static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, in
       case 3: LAUNCH("project_p1", (k_project<3, 1, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 4: LAUNCH("project_p1", (k_project<3, 4, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 5: LAUNCH("project_p1", (k_project<3, 1, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      default: LAUNCH("project_p1", (k_project<3, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 6: LAUNCH("project_p1", (k_project<3, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      default: LAUNCH("project_p1", (k_project<3, 1, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
     }
   }
   *nblocks = (int)nb;

@@ -787,7 +787,7 @@ static inline void aff2_local(const aff2* g, const double x[2], double* xi, doub
         (FV restrictLocal with weight |son|/|father|).
    P1 : local L2 projection onto the nodal basis of the id-ordered corners of K.  For a cut triangle T with
         vertices v_j the product of two linear functions is integrated exactly by
-            int_T u phi = |T|/12 * ( (sum_j u_j)(sum_j phi_j) + sum_j u_j phi_j ),
+            int_T u phi = |T| * (1/12) * ( (sum_j u_j)(sum_j phi_j) + sum_j u_j phi_j ),   (1/12, 1/3: rounded constants)
         u_j = u_old(v_j) (barycentric in the cached old cell), phi_j = barycentric coordinates of v_j in K
         (AffineGeometry::local).  phi_0 = 1 - phi_1 - phi_2 is eliminated through int_T u = |T|/3 sum_j u_j.
         Each (old,new) pair accumulates its own partial sums; pairs are then added in CSR order. */
@@ -840,10 +840,10 @@ void orc_project(const double* xy, const int32_t* cells, const uint8_t* perm, co
           const double s1 = f1[0] + f1[t] + f1[t + 1], s2 = f2[0] + f2[t] + f2[t + 1];
           const double d1 = uj[0] * f1[0] + uj[t] * f1[t] + uj[t + 1] * f1[t + 1];
           const double d2 = uj[0] * f2[0] + uj[t] * f2[t] + uj[t + 1] * f2[t + 1];
-          const double w12 = aT / 12;
+          const double w12 = aT * (1.0 / 12.0);
           r1 += w12 * (su * s1 + d1);
           r2 += w12 * (su * s2 + d2);
-          u += (aT / 3) * su;
+          u += (aT * (1.0 / 3.0)) * su;
         }
       }
       R1 += r1; R2 += r2; U += u;
