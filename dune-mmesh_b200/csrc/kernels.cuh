@@ -772,7 +772,7 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 
 // ---- shared-memory Sutherland-Hodgman, organised in convergent passes ------------------------------------------
 // lineIntersectionPoint, polygoncutting.hh:100-114 (iQ = q1 - q2, fq = q1 x q2 hoisted per clip edge)
-__device__ __noinline__ double2 line_isect(double ax, double ay, double bx, double by, double iQx, double iQy, double fq) {
+__device__ __forceinline__ double2 line_isect(double ax, double ay, double bx, double by, double iQx, double iQy, double fq) {
   double dPx = ax - bx, dPy = ay - by;
   const double scale = dPx * iQy - iQx * dPy;
   const double fp = ax * by - ay * bx;
