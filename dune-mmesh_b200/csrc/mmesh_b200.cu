@@ -61,7 +61,7 @@ struct mmb_context {
   // projection
   int64_t nnew = 0, npairs = 0, n_old = 0;
   DBuf<long long> new_off; DBuf<int32_t> new_cell, old_idx; DBuf<double> old_xy, dofs_old, dofs_new, part_a, part_b, pair_vol;
-  int dofs_ncomp = 0;
+  int dofs_ncomp = 0; int64_t max_old_idx = -1;
   std::vector<int64_t> chunk_i; std::vector<int32_t> chunk_cell_lo, chunk_cell_hi; bool chunks_ok = false;
   // pipelined DOF upload: chunk k reads old DOFs from its home index range [dof_lo[k], dof_lo[k+1]) plus a few remote ones
   bool dof_pipe_ok = false; std::vector<int64_t> dof_lo; std::vector<int32_t> remote_idx; DBuf<int32_t> d_remote_idx;
@@ -226,6 +226,23 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
   CK(cudaSetDevice(ctx->device));
   const int dim = ctx->dim, k = dim + 1;
   ctx->mesh_ok = false;
+  // the kernels trust the snapshot: reject out-of-range indices here instead of reading out of bounds on the device
+  {
+    int64_t bad = 0;
+    for (int64_t i = 0; i < nc * k; ++i) bad += (cells_host[i] < 0 || cells_host[i] >= nv);
+    for (int64_t i = 0; i < nc; ++i) {
+      const unsigned p = perm_host[i];
+      unsigned seen = 0;
+      for (int j = 0; j < k; ++j) seen |= 1u << ((p >> (2 * j)) & 3u);
+      bad += (seen != (1u << k) - 1u);                    // perm must be a permutation of 0..dim
+    }
+    if (dim == 2) for (int64_t i = 0; i < ne; ++i) {
+      const int32_t* e = edges_host + 4 * i;
+      bad += (e[0] < 0 || e[0] >= nv || e[1] < 0 || e[1] >= nv || e[2] < 0 || e[2] >= nv || e[3] < -1 || e[3] >= nv);
+    }
+    for (int64_t i = 0; i < ns * dim; ++i) bad += (facets_host[i] < 0 || facets_host[i] >= nv);
+    REQUIRE(bad == 0, MMB_ERR_INVALID_ARG, "mmb_upload_mesh: vertex index out of range or invalid corner permutation");
+  }
   ctx->nv = nv; ctx->nc = nc; ctx->ne = ne; ctx->ns = ns;
   ctx->own_lo = 0; ctx->own_hi = nc; ctx->n_halo_send = ctx->n_halo_recv = 0;
   ctx->nc_pad = (nc + 3) / 4 * 4;
@@ -587,6 +604,13 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
   REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "projection needs an uploaded 2-D mesh");
   REQUIRE(nnew >= 0 && npairs >= 0 && (nnew == 0 || (new_off_host && new_cell_host)) && (npairs == 0 || (old_xy_host && old_idx_host)),
           MMB_ERR_INVALID_ARG, "mmb_upload_pairs: null arrays");
+  {
+    int64_t bad = 0;
+    if (nnew) bad += (new_off_host[0] != 0 || new_off_host[nnew] != npairs);
+    for (int64_t i = 0; i < nnew; ++i) bad += (new_off_host[i + 1] < new_off_host[i] || new_cell_host[i] < 0 || new_cell_host[i] >= ctx->nc);
+    for (int64_t p = 0; p < npairs; ++p) bad += (old_idx_host[p] < 0);
+    REQUIRE(bad == 0, MMB_ERR_INVALID_ARG, "mmb_upload_pairs: malformed CSR (offsets, new cell or old index out of range)");
+  }
   CK(ctx->new_off.ensure(nnew + 1)); CK(ctx->new_cell.ensure(nnew + 1)); CK(ctx->old_idx.ensure(npairs + 1));
   CK(ctx->old_xy.ensure(6 * (size_t)npairs + 1)); CK(ctx->pair_vol.ensure(npairs + 1));
   const int nb = (int)grid_for(4 * nnew, PROJ_THREADS) + 64;   // + slack for chunked launches
@@ -601,6 +625,8 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
   }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->nnew = nnew; ctx->npairs = npairs;
+  ctx->max_old_idx = -1;
+  for (int64_t p = 0; p < npairs; ++p) ctx->max_old_idx = std::max<int64_t>(ctx->max_old_idx, old_idx_host[p]);
   // chunk table for the pipelined host-buffer step: new cells are listed in ascending cell order (element iteration
   // order, mmesh.hh:1143), so chunk k of the CSR writes DOFs of cells [cell_lo[k], cell_hi[k]]
   ctx->chunk_i.clear(); ctx->chunk_cell_lo.clear(); ctx->chunk_cell_hi.clear();
@@ -668,6 +694,7 @@ static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, in
 }
 static int do_project(mmb_context* ctx, int ncomp) {
   if (ctx->nnew == 0) return MMB_OK;
+  REQUIRE(ctx->max_old_idx < ctx->n_old, MMB_ERR_INVALID_ARG, "projection: a pair references an old cell beyond the DOF array");
   int nb = 0;
   TRY(project_range(ctx, ncomp, 0, ctx->nnew, 0, &nb));
   LAUNCH("reduce_partials", k_reduce_partials, 1, 1024, ctx->part_a.p, ctx->part_b.p, nb, ctx->counters.p);

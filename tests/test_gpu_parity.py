@@ -427,3 +427,30 @@ def test_projection_ragged_csr(gpu_ctx_factory, oracle):
     ctx.upload_pairs(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros((0, 6)), np.zeros(0, np.int32))
     _, mass, cov, npc = ctx.project(1, np.ones(4))
     assert (mass, cov, npc) == (0.0, 0.0, 0)
+
+
+def test_malformed_snapshots_are_rejected(gpu_ctx_factory):
+    """Out-of-range indices / malformed CSR are status codes (MMB_ERR_INVALID_ARG), never device faults."""
+    from mmesh_b200 import capi
+    m = _mesh1(10)
+    ctx = gpu_ctx_factory(2)
+    bad = m.cells.copy(); bad[5, 1] = m.nv
+    with pytest.raises(capi.MMeshError) as e:
+        ctx.upload_mesh(m.xy, bad, m.perm, m.edges, m.segs)
+    assert e.value.status == capi.MMB_ERR_INVALID_ARG
+    badp = m.perm.copy(); badp[3] = 0
+    with pytest.raises(capi.MMeshError):
+        ctx.upload_mesh(m.xy, m.cells, badp, m.edges, m.segs)
+    bade = m.edges.copy(); bade[7, 3] = -2
+    with pytest.raises(capi.MMeshError):
+        ctx.upload_mesh(m.xy, m.cells, m.perm, bade, m.segs)
+    _upload(ctx, m)
+    with pytest.raises(capi.MMeshError):      # state error: marks before any distance update
+        ctx.mark_elements(run_distance=False)
+    with pytest.raises(capi.MMeshError):      # CSR end does not match the pair count
+        ctx.upload_pairs(np.array([0, 2], np.int64), np.array([0], np.int32), np.zeros((3, 6)), np.zeros(3, np.int32))
+    ctx.upload_pairs(np.array([0, 1], np.int64), np.array([0], np.int32), np.zeros((1, 6)), np.array([9], np.int32))
+    with pytest.raises(capi.MMeshError):      # old index 9 but only 4 old DOFs
+        ctx.project(1, np.ones(4))
+    with pytest.raises(capi.MMeshError):      # shifts == NULL without resident shifts
+        ctx.adapt_step(None, 0)
