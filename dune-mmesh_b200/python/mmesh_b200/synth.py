@@ -347,6 +347,33 @@ def cached_corners(m, xy_old, cell_idx):
     return out
 
 
+def flip_case(n, jitter=0.2, seed=7):
+    """Exactly conservative projection set-up at any size (vectorised): old mesh = jittered n x n lattice, new mesh = the
+    same vertices with the OTHER diagonal in every quad; the connected component of a new triangle is its quad
+    (two old children, connectedcomponent.hh:104-127).  Returns (new-mesh snapshot arrays, pair CSR, old areas/centroids)."""
+    old = lattice2d(n, n, 1.0, 1.0, jitter=jitter, seed=seed, hilbert=False, rotate_tds=False)
+    xy = old.xy
+    q = np.arange(n * n, dtype=np.int64)
+    qi, qj = q % n, q // n
+    v00 = qj * (n + 1) + qi
+    v10, v01, v11 = v00 + 1, v00 + n + 1, v00 + n + 2
+    slash = old.cells[0::2, 2] == v11                       # old diagonal v00-v11 ('/'): T0 = (v00, v10, v11)
+    # new triangles use the other diagonal, ccw
+    n0 = np.where(slash[:, None], np.stack([v00, v10, v01], 1), np.stack([v00, v10, v11], 1))
+    n1 = np.where(slash[:, None], np.stack([v10, v11, v01], 1), np.stack([v00, v11, v01], 1))
+    cells = np.empty((2 * n * n, 3), np.int64)
+    cells[0::2], cells[1::2] = n0, n1
+    perm = pack_perm(old.vid[cells])
+    nnew = cells.shape[0]
+    new_off = np.arange(0, 2 * nnew + 1, 2, dtype=np.int64)
+    old_idx = np.repeat(np.stack([2 * q, 2 * q + 1], 1), 2, axis=0).reshape(-1).astype(np.int32)   # both old children per new cell
+    old_xy = cached_corners(old, xy, old_idx)
+    po = xy[old.cells]
+    old_vol = np.abs(cross2(po[:, 1] - po[:, 0], po[:, 2] - po[:, 0])) * 0.5
+    return dict(xy=xy, cells=cells.astype(np.int32), perm=perm, new_off=new_off, new_cell=np.arange(nnew, dtype=np.int32),
+                old_xy=old_xy, old_idx=old_idx, n_old=old.nc, old_vol=old_vol, old_centroid=po.mean(axis=1))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # 3-D (config 5): Kuhn tetrahedra on an n^3 lattice, planar interface z = 0.5
 # ---------------------------------------------------------------------------------------------------------
