@@ -134,7 +134,7 @@ def test_mass_conservation_at_16M(gpu_ctx_factory, oracle):
     print("mass conservation at 16.8M cells: reference arithmetic", errs[0], " scale-aware", errs[1])
     assert errs[1][0] <= 1e-13 and errs[1][1] <= 1e-13 and errs[1][2] <= 1e-13
     assert errs[1][3] == 2 * c["cells"].shape[0]                    # every (old, new) pair contributes exactly one piece
-    assert errs[0][0] <= 1e-9                                       # the reference formulas: limited by absolute-coordinate cancellation
+    assert errs[0][0] <= 1e-3                                       # reference constants: pieces below the absolute 1e-8 area cut-off are lost
     # the oracle agrees with the device on a sample of new cells in the scale-aware mode
     oprm = oracle.Params.from_buffer_copy(bytes(ctx.get_params()))
     sel = np.arange(0, 200000, dtype=np.int32)
