@@ -1,0 +1,52 @@
+"""The Python mirror of the reference's pybind API (mmesh_b200.grid.MMesh), written like the reference's own Python tests
+(python/dune/mmesh/test/distance.py, doc/examples/moving.py:231-252)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_distance_integral_and_user_loop(oracle):
+    from mmesh_b200 import synth
+    from mmesh_b200.grid import MMesh
+    m = synth.config1(n=64)
+    grid = MMesh(m)
+    # python/dune/mmesh/test/distance.py:24-28: the integral of the P1 distance over the unit square is 0.25
+    dist = grid.distance()
+    vol = np.abs(synth.cross2(m.xy[m.cells[:, 1]] - m.xy[m.cells[:, 0]], m.xy[m.cells[:, 2]] - m.xy[m.cells[:, 0]])) / 2
+    integral = float(np.sum(vol * dist.array()[m.cells].mean(axis=1)))
+    assert abs(integral - 0.25) < 1e-8
+    assert abs(dist(7) - dist.array()[m.cells[7]].mean()) < 1e-15
+    # doc/examples/moving.py:231-252: markElements -> ensure movement -> (adapt) -> move -> postAdapt
+    grid.indicator().init()
+    grid.indicator().maxH = 0.45 * grid.indicator().maxH        # users tune the members (test-femadaptation.cc:219-220)
+    shifts = synth.shifts_uniform(m, 0.3 * m.h, 30)
+    marked = grid.markElements()
+    d = oracle.distance_2d(m.xy, m.segs)
+    prm = oracle.Params.from_buffer_copy(bytes(grid._ctx.get_params()))
+    rm, _, rc = oracle.mark(m.xy, d, m.cells, m.perm, prm, oracle.distance_max(d))
+    assert [grid.getMark(c) for c in range(0, m.nc, 97)] == [int(v) for v in rm[::97]]
+    assert marked == (rc[0] + rc[1] > 0 or bool(np.any(oracle.mark_interface_2d(m.xy, m.segs, prm, oracle.distance_max(d)) != 0)))
+    change = grid.ensureVertexMovement(shifts)
+    valid, _, ninv = oracle.trial_validate(m.xy, shifts, m.cells)
+    assert change == (ninv > 0 and len(grid.removed) > 0) and np.array_equal(grid.coordinates(), m.xy)
+    grid.moveVertices(shifts)
+    assert np.array_equal(grid.coordinates(), oracle.move(m.xy, shifts))
+    grid.postAdapt()
+    assert not grid.preAdapt()
+    # interface movement: interface-vertex-indexed shifts
+    from mmesh_b200 import capi
+    niv = int((m.vflags & 1).sum())
+    ish = np.tile([0.0, 1e-4 * m.h], (niv, 1))
+    moved = oracle.move(m.xy, shifts)
+    if oracle.trial_validate(moved, None, m.cells)[2] > 0:      # the moved mesh has inverted cells: mmesh.hh:926-930 throws
+        with pytest.raises(capi.GridError):
+            grid.ensureInterfaceMovement(ish)
+    grid2 = MMesh(m)
+    assert len(grid2.ensureInterfaceMovement(ish)) == 0
+    grid2.moveInterface(ish)
+    iv = np.nonzero(m.vflags & 1)[0]
+    expect = m.xy.copy(); expect[iv] = expect[iv] + ish
+    assert np.array_equal(grid2.coordinates(), expect)
+    with pytest.raises(AssertionError):
+        grid.moveVertices(shifts[:-1])                          # wrong size, as the assert at mmesh.hh:1423
