@@ -926,7 +926,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
       auto& sC = sQ;
       if (nC >= 3) {                                        // cutsettriangulation.hh:55 `if (points.size() < 3) return;`
       // old DOFs and the old cell's geometry are needed only now (about every second neighbour pair is empty)
-      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0, gx = 0.0, gy = 0.0;
       Aff2 gO, gK;
       {
         const double* uo = dofs_old + (int64_t)NCOMP * __ldg(old_idx + pr);
@@ -936,6 +936,8 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
           gO = aff2_make(cx[0], cy[0], cx[1], cy[1], cx[2], cy[2]);
           const double2 g0 = sG[0][tid], g1 = sG[1][tid], g2 = sG[2][tid];
           gK.ox = g0.x; gK.oy = g0.y; gK.i00 = g1.x; gK.i01 = g1.y; gK.i10 = g2.x; gK.i11 = g2.y; gK.vol = 0.0;
+          const double du1 = u1 - u0, du2 = u2 - u0;
+          gx = du1 * gO.i00 + du2 * gO.i01; gy = du1 * gO.i10 + du2 * gO.i11;
         }
       }
       // fan (points[0], points[j-1], points[j]), cutsettriangulation.hh:57-61
@@ -944,10 +946,11 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
         const double2 P = sC[j][tid];
         double uj = 0, f1 = 0, f2 = 0;
         if (NCOMP == 3) {
-          double xo, eo;
-          aff2_local(gO, P.x, P.y, xo, eo);
-          uj = u0 * (1.0 - xo - eo) + u1 * xo + u2 * eo;
-          aff2_local(gK, P.x, P.y, f1, f2);
+          const double d0 = P.x - gO.ox, d1 = P.y - gO.oy;
+          uj = u0 + (d0 * gx + d1 * gy);                       // affine old function: u0 + grad . (x - o)
+          const double e0 = P.x - gK.ox, e1 = P.y - gK.oy;
+          f1 = e0 * gK.i00 + e1 * gK.i10;                      // barycentric coordinates in the new cell
+          f2 = e0 * gK.i01 + e1 * gK.i11;
         }
         if (j == 0) { fx = P.x; fy = P.y; fu = uj; ff1 = f1; ff2 = f2; }
         else if (j >= 2) {

@@ -788,8 +788,8 @@ static inline void aff2_local(const aff2* g, const double x[2], double* xi, doub
    P1 : local L2 projection onto the nodal basis of the id-ordered corners of K.  For a cut triangle T with
         vertices v_j the product of two linear functions is integrated exactly by
             int_T u phi = |T| * (1/12) * ( (sum_j u_j)(sum_j phi_j) + sum_j u_j phi_j ),   (1/12, 1/3: rounded constants)
-        u_j = u_old(v_j) (barycentric in the cached old cell), phi_j = barycentric coordinates of v_j in K
-        (AffineGeometry::local).  phi_0 = 1 - phi_1 - phi_2 is eliminated through int_T u = |T|/3 sum_j u_j.
+        u_j = u_old(v_j) = u0 + g.(v_j - o) with g the gradient of the affine old function, phi_j = barycentric
+        coordinates of v_j in K (J^{-T}(v_j - origin), cf. AffineGeometry::local).  phi_0 = 1 - phi_1 - phi_2 is eliminated through int_T u = |T|/3 sum_j u_j.
         Each (old,new) pair accumulates its own partial sums; pairs are then added in CSR order. */
 void orc_project(const double* xy, const int32_t* cells, const uint8_t* perm, const int64_t* new_off,
                  const int32_t* new_cell, int64_t nnew, const double* old_xy, const int32_t* old_idx,
@@ -817,11 +817,15 @@ void orc_project(const double* xy, const int32_t* cells, const uint8_t* perm, co
         for (int t = 0; t < 3; ++t) { kk[t][0] = k[t][0] - org[0]; kk[t][1] = k[t][1] - org[1]; }
         aff2_init(&gK, kk[0], kk[1], kk[2]);
         aff2_init(&gO, cu[0], cu[1], cu[2]);
+        /* u_old is affine: u(x) = u0 + g . (x - o), g = J^{-1} (u1 - u0, u2 - u0) of the cached old cell */
+        const double du1 = uo[1] - uo[0], du2 = uo[2] - uo[0];
+        const double gx = du1 * gO.i00 + du2 * gO.i01, gy = du1 * gO.i10 + du2 * gO.i11;
         for (int j = 0; j < n; ++j) {
-          double xo, eo;
-          aff2_local(&gO, pts[j], &xo, &eo);
-          uj[j] = uo[0] * (1.0 - xo - eo) + uo[1] * xo + uo[2] * eo;
-          aff2_local(&gK, pts[j], &f1[j], &f2[j]);
+          const double d0 = pts[j][0] - gO.o[0], d1 = pts[j][1] - gO.o[1];
+          uj[j] = uo[0] + (d0 * gx + d1 * gy);
+          const double e0 = pts[j][0] - gK.o[0], e1 = pts[j][1] - gK.o[1];
+          f1[j] = e0 * gK.i00 + e1 * gK.i10;                 /* barycentric coordinates of v_j in K (phi_1, phi_2) */
+          f2[j] = e0 * gK.i01 + e1 * gK.i11;
         }
       }
       double r1 = 0.0, r2 = 0.0, u = 0.0;            /* per-pair partial sums */
