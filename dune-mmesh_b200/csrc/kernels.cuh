@@ -1355,6 +1355,65 @@ k_refinement_points(const double2* __restrict__ xy, const int32_t* __restrict__ 
   if (edge_vertices) edge_vertices[i] = make_int2(k[ia], k[ib]);
 }
 
+// Refinement candidates of MMesh::adapt() (mmesh.hh:828-851): for every element with mark == 1, in index order, the
+// longest edge is inserted unless it is an interface edge or was already inserted by an earlier element.  An edge has two
+// cells, so "already inserted" <=> the face neighbour across that edge has a smaller index, is marked for refinement and
+// picked the same edge.  flag[c] = 1 for exactly the cells whose insertion point enters insert_.
+__device__ __forceinline__ int pick3(int i, int x0, int x1, int x2) { return i == 0 ? x0 : (i == 1 ? x1 : x2); }
+struct IdCorners { int k0, k1, k2, t0, t1, t2; };     // id-sorted vertex ids and their TDS positions
+__device__ __forceinline__ IdCorners id_corners(const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1,
+                                                const int32_t* __restrict__ cv2, const uint8_t* __restrict__ perm, int64_t c) {
+  const int v0 = cv0[c], v1 = cv1[c], v2 = cv2[c];
+  const unsigned p = perm[c];
+  IdCorners r;
+  r.t0 = p & 3; r.t1 = (p >> 2) & 3; r.t2 = (p >> 4) & 3;
+  r.k0 = pick3(r.t0, v0, v1, v2); r.k1 = pick3(r.t1, v0, v1, v2); r.k2 = pick3(r.t2, v0, v1, v2);
+  return r;
+}
+__global__ void __launch_bounds__(256)
+k_refine_candidates(const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2,
+                    const uint8_t* __restrict__ perm, const int8_t* __restrict__ mark, const uint8_t* __restrict__ longest,
+                    const int32_t* __restrict__ nb /*[nc][3]*/, const uint8_t* __restrict__ v_if, const unsigned long long* __restrict__ facet_keys,
+                    int ns, int64_t nc, uint8_t* __restrict__ flag) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  uint8_t f = 0;
+  if (mark[c] == 1) {
+    const IdCorners K = id_corners(cv0, cv1, cv2, perm, c);
+    const int e = longest[c];
+    const int ia = e == 2 ? 1 : 0, ib = e == 0 ? 1 : 2, io = 3 - ia - ib;      // DUNE edges 0:(0,1) 1:(0,2) 2:(1,2)
+    const int a = pick3(ia, K.k0, K.k1, K.k2), b = pick3(ib, K.k0, K.k1, K.k2);
+    bool iface = false;                                                         // MMesh::isInterface(edge), mmesh.hh:607-621
+    if (v_if[a] && v_if[b] && ns > 0) {
+      const unsigned long long key = ((unsigned long long)(unsigned)min(a, b) << 32) | (unsigned)max(a, b);
+      int lo = 0, hi = ns - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned long long km = facet_keys[mid];
+        if (km == key) { iface = true; break; }
+        if (km < key) lo = mid + 1; else hi = mid - 1;
+      }
+    }
+    if (!iface) {
+      f = 1;
+      const int n = nb[3 * c + pick3(io, K.t0, K.t1, K.t2)];                    // neighbour opposite the remaining corner
+      if (n >= 0 && n < c && mark[n] == 1) {
+        const IdCorners N = id_corners(cv0, cv1, cv2, perm, n);
+        const int en = longest[n];
+        const int ja = en == 2 ? 1 : 0, jb = en == 0 ? 1 : 2;
+        const int na = pick3(ja, N.k0, N.k1, N.k2), nbv = pick3(jb, N.k0, N.k1, N.k2);
+        if ((na == a && nbv == b) || (na == b && nbv == a)) f = 0;             // inserted_ already holds this edge id
+      }
+    }
+  }
+  flag[c] = f;
+}
+__global__ void __launch_bounds__(256)
+k_flag_interface_vertices(const int32_t* __restrict__ facets, int64_t n_entries, uint8_t* __restrict__ v_if) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_entries) v_if[facets[i]] = 1;
+}
+
 // halo exchange helpers: owned values -> contiguous send buffer, received values -> halo slots
 __global__ void __launch_bounds__(256)
 k_gather2(const double2* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, double2* __restrict__ dst) {

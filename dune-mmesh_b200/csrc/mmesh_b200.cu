@@ -52,6 +52,7 @@ struct mmb_context {
   DBuf<int32_t> wl, list_out;
   DBuf<uint32_t> block_count;
   DBuf<int32_t> tile_lo_cells, tile_lo_edges;
+  DBuf<int32_t> cell_nb; bool have_nb = false; DBuf<uint8_t> v_if, cand_flag; DBuf<unsigned long long> facet_keys;
   DBuf<Counters> counters;
   bool has_shift = false, dist_valid = false, mesh_ok = false;
   // bvh
@@ -160,6 +161,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->orient.release(); ctx->mark.release(); ctx->imark.release(); ctx->edges.release();
   ctx->wl.release(); ctx->list_out.release(); ctx->block_count.release(); ctx->counters.release();
   ctx->tile_lo_cells.release(); ctx->tile_lo_edges.release();
+  ctx->cell_nb.release(); ctx->v_if.release(); ctx->cand_flag.release(); ctx->facet_keys.release();
   ctx->seg_leaf.release(); ctx->box2.release(); ctx->seg_hint.release(); ctx->ticket.release(); ctx->tri_leaf.release(); ctx->box3.release();
   ctx->new_off.release(); ctx->new_cell.release(); ctx->old_idx.release(); ctx->old_xy.release();
   ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
@@ -298,6 +300,22 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
       for (int c = 0; c < dim; ++c) sorted[s * dim + c] = facets_host[(size_t)keyed[s].second * dim + c];
     CK(cudaMemcpyAsync(ctx->facets_sorted.p, sorted.data(), sorted.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // `sorted` is a stack-owned staging buffer
+  }
+  ctx->have_nb = false;
+  if (dim == 2) {
+    // per-vertex interface flag + sorted (min,max) facet keys: MMesh::isInterface(edge) on the device (mmesh.hh:607-621)
+    CK(ctx->v_if.ensure(nv + 1)); CK(ctx->cand_flag.ensure(ctx->nc_pad + 4)); CK(ctx->facet_keys.ensure(ns + 1));
+    CK(cudaMemsetAsync(ctx->v_if.p, 0, (size_t)nv, ctx->stream));
+    if (ns) {
+      LAUNCH("flag_interface_vertices", k_flag_interface_vertices, grid_for(2 * ns, 256), 256, ctx->facets.p, 2 * ns, ctx->v_if.p);
+      std::vector<unsigned long long> keys((size_t)ns);
+      for (int64_t s2 = 0; s2 < ns; ++s2) {
+        const unsigned a = (unsigned)facets_host[2 * s2], b = (unsigned)facets_host[2 * s2 + 1];
+        keys[(size_t)s2] = ((unsigned long long)std::min(a, b) << 32) | std::max(a, b);
+      }
+      std::sort(keys.begin(), keys.end());
+      CK(cudaMemcpy(ctx->facet_keys.p, keys.data(), (size_t)ns * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
   }
   if (dim == 2) {
     CK(ctx->seg_leaf.ensure(L)); CK(ctx->box2.ensure(2 * (size_t)L)); CK(ctx->seg_hint.ensure(nv)); CK(ctx->ticket.ensure(1));
@@ -782,6 +800,25 @@ int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host
   out.release(); ev.release();
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return MMB_ERR_CUDA; }
   return MMB_OK;
+}
+
+int mmb_upload_neighbours(mmb_context* ctx, const int32_t* cell_nb_host) {
+  if (!ctx || !cell_nb_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "neighbours need an uploaded 2-D mesh");
+  for (int64_t i = 0; i < 3 * ctx->nc; ++i)
+    REQUIRE(cell_nb_host[i] >= -1 && cell_nb_host[i] < ctx->nc, MMB_ERR_INVALID_ARG, "mmb_upload_neighbours: neighbour index out of range");
+  CK(ctx->cell_nb.ensure(3 * (size_t)ctx->nc + 1));
+  CK(cudaMemcpyAsync(ctx->cell_nb.p, cell_nb_host, 3 * (size_t)ctx->nc * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_nb = true;
+  return MMB_OK;
+}
+int mmb_refinement_candidates(mmb_context* ctx, int32_t* cells_host, int64_t cap, int64_t* n_total) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2 && ctx->have_nb, MMB_ERR_STATE, "refinement candidates need a 2-D mesh with neighbours (mmb_upload_neighbours) and marks");
+  LAUNCH("refine_candidates", k_refine_candidates, grid_for(ctx->nc, 256), 256, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p,
+         ctx->mark.p, ctx->longest.p, ctx->cell_nb.p, ctx->v_if.p, ctx->facet_keys.p, (int)ctx->ns, ctx->nc, ctx->cand_flag.p);
+  return compact_flags(ctx, ctx->cand_flag.p, ctx->nc, 1, cells_host, cap, n_total);
 }
 
 // ---- whole step -----------------------------------------------------------------------------------------

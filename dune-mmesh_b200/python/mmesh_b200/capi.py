@@ -19,7 +19,7 @@ EXPORTS = [
     "mmb_indicator_init", "mmb_move_vertices", "mmb_trial_move_validate", "mmb_invalid_cells", "mmb_legality",
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
-    "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
+    "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
     "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
@@ -281,6 +281,18 @@ class Context:
         out = np.empty(new_len.shape[0])
         self._ck(lib().mmb_project_interface_p0(self._h, C.c_int64(new_len.shape[0]), _p(new_len), _p(new_off), C.c_int64(old_idx.shape[0]),
                                                 _p(old_len), _p(old_idx), C.c_int64(dofs_old.shape[0]), _p(dofs_old), _p(out)))
+        return out
+
+    def upload_neighbours(self, nb):
+        nb = _i32(nb)
+        self._ck(lib().mmb_upload_neighbours(self._h, _p(nb)))
+
+    def refinement_candidates(self):
+        n = C.c_int64()
+        self._ck(lib().mmb_refinement_candidates(self._h, None, C.c_int64(0), C.byref(n)))
+        out = np.empty(n.value, np.int32)
+        if n.value:
+            self._ck(lib().mmb_refinement_candidates(self._h, _p(out), C.c_int64(n.value), C.byref(n)))
         return out
 
     def refinement_points(self, cells):

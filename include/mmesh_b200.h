@@ -139,6 +139,12 @@ int mmb_project_interface_p0(mmb_context* ctx, int64_t nnew, const double* new_l
    centre of the longest edge and, optionally, its two vertex indices (id order). */
 int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host, double* points_host, int32_t* edge_vertices_host);
 
+/* Refinement candidates of MMesh::adapt() (mmesh.hh:828-851): the cells (index order) whose longest edge enters insert_,
+   i.e. marked +1, edge not an interface edge, edge id not yet inserted by an earlier cell.  Needs the face neighbours
+   (cell_nb[c][k] = index of face->neighbor(k), -1 for the infinite face).  Feed the result to mmb_refinement_points. */
+int mmb_upload_neighbours(mmb_context* ctx, const int32_t* cell_nb_host);
+int mmb_refinement_candidates(mmb_context* ctx, int32_t* cells_host, int64_t cap, int64_t* n_total);
+
 /* One whole adapt step on resident data, in the reference's user-loop order (doc/examples/moving.py:231-252):
    markElements (distance + marks) -> ensureVertexMovement (trial validity) -> adapt(handle) projection of the
    uploaded pairs -> moveVertices -> in-circle legality of the moved mesh (input of the next host TDS pass).

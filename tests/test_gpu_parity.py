@@ -454,3 +454,34 @@ def test_malformed_snapshots_are_rejected(gpu_ctx_factory):
         ctx.project(1, np.ones(4))
     with pytest.raises(capi.MMeshError):      # shifts == NULL without resident shifts
         ctx.adapt_step(None, 0)
+
+
+def test_refinement_candidates_like_adapt(gpu_ctx_factory, oracle):
+    """MMesh::adapt() insertion candidates (mmesh.hh:828-851): per marked cell in index order, longest edge, skipped when it
+    is an interface edge or its edge id was inserted before; emulated here with a python set like `inserted_`."""
+    from mmesh_b200 import synth
+    for m in (_mesh1(70), synth.config2(n=90)):
+        ctx = gpu_ctx_factory(2)
+        _upload(ctx, m)
+        ctx.upload_neighbours(m.nb)
+        prm = ctx.indicator_init()
+        prm.maxH *= 0.28
+        prm.minH *= 0.2
+        ctx.set_params(prm)
+        marks, le, counts = ctx.mark_elements(run_distance=True)
+        iface = {tuple(sorted(e)) for e in m.segs.tolist()}
+        EV = [(0, 1), (0, 2), (1, 2)]
+        inserted, expect = set(), []
+        for c in np.nonzero(marks == 1)[0]:
+            k = [int(m.cells[c][(int(m.perm[c]) >> (2 * t)) & 3]) for t in range(3)]
+            e = tuple(sorted((k[EV[le[c]][0]], k[EV[le[c]][1]])))
+            if e in iface:
+                continue
+            if e not in inserted:
+                inserted.add(e)
+                expect.append(int(c))
+        got = ctx.refinement_candidates()
+        assert counts[0] > 100 and len(expect) < counts[0]          # some edges are shared by two marked cells
+        assert got.tolist() == expect
+        pts, ev = ctx.refinement_points(got)
+        assert len({tuple(sorted(x)) for x in ev.tolist()}) == len(got)      # unique edges
