@@ -1408,6 +1408,82 @@ k_refine_candidates(const int32_t* __restrict__ cv0, const int32_t* __restrict__
   }
   flag[c] = f;
 }
+// Coarsening candidates of MMesh::adapt() (mmesh.hh:853-865).  LongestEdgeRefinement::coarsening
+// (longestedgerefinement.hh:64-112) sums, per id-ordered corner, the lengths of its two element edges (edge order 0,1,2)
+// and std::sorts the three (vertex, length) pairs with a comparator that is NOT a strict weak order; libstdc++ sorts
+// <= 16 elements by insertion sort, where element i reaches the front iff comp(*i, *first), so the returned vertex is
+// the fold   y = comp(x1, x0) ? x1 : x0;   result = comp(x2, y) ? x2 : y.
+__device__ __forceinline__ bool coarsen_less(int la, double sa, bool ca, int lb, double sb, bool cb) {
+  if (la < lb) return true;                         // :95-97
+  if (sa < sb - 1e-14) return true;                 // :100
+  if (!ca && cb) return true;                       // :103-106
+  return false;
+}
+// pass 1: chosen[c] = vertex picked by a cell with mark -1 (else -1); first_claim[v] = lowest such cell index
+__global__ void __launch_bounds__(256)
+k_coarsen_choice(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1,
+                 const int32_t* __restrict__ cv2, const uint8_t* __restrict__ perm, const int8_t* __restrict__ mark,
+                 const uint8_t* __restrict__ v_if, const uint8_t* __restrict__ v_bnd, const int32_t* __restrict__ v_level,
+                 int64_t nc, int32_t* __restrict__ chosen, int32_t* __restrict__ first_claim) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  int v = -1;
+  if (mark[c] == -1) {
+    const IdCorners K = id_corners(cv0, cv1, cv2, perm, c);
+    const double2 p0 = ldg2(xy + K.k0), p1 = ldg2(xy + K.k1), p2 = ldg2(xy + K.k2);
+    const double e0 = edge_len2d(p0, p1), e1 = edge_len2d(p0, p2), e2 = edge_len2d(p1, p2);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    s0 += e0; s1 += e0;  s0 += e1; s2 += e1;  s1 += e2; s2 += e2;      // :80-90, edges 0:(0,1) 1:(0,2) 2:(1,2)
+    const int l0 = v_level[K.k0], l1 = v_level[K.k1], l2 = v_level[K.k2];
+    const bool c0 = v_if[K.k0] | v_bnd[K.k0], c1 = v_if[K.k1] | v_bnd[K.k1], c2 = v_if[K.k2] | v_bnd[K.k2];
+    const bool f1 = coarsen_less(l1, s1, c1, l0, s0, c0);
+    const int ly = f1 ? l1 : l0; const double sy = f1 ? s1 : s0; const bool cy = f1 ? c1 : c0; const int ky = f1 ? K.k1 : K.k0;
+    v = coarsen_less(l2, s2, c2, ly, sy, cy) ? K.k2 : ky;
+    atomicMin(first_claim + v, (int)c);
+  }
+  chosen[c] = v;
+}
+// pass 2: removed_.insert(id(vertex)).second  <=>  this cell is the first (lowest index) one that picked the vertex
+__global__ void __launch_bounds__(256)
+k_coarsen_flag(const int32_t* __restrict__ chosen, const int32_t* __restrict__ first_claim, int64_t nc, uint8_t* __restrict__ flag) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int v = chosen[c];
+  flag[c] = (v >= 0 && first_claim[v] == (int)c) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+k_gather_i32(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, int32_t* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+// interface loop (mmesh.hh:869-908): mark -1 -> first vertex of the element with exactly two incident interface
+// elements (isRemoveable, longestedgerefinement.hh:160-168) unless the bulk loop already put it into removed_
+__global__ void __launch_bounds__(256)
+k_if_coarsen_choice(const int2* __restrict__ segs, const int8_t* __restrict__ imark, const int32_t* __restrict__ v_ifcount,
+                    const int32_t* __restrict__ first_claim, int ns, int32_t* __restrict__ chosen, int32_t* __restrict__ first_seg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns) return;
+  int v = -1;
+  if (imark[s] == -1) {
+    const int2 sv = segs[s];
+    v = v_ifcount[sv.x] == 2 ? sv.x : (v_ifcount[sv.y] == 2 ? sv.y : -1);
+    if (v >= 0 && first_claim[v] != 0x7f7f7f7f) v = -1;
+    if (v >= 0) atomicMin(first_seg + v, s);
+  }
+  chosen[s] = v;
+}
+__global__ void __launch_bounds__(256)
+k_flag_boundary_vertices(const int4* __restrict__ edges, int64_t ne, uint8_t* __restrict__ v_bnd) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const int4 q = edges[e];
+  if (q.w < 0) { v_bnd[q.x] = 1; v_bnd[q.y] = 1; }          // hull edge: both ends are incident to the infinite vertex
+}
+__global__ void __launch_bounds__(256)
+k_count_interface_elements(const int32_t* __restrict__ facets, int64_t n_entries, int32_t* __restrict__ v_ifcount) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_entries) atomicAdd(v_ifcount + facets[i], 1);
+}
 __global__ void __launch_bounds__(256)
 k_flag_interface_vertices(const int32_t* __restrict__ facets, int64_t n_entries, uint8_t* __restrict__ v_if) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

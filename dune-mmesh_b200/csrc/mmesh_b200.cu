@@ -53,6 +53,7 @@ struct mmb_context {
   DBuf<uint32_t> block_count;
   DBuf<int32_t> tile_lo_cells, tile_lo_edges;
   DBuf<int32_t> cell_nb; bool have_nb = false; DBuf<uint8_t> v_if, cand_flag; DBuf<unsigned long long> facet_keys;
+  DBuf<uint8_t> v_bnd; DBuf<int32_t> v_ifcount, v_level, first_claim, first_seg, chosen; bool cand_ready = false, have_levels = false;
   DBuf<Counters> counters;
   bool has_shift = false, dist_valid = false, mesh_ok = false;
   // bvh
@@ -162,6 +163,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->wl.release(); ctx->list_out.release(); ctx->block_count.release(); ctx->counters.release();
   ctx->tile_lo_cells.release(); ctx->tile_lo_edges.release();
   ctx->cell_nb.release(); ctx->v_if.release(); ctx->cand_flag.release(); ctx->facet_keys.release();
+  ctx->v_bnd.release(); ctx->v_ifcount.release(); ctx->v_level.release(); ctx->first_claim.release(); ctx->first_seg.release(); ctx->chosen.release();
   ctx->seg_leaf.release(); ctx->box2.release(); ctx->seg_hint.release(); ctx->ticket.release(); ctx->tri_leaf.release(); ctx->box3.release();
   ctx->new_off.release(); ctx->new_cell.release(); ctx->old_idx.release(); ctx->old_xy.release();
   ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
@@ -301,10 +303,10 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
     CK(cudaMemcpyAsync(ctx->facets_sorted.p, sorted.data(), sorted.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // `sorted` is a stack-owned staging buffer
   }
-  ctx->have_nb = false;
+  ctx->have_nb = false; ctx->cand_ready = false; ctx->have_levels = false;
   if (dim == 2) {
     // per-vertex interface flag + sorted (min,max) facet keys: MMesh::isInterface(edge) on the device (mmesh.hh:607-621)
-    CK(ctx->v_if.ensure(nv + 1)); CK(ctx->cand_flag.ensure(ctx->nc_pad + 4)); CK(ctx->facet_keys.ensure(ns + 1));
+    CK(ctx->v_if.ensure(nv + 1)); CK(ctx->cand_flag.ensure((size_t)std::max(ctx->nc_pad, ns) + 4)); CK(ctx->facet_keys.ensure(ns + 1));
     CK(cudaMemsetAsync(ctx->v_if.p, 0, (size_t)nv, ctx->stream));
     if (ns) {
       LAUNCH("flag_interface_vertices", k_flag_interface_vertices, grid_for(2 * ns, 256), 256, ctx->facets.p, 2 * ns, ctx->v_if.p);
@@ -819,6 +821,85 @@ int mmb_refinement_candidates(mmb_context* ctx, int32_t* cells_host, int64_t cap
   LAUNCH("refine_candidates", k_refine_candidates, grid_for(ctx->nc, 256), 256, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p,
          ctx->mark.p, ctx->longest.p, ctx->cell_nb.p, ctx->v_if.p, ctx->facet_keys.p, (int)ctx->ns, ctx->nc, ctx->cand_flag.p);
   return compact_flags(ctx, ctx->cand_flag.p, ctx->nc, 1, cells_host, cap, n_total);
+}
+
+// per-mesh state of the coarsening candidates, built on first use (not part of the per-step footprint)
+static int ensure_candidate_state(mmb_context* ctx) {
+  if (ctx->cand_ready) return MMB_OK;
+  const size_t nv = (size_t)ctx->nv;
+  CK(ctx->v_bnd.ensure(nv + 1)); CK(ctx->v_ifcount.ensure(nv + 1)); CK(ctx->v_level.ensure(nv + 1));
+  CK(ctx->first_claim.ensure(nv + 1)); CK(ctx->first_seg.ensure(nv + 1));
+  CK(ctx->chosen.ensure((size_t)std::max(ctx->nc, ctx->ns) + 1));
+  CK(cudaMemsetAsync(ctx->v_bnd.p, 0, nv, ctx->stream));
+  CK(cudaMemsetAsync(ctx->v_ifcount.p, 0, nv * sizeof(int32_t), ctx->stream));
+  if (!ctx->have_levels) CK(cudaMemsetAsync(ctx->v_level.p, 0, nv * sizeof(int32_t), ctx->stream));   // VertexInfo default (mmesh.hh:132)
+  if (ctx->ne) LAUNCH("flag_boundary_vertices", k_flag_boundary_vertices, grid_for(ctx->ne, 256), 256, (const int4*)ctx->edges.p, ctx->ne, ctx->v_bnd.p);
+  if (ctx->ns) LAUNCH("count_interface_elements", k_count_interface_elements, grid_for(2 * ctx->ns, 256), 256, ctx->facets.p, 2 * ctx->ns, ctx->v_ifcount.p);
+  CK(cudaGetLastError());
+  ctx->cand_ready = true;
+  return MMB_OK;
+}
+int mmb_upload_vertex_levels(mmb_context* ctx, const int32_t* level_host) {
+  if (!ctx || !level_host) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "vertex levels need an uploaded 2-D mesh");
+  for (int64_t i = 0; i < ctx->nv; ++i)
+    REQUIRE(level_host[i] >= 0, MMB_ERR_INVALID_ARG, "mmb_upload_vertex_levels: insertionLevel is unsigned in the reference");
+  CK(ctx->v_level.ensure((size_t)ctx->nv + 1));
+  CK(cudaMemcpyAsync(ctx->v_level.p, level_host, (size_t)ctx->nv * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_levels = true;
+  return MMB_OK;
+}
+static int bulk_coarsen_choice(mmb_context* ctx) {
+  TRY(ensure_candidate_state(ctx));
+  CK(cudaMemsetAsync(ctx->first_claim.p, 0x7f, (size_t)ctx->nv * sizeof(int32_t), ctx->stream));
+  LAUNCH("coarsen_choice", k_coarsen_choice, grid_for(ctx->nc, 256), 256, (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p,
+         ctx->perm.p, ctx->mark.p, ctx->v_if.p, ctx->v_bnd.p, ctx->v_level.p, ctx->nc, ctx->chosen.p, ctx->first_claim.p);
+  return MMB_OK;
+}
+int mmb_coarsening_candidates(mmb_context* ctx, int32_t* cells_host, int32_t* vertices_host, int64_t cap, int64_t* n_total) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2 && ctx->ne > 0, MMB_ERR_STATE, "coarsening candidates need a 2-D mesh with edges and marks");
+  TRY(bulk_coarsen_choice(ctx));
+  LAUNCH("coarsen_flag", k_coarsen_flag, grid_for(ctx->nc, 256), 256, ctx->chosen.p, ctx->first_claim.p, ctx->nc, ctx->cand_flag.p);
+  int64_t tot = 0;
+  TRY(compact_flags(ctx, ctx->cand_flag.p, ctx->nc, 1, cells_host, cap, &tot));
+  if (n_total) *n_total = tot;
+  const int64_t n = std::min(cap, tot);
+  if (vertices_host && n > 0) {
+    CK(ctx->wl.ensure((size_t)n));
+    LAUNCH("gather_i32", k_gather_i32, grid_for(n, 256), 256, ctx->chosen.p, ctx->list_out.p, n, ctx->wl.p);
+    CK(cudaMemcpyAsync(vertices_host, ctx->wl.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return MMB_OK;
+}
+int mmb_interface_candidates(mmb_context* ctx, int32_t* insert_segs_host, int64_t cap_insert, int64_t* n_insert,
+                             int32_t* remove_segs_host, int32_t* remove_vertices_host, int64_t cap_remove, int64_t* n_remove) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2 && ctx->ne > 0, MMB_ERR_STATE, "interface candidates need a 2-D mesh with edges and marks");
+  if (n_insert) *n_insert = 0;
+  if (n_remove) *n_remove = 0;
+  if (ctx->ns == 0) return MMB_OK;
+  // insert_: every interface element with mark +1 (its edge id cannot be in inserted_: the bulk loop skips interface edges)
+  TRY(compact_flags(ctx, (const uint8_t*)ctx->imark.p, ctx->ns, 1, insert_segs_host, cap_insert, n_insert));
+  // remove_: removed_ already holds what the bulk loop chose
+  TRY(bulk_coarsen_choice(ctx));
+  CK(cudaMemsetAsync(ctx->first_seg.p, 0x7f, (size_t)ctx->nv * sizeof(int32_t), ctx->stream));
+  LAUNCH("if_coarsen_choice", k_if_coarsen_choice, grid_for(ctx->ns, 256), 256, (const int2*)ctx->facets.p, ctx->imark.p, ctx->v_ifcount.p,
+         ctx->first_claim.p, (int)ctx->ns, ctx->chosen.p, ctx->first_seg.p);
+  LAUNCH("coarsen_flag", k_coarsen_flag, grid_for(ctx->ns, 256), 256, ctx->chosen.p, ctx->first_seg.p, ctx->ns, ctx->cand_flag.p);
+  int64_t tot = 0;
+  TRY(compact_flags(ctx, ctx->cand_flag.p, ctx->ns, 1, remove_segs_host, cap_remove, &tot));
+  if (n_remove) *n_remove = tot;
+  const int64_t n = std::min(cap_remove, tot);
+  if (remove_vertices_host && n > 0) {
+    CK(ctx->wl.ensure((size_t)n));
+    LAUNCH("gather_i32", k_gather_i32, grid_for(n, 256), 256, ctx->chosen.p, ctx->list_out.p, n, ctx->wl.p);
+    CK(cudaMemcpyAsync(remove_vertices_host, ctx->wl.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return MMB_OK;
 }
 
 // ---- whole step -----------------------------------------------------------------------------------------

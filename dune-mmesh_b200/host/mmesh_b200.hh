@@ -35,6 +35,18 @@ struct Snapshot {
   std::vector<std::array<int32_t, dim>> facets;     // interface facets
   std::vector<uint8_t> vflags;                      // bit0 isInterface, bit1 boundaryFlag == 1 (host-side use only)
   std::vector<int32_t> interfaceVertices;           // interface leaf vertex index -> bulk vertex index (interface/indexsets.hh:238-277)
+  std::vector<std::array<int32_t, 3>> neighbours;   // 2-D, optional: face->neighbor(k) cell index, -1 = infinite face
+  std::vector<int32_t> insertionLevel;              // optional: VertexInfo::insertionLevel (mmesh.hh:132), default 0
+};
+
+// insert_ / remove_ of MMesh::adapt() before adapt_() (mmesh.hh:826-908), as index lists
+struct AdaptCandidates {
+  std::vector<int32_t> insertCells;                       // cells whose longest edge is bisected (element order)
+  std::vector<std::array<double, 2>> insertPoints;        // RefinementInsertionPoint::point (edge centre)
+  std::vector<std::array<int32_t, 2>> insertEdgeVertices; // ip.v0, ip.v1
+  std::vector<int32_t> removeCells, removeVertices;       // bulk loop: (element, vertex to remove)
+  std::vector<int32_t> insertSegments;                    // interface elements to bisect
+  std::vector<int32_t> removeSegments, removeSegmentVertices;
 };
 
 template <int dim> class MMesh;
@@ -96,6 +108,10 @@ class MMesh {
                           s.cells.empty() ? nullptr : s.cells[0].data(), s.perm.data(), (int64_t)s.edges.size(),
                           s.edges.empty() ? nullptr : s.edges[0].data(), (int64_t)s.facets.size(),
                           s.facets.empty() ? nullptr : s.facets[0].data()));
+    if (dim == 2 && s.neighbours.size() == s.cells.size() && !s.cells.empty())
+      check(mmb_upload_neighbours(ctx_, s.neighbours[0].data()));
+    if (dim == 2 && s.insertionLevel.size() == s.x.size() && !s.x.empty())
+      check(mmb_upload_vertex_levels(ctx_, s.insertionLevel.data()));
     marks_.assign(s.cells.size(), 0);
     refineMarked_ = coarsenMarked_ = 0;
     removed_.clear();
@@ -183,6 +199,36 @@ class MMesh {
     return true;
   }
   int longestEdge(std::size_t cellIndex) const { return longest_.at(cellIndex); }    // longestedgerefinement.hh:41-57
+  //! the two candidate loops of adapt() (mmesh.hh:826-908) after markElements(); needs Snapshot::neighbours (2-D).
+  //! Vertices already in removed() (from ensureVertexMovement) are filtered here like removed_.insert(...).second.
+  AdaptCandidates adaptCandidates() {
+    static_assert(dim == 2 || dim == 3, "");
+    AdaptCandidates a;
+    if (dim != 2) throw InvalidStateException("adaptCandidates: 2-D only");
+    int64_t n = 0;
+    check(mmb_refinement_candidates(ctx_, nullptr, 0, &n));
+    a.insertCells.resize((std::size_t)n); a.insertPoints.resize((std::size_t)n); a.insertEdgeVertices.resize((std::size_t)n);
+    if (n > 0) {
+      check(mmb_refinement_candidates(ctx_, a.insertCells.data(), n, &n));
+      check(mmb_refinement_points(ctx_, n, a.insertCells.data(), a.insertPoints[0].data(), a.insertEdgeVertices[0].data()));
+    }
+    check(mmb_coarsening_candidates(ctx_, nullptr, nullptr, 0, &n));
+    std::vector<int32_t> rc((std::size_t)n), rv((std::size_t)n);
+    if (n > 0) check(mmb_coarsening_candidates(ctx_, rc.data(), rv.data(), n, &n));
+    auto seen = [&](int32_t v) { for (int32_t r : removed_) if (r == v) return true; return false; };
+    for (std::size_t i = 0; i < rc.size(); ++i)
+      if (!seen(rv[i])) { a.removeCells.push_back(rc[i]); a.removeVertices.push_back(rv[i]); }
+    if (!snap_->facets.empty()) {
+      int64_t ni = 0, nr = 0;
+      check(mmb_interface_candidates(ctx_, nullptr, 0, &ni, nullptr, nullptr, 0, &nr));
+      a.insertSegments.resize((std::size_t)ni);
+      std::vector<int32_t> rs((std::size_t)nr), rsv((std::size_t)nr);
+      check(mmb_interface_candidates(ctx_, a.insertSegments.data(), ni, &ni, rs.data(), rsv.data(), nr, &nr));
+      for (std::size_t i = 0; i < rs.size(); ++i)
+        if (!seen(rsv[i])) { a.removeSegments.push_back(rs[i]); a.removeSegmentVertices.push_back(rsv[i]); }
+    }
+    return a;
+  }
   bool preAdapt() const { return coarsenMarked_ > 0 || !removed_.empty(); }          // mmesh.hh:762-765 (bulk part)
   void postAdapt() {                                                                  // mmesh.hh:1456-1474
     std::fill(marks_.begin(), marks_.end(), 0);

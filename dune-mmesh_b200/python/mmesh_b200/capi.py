@@ -19,7 +19,7 @@ EXPORTS = [
     "mmb_indicator_init", "mmb_move_vertices", "mmb_trial_move_validate", "mmb_invalid_cells", "mmb_legality",
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
-    "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
+    "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
     "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
@@ -294,6 +294,33 @@ class Context:
         if n.value:
             self._ck(lib().mmb_refinement_candidates(self._h, _p(out), C.c_int64(n.value), C.byref(n)))
         return out
+
+    def upload_vertex_levels(self, levels):
+        levels = _i32(levels)
+        self._ck(lib().mmb_upload_vertex_levels(self._h, _p(levels)))
+
+    def coarsening_candidates(self):
+        """(cells, vertices) of remove_ after the bulk loop of adapt() (mmesh.hh:853-865)."""
+        n = C.c_int64()
+        self._ck(lib().mmb_coarsening_candidates(self._h, None, None, C.c_int64(0), C.byref(n)))
+        cells = np.empty(n.value, np.int32)
+        verts = np.empty(n.value, np.int32)
+        if n.value:
+            self._ck(lib().mmb_coarsening_candidates(self._h, _p(cells), _p(verts), C.c_int64(n.value), C.byref(n)))
+        return cells, verts
+
+    def interface_candidates(self):
+        """(insert_segs, remove_segs, remove_vertices) of the interface loop of adapt() (mmesh.hh:869-908)."""
+        ni, nr = C.c_int64(), C.c_int64()
+        self._ck(lib().mmb_interface_candidates(self._h, None, C.c_int64(0), C.byref(ni), None, None, C.c_int64(0), C.byref(nr)))
+        ins = np.empty(ni.value, np.int32)
+        rs = np.empty(nr.value, np.int32)
+        rv = np.empty(nr.value, np.int32)
+        if ni.value or nr.value:
+            self._ck(lib().mmb_interface_candidates(self._h, _p(ins) if ni.value else None, C.c_int64(ni.value), C.byref(ni),
+                                                    _p(rs) if nr.value else None, _p(rv) if nr.value else None,
+                                                    C.c_int64(nr.value), C.byref(nr)))
+        return ins, rs, rv
 
     def refinement_points(self, cells):
         cells = _i32(cells)

@@ -94,6 +94,10 @@ class MMesh:
         x = m.xy if m.dim == 2 else m.xyz
         facets = m.segs if m.dim == 2 else m.tris
         self._ctx.upload_mesh(x, m.cells, m.perm, getattr(m, "edges", None), facets)
+        if m.dim == 2 and getattr(m, "nb", None) is not None:
+            self._ctx.upload_neighbours(m.nb)                      # face->neighbor(k), needed by adaptCandidates
+        if m.dim == 2 and getattr(m, "insertion_level", None) is not None:
+            self._ctx.upload_vertex_levels(m.insertion_level)
 
     # ---- movement ----
     def moveVertices(self, shifts):
@@ -149,6 +153,22 @@ class MMesh:
             self._imarks = self._ctx.mark_interface()
             change = change or bool(np.any(self._imarks != 0))
         return bool(change)
+
+    def adaptCandidates(self):
+        """insert_ / remove_ of adapt() before adapt_() (mmesh.hh:826-908), 2-D: dict of index lists + insertion points.
+        Vertices already in self.removed (ensureVertexMovement) are filtered like removed_.insert(...).second."""
+        assert self._m.dim == 2
+        ins = self._ctx.refinement_candidates()
+        pts, ev = self._ctx.refinement_points(ins) if len(ins) else (np.zeros((0, 2)), np.zeros((0, 2), np.int32))
+        rc, rv = self._ctx.coarsening_candidates()
+        keep = np.array([v not in self.removed for v in rv.tolist()], bool)
+        out = dict(insert_cells=ins, insert_points=pts, insert_edge_vertices=ev,
+                   remove_cells=rc[keep], remove_vertices=rv[keep])
+        if self._ctx.ns:
+            si, rs, rsv = self._ctx.interface_candidates()
+            keep = np.array([v not in self.removed for v in rsv.tolist()], bool)
+            out.update(insert_segments=si, remove_segments=rs[keep], remove_segment_vertices=rsv[keep])
+        return out
 
     def getMark(self, element_index):
         return int(self._marks[element_index])

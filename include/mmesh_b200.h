@@ -145,6 +145,23 @@ int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host
 int mmb_upload_neighbours(mmb_context* ctx, const int32_t* cell_nb_host);
 int mmb_refinement_candidates(mmb_context* ctx, int32_t* cells_host, int64_t cap, int64_t* n_total);
 
+/* Coarsening candidates of MMesh::adapt() (mmesh.hh:853-865): for every cell with mark -1, in index order, the vertex
+   LongestEdgeRefinement::coarsening picks (longestedgerefinement.hh:64-112: per-corner sum of element edge lengths,
+   insertionLevel, interface/boundary constraint; std::sort of libstdc++ reproduced), kept only when
+   removed_.insert(id) succeeds, i.e. for the first cell choosing that vertex.  removed_ is taken as empty on entry (the
+   host filters against what ensureVertexMovement already put there).  Output: (cell, vertex) pairs in cell order.
+   Boundary vertices (atBoundary, :114-120) are derived from the hull edges of the uploaded edge quads, interface
+   vertices from the facets; mmb_upload_vertex_levels supplies VertexInfo::insertionLevel (default 0, mmesh.hh:132).
+   Single-GPU snapshots only: a shard's edge list covers its owned edges, not the halo's. */
+int mmb_upload_vertex_levels(mmb_context* ctx, const int32_t* insertion_level_host);
+int mmb_coarsening_candidates(mmb_context* ctx, int32_t* cells_host, int32_t* vertices_host, int64_t cap, int64_t* n_total);
+/* Interface loop of MMesh::adapt() (mmesh.hh:869-908) after mmb_mark_interface: insert_ = interface elements with
+   mark +1 (refinement point = element centre); remove_ = for mark -1 the first element vertex with exactly two
+   incident interface elements (isRemoveable, longestedgerefinement.hh:160-168), dropped when the bulk loop or an
+   earlier interface element already removed it.  Facet rows are the interface elements' vertex order. */
+int mmb_interface_candidates(mmb_context* ctx, int32_t* insert_segs_host, int64_t cap_insert, int64_t* n_insert,
+                             int32_t* remove_segs_host, int32_t* remove_vertices_host, int64_t cap_remove, int64_t* n_remove);
+
 /* One whole adapt step on resident data, in the reference's user-loop order (doc/examples/moving.py:231-252):
    markElements (distance + marks) -> ensureVertexMovement (trial validity) -> adapt(handle) projection of the
    uploaded pairs -> moveVertices -> in-circle legality of the moved mesh (input of the next host TDS pass).

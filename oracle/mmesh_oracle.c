@@ -565,6 +565,124 @@ void orc_mark_interface_2d(const double* xy, const int32_t* segs, int64_t ns, co
     mark[s] = (int8_t)(coarse > 0 ? -1 : (refine > 0 ? 1 : 0));
   }
 }
+/* longestedgerefinement.hh:92-112: the comparator handed to std::sort (a, b = (vertex, summed edge length)) */
+typedef struct { int idx; int64_t level; double len; int constrained; } coarsen_key;
+static inline int coarsen_less(const coarsen_key* a, const coarsen_key* b) {
+  if (a->level < b->level) return 1;                    /* :95-97 */
+  if (a->len < b->len - 1e-14) return 1;                /* :100 */
+  if (!a->constrained && b->constrained) return 1;      /* :103-106 */
+  return 0;
+}
+/* libstdc++ std::sort on <= 16 elements is __insertion_sort (bits/stl_algo.h): element i moves to the front iff
+   comp(*i, *first); otherwise __unguarded_linear_insert shifts it left while comp(val, *next). */
+static void insertion_sort_keys(coarsen_key* v, int n) {
+  for (int i = 1; i < n; ++i) {
+    coarsen_key val = v[i];
+    if (coarsen_less(&val, &v[0])) {
+      for (int j = i; j > 0; --j) v[j] = v[j - 1];
+      v[0] = val;
+    } else {
+      int j = i;
+      while (coarsen_less(&val, &v[j - 1])) { v[j] = v[j - 1]; --j; }
+      v[j] = val;
+    }
+  }
+}
+void orc_coarsening_order(int n, const int64_t* level, const double* len, const uint8_t* constrained, int* order) {
+  coarsen_key v[8];
+  if (n > 8) n = 8;
+  for (int k = 0; k < n; ++k) { v[k].idx = k; v[k].level = level[k]; v[k].len = len[k]; v[k].constrained = constrained[k]; }
+  insertion_sort_keys(v, n);
+  for (int k = 0; k < n; ++k) order[k] = v[k].idx;
+}
+int orc_coarsening_choice_2d(const double corners6[6], const int64_t level[3], const uint8_t constrained[3]) {
+  static const int EV[3][2] = { { 0, 1 }, { 0, 2 }, { 1, 2 } };
+  coarsen_key v[3];
+  for (int k = 0; k < 3; ++k) { v[k].idx = k; v[k].level = level[k]; v[k].len = 0.0; v[k].constrained = constrained[k]; }
+  for (int i = 0; i < 3; ++i) {                          /* :80-90 */
+    const double len = edge_len2d(corners6 + 2 * EV[i][0], corners6 + 2 * EV[i][1]);
+    v[EV[i][0]].len += len; v[EV[i][1]].len += len;
+  }
+  insertion_sort_keys(v, 3);
+  return v[0].idx;
+}
+/* tiny open-addressing set of 64-bit keys (inserted_ / removed_ of mmesh.hh:2022-2023) */
+typedef struct { uint64_t* slot; uint64_t mask; } keyset;
+static int keyset_init(keyset* s, int64_t n) {
+  uint64_t cap = 16; while (cap < (uint64_t)(2 * n + 2)) cap <<= 1;
+  s->slot = (uint64_t*)malloc(cap * sizeof(uint64_t)); s->mask = cap - 1;
+  if (!s->slot) return 0;
+  memset(s->slot, 0xff, cap * sizeof(uint64_t));
+  return 1;
+}
+static int keyset_insert(keyset* s, uint64_t key) {       /* 1 if newly inserted */
+  uint64_t h = (key * 0x9E3779B97F4A7C15ull) & s->mask;
+  while (s->slot[h] != ~0ull) { if (s->slot[h] == key) return 0; h = (h + 1) & s->mask; }
+  s->slot[h] = key; return 1;
+}
+static int keyset_has(const keyset* s, uint64_t key) {
+  uint64_t h = (key * 0x9E3779B97F4A7C15ull) & s->mask;
+  while (s->slot[h] != ~0ull) { if (s->slot[h] == key) return 1; h = (h + 1) & s->mask; }
+  return 0;
+}
+static inline uint64_t edge_key(int a, int b) { return a < b ? ((uint64_t)a << 32) | (uint32_t)b : ((uint64_t)b << 32) | (uint32_t)a; }
+void orc_adapt_candidates_2d(const double* xy, int64_t nv, const int32_t* cells, const uint8_t* perm, int64_t nc,
+                             const int32_t* cell_nb, const int8_t* mark, const uint8_t* longest_edge,
+                             const int32_t* segs, int64_t ns, const int8_t* imark, const int32_t* vertex_level,
+                             int32_t* ins_cells, int64_t* n_ins, int32_t* rem_cells, int32_t* rem_vertices, int64_t* n_rem,
+                             int32_t* ins_segs, int64_t* n_ins_segs, int32_t* rem_segs, int32_t* rem_seg_vertices,
+                             int64_t* n_rem_segs) {
+  static const int EV[3][2] = { { 0, 1 }, { 0, 2 }, { 1, 2 } };
+  uint8_t* v_if = (uint8_t*)calloc((size_t)nv + 1, 1);    /* VertexInfo::isInterface */
+  uint8_t* v_bnd = (uint8_t*)calloc((size_t)nv + 1, 1);   /* atBoundary(v): incident to the infinite vertex (:114-120) */
+  int32_t* v_cnt = (int32_t*)calloc((size_t)nv + 1, sizeof(int32_t));   /* incident interface elements (:160-168) */
+  keyset iface, inserted, removed;
+  keyset_init(&iface, ns); keyset_init(&inserted, nc + ns); keyset_init(&removed, nc + ns);
+  for (int64_t s = 0; s < ns; ++s) {
+    const int a = segs[2 * s], b = segs[2 * s + 1];
+    v_if[a] = v_if[b] = 1; v_cnt[a]++; v_cnt[b]++;
+    keyset_insert(&iface, edge_key(a, b));
+  }
+  for (int64_t c = 0; c < nc; ++c)
+    for (int k = 0; k < 3; ++k)
+      if (cell_nb[3 * c + k] < 0) { v_bnd[cells[3 * c + (k + 1) % 3]] = 1; v_bnd[cells[3 * c + (k + 2) % 3]] = 1; }
+  int64_t ni = 0, nr = 0;
+  for (int64_t c = 0; c < nc; ++c) {                      /* mmesh.hh:828-866 */
+    int k[3];
+    for (int t = 0; t < 3; ++t) k[t] = cells[3 * c + ((perm[c] >> (2 * t)) & 3)];
+    if (mark[c] == 1) {
+      const int e = longest_edge[c];
+      const int a = k[EV[e][0]], b = k[EV[e][1]];
+      if (!keyset_has(&iface, edge_key(a, b)))            /* :844 isInterface(ip.edge) */
+        if (keyset_insert(&inserted, edge_key(a, b))) ins_cells[ni++] = (int32_t)c;
+    } else if (mark[c] == -1) {
+      double cr[6]; int64_t lev[3]; uint8_t con[3];
+      for (int t = 0; t < 3; ++t) {
+        cr[2 * t] = xy[2 * (int64_t)k[t]]; cr[2 * t + 1] = xy[2 * (int64_t)k[t] + 1];
+        lev[t] = vertex_level ? vertex_level[k[t]] : 0;
+        con[t] = (uint8_t)(v_if[k[t]] || v_bnd[k[t]]);
+      }
+      const int v = k[orc_coarsening_choice_2d(cr, lev, con)];
+      if (keyset_insert(&removed, (uint64_t)v)) { rem_cells[nr] = (int32_t)c; rem_vertices[nr] = v; ++nr; }
+    }
+  }
+  *n_ins = ni; *n_rem = nr;
+  int64_t nis = 0, nrs = 0;
+  if (imark) {
+    for (int64_t s = 0; s < ns; ++s) {                    /* mmesh.hh:869-908 */
+      if (imark[s] == 1) {
+        if (keyset_insert(&inserted, edge_key(segs[2 * s], segs[2 * s + 1]))) ins_segs[nis++] = (int32_t)s;
+      } else if (imark[s] == -1) {
+        int v = -1;
+        for (int j = 0; j < 2 && v < 0; ++j) if (v_cnt[segs[2 * s + j]] == 2) v = segs[2 * s + j];
+        if (v >= 0 && keyset_insert(&removed, (uint64_t)v)) { rem_segs[nrs] = (int32_t)s; rem_seg_vertices[nrs] = v; ++nrs; }
+      }
+    }
+  }
+  if (n_ins_segs) *n_ins_segs = nis;
+  if (n_rem_segs) *n_rem_segs = nrs;
+  free(v_if); free(v_bnd); free(v_cnt); free(iface.slot); free(inserted.slot); free(removed.slot);
+}
 /* 3-D: 6 edges in DUNE tetrahedron edge order; coarsening disabled (ratioindicator.hh:151-156) so only the
    refine count decides; volume / circumradius cannot influence the result and are not evaluated. */
 void orc_mark_3d(const double* xyz, const double* dist, const int32_t* cells, const uint8_t* perm, int64_t nc,

@@ -117,6 +117,27 @@ void orc_project_interface_p0(const double* new_len, const int64_t* new_off, int
                               const double* old_len, const int32_t* old_idx,
                               const double* dofs_old, double* dofs_new);
 
+/* ---- MMesh::adapt() candidate loops (mmesh.hh:826-908) -------------------------------------------------------
+   LongestEdgeRefinement::coarsening (longestedgerefinement.hh:64-112) on the id-ordered corners of one triangle:
+   returns the element-local corner index std::sort puts first.  The comparator is not a strict weak order, so the
+   result depends on the sort: this follows libstdc++'s insertion sort (n <= 16), the reference's toolchain;
+   tests/native/sort_pin.cc pins it against the real std::sort. */
+void orc_coarsening_order(int n, const int64_t* level, const double* len, const uint8_t* constrained, int* order);
+int orc_coarsening_choice_2d(const double corners6[6], const int64_t level[3], const uint8_t constrained[3]);
+/* Both loops of adapt() up to (not including) adapt_():
+   bulk: mark +1 -> insert_ entry unless the longest edge is an interface edge or its id is already in inserted_;
+         mark -1 -> remove_ entry unless the chosen vertex is already in removed_ (both sets start empty);
+   interface: mark +1 -> insert_ (segment midpoint), mark -1 -> first vertex with exactly two incident interface
+         elements (isRemoveable), deduplicated against removed_ (which the bulk loop filled first).
+   cell_nb[c][k] = face->neighbor(k) (-1 = infinite face); vertex_level = VertexInfo::insertionLevel.
+   Output arrays must hold nc (bulk) / ns (interface) entries; imark may be NULL (interface loop skipped). */
+void orc_adapt_candidates_2d(const double* xy, int64_t nv, const int32_t* cells, const uint8_t* perm, int64_t nc,
+                             const int32_t* cell_nb, const int8_t* mark, const uint8_t* longest_edge,
+                             const int32_t* segs, int64_t ns, const int8_t* imark, const int32_t* vertex_level,
+                             int32_t* ins_cells, int64_t* n_ins, int32_t* rem_cells, int32_t* rem_vertices, int64_t* n_rem,
+                             int32_t* ins_segs, int64_t* n_ins_segs, int32_t* rem_segs, int32_t* rem_seg_vertices,
+                             int64_t* n_rem_segs);
+
 /* OpenMP threads used by the batch loops (the reference is single-threaded per rank; 1 by default) */
 void orc_set_threads(int n);
 int orc_num_threads(void);

@@ -200,6 +200,47 @@ def mark_interface_2d(xy, segs, prm, maxDist):
     return m
 
 
+def coarsening_order(level, length, constrained):
+    """libstdc++ insertion-sort order of the coarsening comparator (longestedgerefinement.hh:92-112)."""
+    level = np.ascontiguousarray(level, np.int64)
+    length = _f64(length)
+    constrained = np.ascontiguousarray(constrained, np.uint8)
+    n = level.shape[0]
+    order = (C.c_int * n)()
+    lib().orc_coarsening_order(C.c_int(n), _p(level), _p(length), _p(constrained), order)
+    return list(order)
+
+
+def coarsening_choice_2d(corners, level, constrained):
+    corners = _f64(corners)
+    level = np.ascontiguousarray(level, np.int64)
+    constrained = np.ascontiguousarray(constrained, np.uint8)
+    lib().orc_coarsening_choice_2d.restype = C.c_int
+    return int(lib().orc_coarsening_choice_2d(_p(corners), _p(level), _p(constrained)))
+
+
+def adapt_candidates_2d(xy, cells, perm, cell_nb, mark, longest_edge, segs, imark=None, vertex_level=None):
+    """Both candidate loops of MMesh::adapt() (mmesh.hh:826-908).  Returns dict of int32 arrays."""
+    xy, cells, cell_nb, segs = _f64(xy), _i32(cells), _i32(cell_nb), _i32(segs).reshape(-1, 2)
+    perm = np.ascontiguousarray(perm, np.uint8)
+    mark = np.ascontiguousarray(mark, np.int8)
+    longest_edge = np.ascontiguousarray(longest_edge, np.uint8)
+    nv, nc, ns = xy.shape[0], cells.shape[0], segs.shape[0]
+    imark_a = None if imark is None else np.ascontiguousarray(imark, np.int8)
+    lev = None if vertex_level is None else _i32(vertex_level)
+    ins = np.empty(nc, np.int32); remc = np.empty(nc, np.int32); remv = np.empty(nc, np.int32)
+    inss = np.empty(max(ns, 1), np.int32); rems = np.empty(max(ns, 1), np.int32); remsv = np.empty(max(ns, 1), np.int32)
+    n = [C.c_int64() for _ in range(4)]
+    lib().orc_adapt_candidates_2d(_p(xy), C.c_int64(nv), _p(cells), _p(perm), C.c_int64(nc), _p(cell_nb), _p(mark),
+                                  _p(longest_edge), _p(segs), C.c_int64(ns),
+                                  None if imark_a is None else _p(imark_a), None if lev is None else _p(lev),
+                                  _p(ins), C.byref(n[0]), _p(remc), _p(remv), C.byref(n[1]),
+                                  _p(inss), C.byref(n[2]), _p(rems), _p(remsv), C.byref(n[3]))
+    return dict(insert_cells=ins[:n[0].value].copy(), remove_cells=remc[:n[1].value].copy(),
+                remove_vertices=remv[:n[1].value].copy(), insert_segs=inss[:n[2].value].copy(),
+                remove_segs=rems[:n[3].value].copy(), remove_seg_vertices=remsv[:n[3].value].copy())
+
+
 def cell_geometry_2d(xy, cell, perm):
     xy, cell = _f64(xy), _i32(cell)
     ctr = np.empty(2)

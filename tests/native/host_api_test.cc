@@ -24,6 +24,8 @@ int main(int argc, char** argv) {
   for (auto& p : s.perm) { int t; in >> t; p = (uint8_t)t; }
   for (auto& e : s.edges) in >> e[0] >> e[1] >> e[2] >> e[3];
   for (auto& f : s.facets) in >> f[0] >> f[1];
+  s.neighbours.resize(nc);
+  for (auto& n : s.neighbours) in >> n[0] >> n[1] >> n[2];
   try {
     MMesh<2> grid(0);
     grid.setSnapshot(s);
@@ -37,6 +39,22 @@ int main(int argc, char** argv) {
     std::printf("\nlongest");
     for (std::size_t c = 0; c < nc; ++c) std::printf(" %d", grid.longestEdge(c));
     std::printf("\nmaxdist %.17g\n", grid.distance().maximum());
+    {                                             // the candidate loops of adapt() (mmesh.hh:826-908)
+      const AdaptCandidates a = grid.adaptCandidates();
+      std::printf("insertCells");
+      for (int32_t c : a.insertCells) std::printf(" %d", c);
+      std::printf("\ninsertPoints");
+      for (auto& p : a.insertPoints) std::printf(" %.17g %.17g", p[0], p[1]);
+      std::printf("\nremoveCells");
+      for (int32_t c : a.removeCells) std::printf(" %d", c);
+      std::printf("\nremoveVertices");
+      for (int32_t c : a.removeVertices) std::printf(" %d", c);
+      std::printf("\ninsertSegments");
+      for (int32_t c : a.insertSegments) std::printf(" %d", c);
+      std::printf("\nremoveSegmentVertices");
+      for (int32_t c : a.removeSegmentVertices) std::printf(" %d", c);
+      std::printf("\n");
+    }
     const bool change = grid.ensureVertexMovement(shifts);
     std::printf("change %d\nremoved", (int)change);
     for (int32_t v : grid.removed()) std::printf(" %d", v);

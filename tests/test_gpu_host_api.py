@@ -34,7 +34,7 @@ def test_host_class_user_loop(oracle, tmp_path):
     f = tmp_path / "snap.txt"
     with open(f, "w") as out:
         out.write("%d %d %d %d\n" % (m.nv, m.nc, m.edges.shape[0], m.segs.shape[0]))
-        for arr, fmt in ((m.xy, "%.17g"), (s, "%.17g"), (m.vflags, "%d"), (m.cells, "%d"), (m.perm, "%d"), (m.edges, "%d"), (m.segs, "%d")):
+        for arr, fmt in ((m.xy, "%.17g"), (s, "%.17g"), (m.vflags, "%d"), (m.cells, "%d"), (m.perm, "%d"), (m.edges, "%d"), (m.segs, "%d"), (m.nb, "%d")):
             np.savetxt(out, np.asarray(arr).reshape(len(arr), -1), fmt=fmt)
     res = subprocess.run([EXE, str(f)], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stderr
@@ -49,6 +49,20 @@ def test_host_class_user_loop(oracle, tmp_path):
     assert np.array_equal(np.array(lines["longest"], int), le)
     assert float(lines["maxdist"][0]) == oracle.distance_max(d)
     assert int(lines["marked"][0]) == int(counts[0] + counts[1] > 0 or True)
+    imark = oracle.mark_interface_2d(m.xy, m.segs, prm, oracle.distance_max(d))
+    cand = oracle.adapt_candidates_2d(m.xy, m.cells, m.perm, m.nb, marks, le, m.segs, imark, None)
+    assert [int(v) for v in lines["insertCells"]] == cand["insert_cells"].tolist()
+    assert [int(v) for v in lines["removeCells"]] == cand["remove_cells"].tolist()
+    assert [int(v) for v in lines["removeVertices"]] == cand["remove_vertices"].tolist()
+    assert [int(v) for v in lines["insertSegments"]] == cand["insert_segs"].tolist()
+    assert [int(v) for v in lines["removeSegmentVertices"]] == cand["remove_seg_vertices"].tolist()
+    EV = [(0, 1), (0, 2), (1, 2)]
+    pts = np.array([float(v) for v in lines["insertPoints"]]).reshape(-1, 2)
+    for p, c in zip(pts, cand["insert_cells"]):
+        k = [int(m.cells[c][(int(m.perm[c]) >> (2 * t)) & 3]) for t in range(3)]
+        a, b = m.xy[k[EV[le[c]][0]]], m.xy[k[EV[le[c]][1]]]
+        assert np.array_equal(p, a + 0.5 * (b - a))
+    assert len(cand["insert_cells"]) + len(cand["remove_cells"]) > 0
     valid, _, ninv = oracle.trial_validate(m.xy, s, m.cells)
     # host part of ensureVertexMovement (mmesh.hh:1109-1124): non-interface, non-boundary corners of invalid cells,
     # in sub-entity (id) order, first occurrence only

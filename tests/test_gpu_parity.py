@@ -485,3 +485,35 @@ def test_refinement_candidates_like_adapt(gpu_ctx_factory, oracle):
         assert got.tolist() == expect
         pts, ev = ctx.refinement_points(got)
         assert len({tuple(sorted(x)) for x in ev.tolist()}) == len(got)      # unique edges
+
+
+def test_adapt_candidate_lists_match_oracle(gpu_ctx_factory, oracle):
+    """Both candidate loops of MMesh::adapt() (mmesh.hh:826-908) against the oracle: insert_ cells, remove_ (cell, vertex)
+    pairs with the libstdc++-pinned coarsening choice, interface insert_/remove_ lists.  Bit-exact index lists."""
+    from mmesh_b200 import synth
+    rng = np.random.default_rng(11)
+    for m, fmax, fmin in ((_mesh1(70), 0.4, 1.6), (synth.config2(n=90), 0.5, 1.4)):
+        ctx = gpu_ctx_factory(2)
+        _upload(ctx, m)
+        ctx.upload_neighbours(m.nb)
+        level = rng.integers(0, 3, m.nv).astype(np.int32)
+        prm = ctx.indicator_init()
+        prm.maxH *= fmax
+        prm.minH *= fmin
+        ctx.set_params(prm)
+        marks, le, counts = ctx.mark_elements(run_distance=True)
+        imark = ctx.mark_interface()
+        assert counts[0] > 50 and counts[1] > 50
+        for lev in (None, level):
+            if lev is not None:
+                ctx.upload_vertex_levels(lev)
+            want = oracle.adapt_candidates_2d(m.xy, m.cells, m.perm, m.nb, marks, le, m.segs, imark, lev)
+            assert ctx.refinement_candidates().tolist() == want["insert_cells"].tolist()
+            cells, verts = ctx.coarsening_candidates()
+            assert cells.tolist() == want["remove_cells"].tolist()
+            assert verts.tolist() == want["remove_vertices"].tolist()
+            ins, rs, rv = ctx.interface_candidates()
+            assert ins.tolist() == want["insert_segs"].tolist()
+            assert rs.tolist() == want["remove_segs"].tolist()
+            assert rv.tolist() == want["remove_seg_vertices"].tolist()
+            assert len(want["remove_cells"]) > 20

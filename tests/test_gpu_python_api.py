@@ -27,6 +27,13 @@ def test_distance_integral_and_user_loop(oracle):
     rm, _, rc = oracle.mark(m.xy, d, m.cells, m.perm, prm, oracle.distance_max(d))
     assert [grid.getMark(c) for c in range(0, m.nc, 97)] == [int(v) for v in rm[::97]]
     assert marked == (rc[0] + rc[1] > 0 or bool(np.any(oracle.mark_interface_2d(m.xy, m.segs, prm, oracle.distance_max(d)) != 0)))
+    cand = grid.adaptCandidates()                                  # mmesh.hh:826-908
+    im = oracle.mark_interface_2d(m.xy, m.segs, prm, oracle.distance_max(d))
+    want = oracle.adapt_candidates_2d(m.xy, m.cells, m.perm, m.nb, rm, _, m.segs, im, None)
+    assert cand["insert_cells"].tolist() == want["insert_cells"].tolist() and len(want["insert_cells"]) > 0
+    assert cand["remove_vertices"].tolist() == want["remove_vertices"].tolist()
+    assert cand["insert_segments"].tolist() == want["insert_segs"].tolist()
+    assert cand["remove_segment_vertices"].tolist() == want["remove_seg_vertices"].tolist()
     change = grid.ensureVertexMovement(shifts)
     valid, _, ninv = oracle.trial_validate(m.xy, shifts, m.cells)
     assert change == (ninv > 0 and len(grid.removed) > 0) and np.array_equal(grid.coordinates(), m.xy)
