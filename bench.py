@@ -53,30 +53,49 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.t_begin = self.t_end = None
 
-    def start(self):
+    def start(self, wait_s=5.0):
+        """Launch nvidia-smi and wait for its first row (it can take a second on an 8-GPU box)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.monotonic()
+            while not self.rows and time.monotonic() - t0 < wait_s:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t_begin = time.monotonic()
+
+    def end(self):
+        self.t_end = time.monotonic()
+
+    def loaded_seconds(self):
+        return (self.t_end - self.t_begin) if self.t_begin is not None and self.t_end is not None else 0.0
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.03)                                     # let the last row of the window arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        lo = self.t_begin if self.t_begin is not None else -1e300
+        hi = (self.t_end if self.t_end is not None else 1e300) + 0.02
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for t, r in self.rows:
+            if t < lo or t > hi:                             # only samples taken while the GPU was under the bench load
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
@@ -86,6 +105,9 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+CLOCK_WINDOW_S = 0.25      # nvidia-smi samples every 20 ms: keep the load on for at least this long
 
 
 def make_workload(args):
@@ -147,13 +169,13 @@ def run_reference_arm(args):
     m = w["mesh"]
     prm = O.indicator_init_2d(m.xy, m.edges, m.segs, O.Params.default())
     threads = os.cpu_count() or 1
-    sample = min(m.nc, 8 * args.cpu_sample)               # all host threads: a larger bounded sample than the 1-core baseline
-    for _ in range(max(0, min(args.warmup, 1))):
+    sample = min(m.nc, args.cpu_sample)                   # each step = this bounded sample, all host threads
+    for _ in range(max(0, args.warmup)):
         cpu_reference_step(O, w, sample, prm, threads)
-    ts = [cpu_reference_step(O, w, sample, prm, threads) for _ in range(max(1, min(args.steps, 3)))]
+    ts = [cpu_reference_step(O, w, sample, prm, threads) for _ in range(max(1, args.steps))]
     dt = float(np.mean(ts))
     val = sample / dt
-    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": min(args.warmup, 1),
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": max(0, args.warmup),
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": w["name"], "projection": "DG-P1, self+face-neighbour pairs (phi=1)"},
@@ -172,7 +194,8 @@ def main():
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--nx", type=int, default=None)
     ap.add_argument("--ny", type=int, default=None)
-    ap.add_argument("--cpu-sample", type=int, default=32768)
+    ap.add_argument("--cpu-sample", type=int, default=262144,
+                    help="cells per CPU-baseline step: ~8 s on one core (cpu_baseline), <1 s with all host threads (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -226,23 +249,33 @@ def main():
     # ---- timed region: K resident steps, CUDA events on the launching stream, per-kernel events inside ----
     clocks = ClockSampler(local_rank)
     clocks.start()
-    time.sleep(0.3)
     ctx.timing_enable(True)
     ctx.timing_reset()
     l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    clocks.begin()
     e0.record(stream)
     for _ in range(args.steps):
         step_resident()
     e1.record(stream)
     torch.cuda.synchronize()
+    clocks.end()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - l0
     per_kernel = ctx.timing_get()
     ctx.timing_enable(False)
     ctx.timing_reset()
+    clock_window = "timed region"
+    if clocks.loaded_seconds() < CLOCK_WINDOW_S:             # short timed region: keep the same load on (untimed, an even
+        n_ext = int(np.ceil(CLOCK_WINDOW_S / max(ms / args.steps * 1e-3, 1e-6)))   # number of steps) so the sampler sees it
+        for _ in range(n_ext + (n_ext & 1)):
+            step_resident()
+        ctx.synchronize()
+        clocks.end()
+        clock_window = "timed region + %d identical untimed steps" % (n_ext + (n_ext & 1))
     clk = clocks.stop()
+    clk["window"] = clock_window
     ms_per_step = ms / args.steps
     value = nc / (ms_per_step * 1e-3)
 
