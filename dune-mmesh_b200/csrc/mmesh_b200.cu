@@ -54,6 +54,7 @@ struct mmb_context {
   DBuf<int32_t> tile_lo_cells, tile_lo_edges;
   DBuf<int32_t> cell_nb; bool have_nb = false; DBuf<uint8_t> v_if, cand_flag; DBuf<unsigned long long> facet_keys;
   DBuf<uint8_t> v_bnd; DBuf<int32_t> v_ifcount, v_level, first_claim, first_seg, chosen; bool cand_ready = false, have_levels = false;
+  bool hp_active = false, hp_pipe_dofs = false; int hp_ncomp = 0;   // host-buffer step in flight (begin .. finish)
   DBuf<Counters> counters;
   bool has_shift = false, dist_valid = false, mesh_ok = false;
   // bvh
@@ -946,9 +947,10 @@ int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_s
 // the old DOFs overlaps the validity pass, the projection runs in chunks whose new DOFs stream back while the next
 // chunk is computed, and the flag arrays return behind the kernels that produced them.  (Pinned host buffers are
 // needed for real overlap; pageable ones still work, serialised by the driver.)
-int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host,
-                        double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host, uint8_t* valid_fp_host,
-                        int8_t* orient_sign_host, uint8_t* edge_flags_host, mmb_step_result* res) {
+// The three phases are exported separately so that a sharded caller can put its collectives between them
+// (multigpu.py): begin -> [all-reduce MAX of the distance maximum] -> marks -> [halo exchange of the shifts] -> finish.
+int mmb_step_host_begin(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host,
+                        int will_download_dofs) {
   if (!ctx) return MMB_ERR_INVALID_ARG;
   REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
   REQUIRE(ncomp == 0 || ctx->dim == 2, MMB_ERR_INVALID_ARG, "projection is 2-D only (geometryInFather, entity.hh:573-594)");
@@ -971,7 +973,7 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
   if (shifts_host) CK(cudaMemcpyAsync(ctx->shift.p, shifts_host, (size_t)ctx->nv * ctx->dim * sizeof(double), cudaMemcpyHostToDevice, S1));
   ctx->has_shift = true;
   CK(cudaEventRecord(ev[1], S1));
-  const bool pipe_dofs = ncomp && dofs_old_host && dofs_new_host && ctx->nnew && ctx->chunks_ok && ctx->dof_pipe_ok &&
+  const bool pipe_dofs = ncomp && dofs_old_host && will_download_dofs && ctx->nnew && ctx->chunks_ok && ctx->dof_pipe_ok &&
                          (ctx->dof_lo.empty() || ctx->dof_lo.back() <= n_old);
   if (ncomp && dofs_old_host) {
     if (pipe_dofs) {
@@ -1001,9 +1003,19 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
     ctx->n_old = n_old; ctx->dofs_ncomp = ncomp;
   }
   CK(cudaEventRecord(ev[2], S1));
-  // S0: markElements needs neither shifts nor DOFs
+  ctx->hp_active = true; ctx->hp_pipe_dofs = pipe_dofs; ctx->hp_ncomp = ncomp;
+  // S0: Distance::update needs neither shifts nor DOFs
   TRY(zero_counters(ctx));
   TRY(do_distance(ctx));
+  CK(cudaGetLastError());
+  return MMB_OK;
+}
+int mmb_step_host_marks(mmb_context* ctx, int8_t* marks_host, uint8_t* longest_edge_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->hp_active, MMB_ERR_STATE, "mmb_step_host_marks without mmb_step_host_begin");
+  cudaStream_t S0 = ctx->stream, S2 = ctx->s_d2h;
+  cudaEvent_t* ev = ctx->pipe_ev.data();
+  const size_t nc = (size_t)ctx->nc;
   TRY(do_mark(ctx));
   if (ctx->dim == 2 && ctx->ns)
     LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
@@ -1012,14 +1024,27 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
   CK(cudaStreamWaitEvent(S2, ev[3], 0));
   if (marks_host) CK(cudaMemcpyAsync(marks_host, ctx->mark.p, nc, cudaMemcpyDeviceToHost, S2));
   if (longest_edge_host) CK(cudaMemcpyAsync(longest_edge_host, ctx->longest.p, nc, cudaMemcpyDeviceToHost, S2));
-  CK(cudaStreamWaitEvent(S0, ev[1], 0));                           // shifts have landed
+  CK(cudaStreamWaitEvent(S0, ev[1], 0));                           // shifts have landed: whatever follows on S0 may read them
+  CK(cudaGetLastError());
+  return MMB_OK;
+}
+int mmb_step_host_finish(mmb_context* ctx, double* dofs_new_host, uint8_t* valid_fp_host, int8_t* orient_sign_host,
+                         uint8_t* edge_flags_host, int reduce_vector, mmb_step_result* res) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->hp_active, MMB_ERR_STATE, "mmb_step_host_finish without mmb_step_host_begin");
+  ctx->hp_active = false;
+  cudaStream_t S0 = ctx->stream, S2 = ctx->s_d2h;
+  cudaEvent_t* ev = ctx->pipe_ev.data();
+  const size_t nc = (size_t)ctx->nc;
+  const int ncomp = ctx->hp_ncomp;
+  const bool pipe_dofs = ctx->hp_pipe_dofs && dofs_new_host;
   TRY(do_validate(ctx, true));
   CK(cudaEventRecord(ev[4], S0));
   CK(cudaStreamWaitEvent(S2, ev[4], 0));
   if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, nc, cudaMemcpyDeviceToHost, S2));
   if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, nc, cudaMemcpyDeviceToHost, S2));
   if (ncomp && ctx->nnew) {
-    if (!pipe_dofs) CK(cudaStreamWaitEvent(S0, ev[2], 0));         // old DOFs have landed (monolithic upload)
+    if (!pipe_dofs) CK(cudaStreamWaitEvent(S0, ev[2], 0));         // old DOFs have landed (monolithic upload / all ranges)
     const bool chunked = ctx->chunks_ok && dofs_new_host;
     const int C = chunked ? (int)ctx->chunk_cell_lo.size() : 1;
     int pb = 0;
@@ -1050,11 +1075,24 @@ int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, 
   CK(cudaStreamWaitEvent(S2, ev[5], 0));
   if (edge_flags_host && ctx->ne) CK(cudaMemcpyAsync(edge_flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, S2));
   CK(cudaEventRecord(ev[6], S2));
+  if (reduce_vector) {                                             // sharded caller: counts + mass for the SUM all-reduce
+    CK(ctx->reduce_vec.ensure(16));
+    LAUNCH("reduce_vector", k_reduce_vector, 1, 32, ctx->counters.p, ctx->reduce_vec.p);
+  }
   CK(cudaStreamWaitEvent(S0, ev[6], 0));                           // the step is complete on S0 only when all copies are
   CK(cudaGetLastError());
   if (res) return step_result(ctx, res);
-  CK(cudaStreamSynchronize(S0));
+  if (!reduce_vector) CK(cudaStreamSynchronize(S0));
   return MMB_OK;
+}
+int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host,
+                        double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host, uint8_t* valid_fp_host,
+                        int8_t* orient_sign_host, uint8_t* edge_flags_host, mmb_step_result* res) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  TRY(mmb_step_host_begin(ctx, shifts_host, ncomp, n_old, dofs_old_host, dofs_new_host != nullptr));
+  const int rc = mmb_step_host_marks(ctx, marks_host, longest_edge_host);
+  if (rc != MMB_OK) { ctx->hp_active = false; return rc; }
+  return mmb_step_host_finish(ctx, dofs_new_host, valid_fp_host, orient_sign_host, edge_flags_host, 0, res);
 }
 
 // ---- 3-D P0 trace / skeleton ----------------------------------------------------------------------------

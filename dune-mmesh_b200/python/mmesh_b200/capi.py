@@ -19,7 +19,7 @@ EXPORTS = [
     "mmb_indicator_init", "mmb_move_vertices", "mmb_trial_move_validate", "mmb_invalid_cells", "mmb_legality",
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
-    "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
+    "mmb_step_host_begin", "mmb_step_host_marks", "mmb_step_host_finish", "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
     "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 

@@ -174,6 +174,19 @@ int mmb_adapt_step(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_s
 int mmb_adapt_step_host(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host,
                         double* dofs_new_host, int8_t* marks_host, uint8_t* longest_edge_host, uint8_t* valid_fp_host,
                         int8_t* orient_sign_host, uint8_t* edge_flags_host, mmb_step_result* res);
+/* The same pipelined step in three calls, for a sharded caller that must place its collectives in between:
+     mmb_step_host_begin   async H2D of shifts and old DOFs (own copy stream), Distance::update
+       -> all-reduce MAX of the distance maximum (mmb_device_buffer(2))
+     mmb_step_host_marks   marks (+ async D2H); afterwards the launching stream is ordered behind the shift upload
+       -> halo exchange of the shifts (mmb_halo_pack_shifts / all-to-all / mmb_halo_unpack_shifts)
+     mmb_step_host_finish  trial validity, chunked projection with the new DOFs streaming back, moveVertices, legality,
+                           D2H of the flags; reduce_vector != 0 also fills mmb_device_buffer(3) for the SUM all-reduce
+                           and returns without synchronising (the caller's read of that vector does). */
+int mmb_step_host_begin(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host,
+                        int will_download_dofs);
+int mmb_step_host_marks(mmb_context* ctx, int8_t* marks_host, uint8_t* longest_edge_host);
+int mmb_step_host_finish(mmb_context* ctx, double* dofs_new_host, uint8_t* valid_fp_host, int8_t* orient_sign_host,
+                         uint8_t* edge_flags_host, int reduce_vector, mmb_step_result* res);
 
 /* Asynchronous field transfers on the context's stream (pinned host buffers; complete after mmb_synchronize).
    Used by the sharded step, where collectives sit between the phases. */

@@ -30,6 +30,45 @@ ctx.upload_shifts(sl)
 sm.step(3)
 torch.cuda.synchronize()
 got = sm.result()
+# the host-buffer (pipelined) sharded step must give the same scalars and the same fields as step() + downloads
+lnc, lne = sh.cells.shape[0], sh.edges.shape[0]
+ctx.upload_coords(sh.xy)                                        # undo the move bit for bit
+pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+sl_h, dofs_h = pin(sl), pin(dofs[sh.lcells])
+out = dict(dofs=torch.empty((lnc, 3), dtype=torch.float64).pin_memory(), marks=torch.empty(lnc, dtype=torch.int8).pin_memory(),
+           longest=torch.empty(lnc, dtype=torch.uint8).pin_memory(), valid=torch.empty(lnc, dtype=torch.uint8).pin_memory(),
+           orient=torch.empty(lnc, dtype=torch.int8).pin_memory(), eflag=torch.empty(max(lne, 1), dtype=torch.uint8).pin_memory())
+sm.step_host(3, sl_h, dofs_h, lnc, out["dofs"], out["marks"], out["longest"], out["valid"], out["orient"], out["eflag"])
+got_host = sm.result()
+torch.cuda.synchronize()
+host_fields = {k: v.numpy().copy() for k, v in out.items()}
+# resident path again on restored coordinates, fields downloaded afterwards
+ctx.upload_coords(sh.xy)
+ctx.project(3, dofs[sh.lcells], download=False)
+ctx.upload_shifts(sl)
+sm.step(3)
+torch.cuda.synchronize()
+import ctypes
+Lb = capi.lib()
+res_f = dict(dofs=np.empty((lnc, 3)), marks=np.empty(lnc, np.int8), longest=np.empty(lnc, np.uint8), valid=np.empty(lnc, np.uint8),
+             orient=np.empty(lnc, np.int8), eflag=np.empty(max(lne, 1), np.uint8))
+Pn = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+ctx._ck(Lb.mmb_download_fields(ctx._h, ctypes.c_int(3), Pn(res_f["dofs"]), Pn(res_f["marks"]), Pn(res_f["longest"]), Pn(res_f["valid"]),
+                               Pn(res_f["orient"]), Pn(res_f["eflag"])))
+host_ok = True
+own = slice(sh.own_lo, sh.own_hi)
+for k in ("marks", "longest", "valid", "orient"):
+    if not np.array_equal(host_fields[k][own], res_f[k][own]):
+        host_ok = False; print("rank", rank, "HOST FIELD MISMATCH", k)
+if not np.array_equal(host_fields["eflag"][:lne], res_f["eflag"][:lne]):
+    host_ok = False; print("rank", rank, "HOST FIELD MISMATCH eflag")
+if not np.array_equal(host_fields["dofs"][own], res_f["dofs"][own]):
+    host_ok = False; print("rank", rank, "HOST FIELD MISMATCH dofs", np.abs(host_fields["dofs"][own] - res_f["dofs"][own]).max())
+for k in got:
+    if got_host[k] != got[k] and not (k in ("mass_new", "covered_area") and abs(got_host[k] - got[k]) <= 1e-13 * abs(got[k])):
+        host_ok = False; print("rank", rank, "HOST SCALAR MISMATCH", k, got_host[k], got[k])
+hflag = torch.tensor([1 if host_ok else 0], device="cuda")
+dist.all_reduce(hflag, op=dist.ReduceOp.MIN)
 
 
 ok = True
@@ -48,6 +87,8 @@ if rank == 0:
     for k in ("mass_new", "covered_area"):
         if abs(got[k] - r[k]) > 1e-13 * abs(r[k]):
             ok = False; print("MISMATCH", k, got[k], r[k])
+    if hflag.item() != 1:
+        ok = False; print("host-buffer sharded step differs from the resident one")
     print("mgpu_check world", world, "cells", m.nc, "OK" if ok else "FAILED", got)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
