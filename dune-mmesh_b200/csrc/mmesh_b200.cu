@@ -34,6 +34,15 @@ struct DBuf {
 
 }  // namespace
 
+// number of projection chunks of the pipelined host-buffer step (the tail after the last upload is one chunk's compute +
+// download); MMB_CHUNKS overrides
+static const int MAX_CHUNKS = 64;
+static int pipeline_chunks() {
+  static int c = -1;
+  if (c < 0) { const char* e = getenv("MMB_CHUNKS"); c = e ? atoi(e) : 32; c = std::max(1, std::min(c, MAX_CHUNKS)); }
+  return c;
+}
+
 struct mmb_context {
   int device = 0, dim = 2;
   cudaStream_t stream = nullptr; bool own_stream = false;
@@ -485,8 +494,17 @@ int mmb_marked_cells(mmb_context* ctx, int which, int32_t* cells_host, int64_t c
 }
 
 // ---- legality -------------------------------------------------------------------------------------------
-static int do_legality(mmb_context* ctx) {
+// shifted = true evaluates the flags on x (+) shift, the coordinates moveVertices is about to write (same IEEE additions,
+// so the flags are bit-identical to running after the move); the pipelined host step uses it to get the flags out early
+static int do_legality(mmb_context* ctx, bool shifted = false) {
   if (ctx->ne == 0) return MMB_OK;
+  if (shifted) {
+    LAUNCH("legality", k_legality<true>, grid_for(ctx->ne, TILE), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
+           (const int4*)ctx->edges.p, ctx->ne, ctx->tile_lo_edges.p, ctx->nv, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p);
+    LAUNCH("exact_incircle", k_exact_incircle<true>, ctx->num_sms * 4, 128, (const double2*)ctx->x.p,
+           (const double2*)ctx->shift.p, (const int4*)ctx->edges.p, ctx->wl.p, ctx->edge_flag.p, ctx->counters.p);
+    return MMB_OK;
+  }
   LAUNCH("legality", k_legality<false>, grid_for(ctx->ne, TILE), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
          (const int4*)ctx->edges.p, ctx->ne, ctx->tile_lo_edges.p, ctx->nv, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p);
   LAUNCH("exact_incircle", k_exact_incircle<false>, ctx->num_sms * 4, 128, (const double2*)ctx->x.p,
@@ -651,7 +669,7 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
   // chunk table for the pipelined host-buffer step: new cells are listed in ascending cell order (element iteration
   // order, mmesh.hh:1143), so chunk k of the CSR writes DOFs of cells [cell_lo[k], cell_hi[k]]
   ctx->chunk_i.clear(); ctx->chunk_cell_lo.clear(); ctx->chunk_cell_hi.clear();
-  const int C = nnew >= (1 << 16) ? 8 : 1;
+  const int C = nnew >= (1 << 16) ? pipeline_chunks() : 1;
   bool ascending = true;
   for (int64_t i = 1; i < nnew && ascending; ++i) ascending = new_cell_host[i] > new_cell_host[i - 1];
   ctx->chunks_ok = ascending && nnew > 0;
@@ -957,7 +975,7 @@ int mmb_step_host_begin(mmb_context* ctx, const double* shifts_host, int ncomp, 
   REQUIRE(ncomp == 0 || ncomp == 1 || ncomp == 3, MMB_ERR_INVALID_ARG, "ncomp must be 0, 1 (P0) or 3 (DG-P1)");
   REQUIRE(shifts_host || ctx->has_shift, MMB_ERR_STATE, "shifts == NULL but no resident shifts");
   if (!ctx->s_h2d) { CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)); }
-  while (ctx->pipe_ev.size() < 32) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->pipe_ev.push_back(e); }
+  while (ctx->pipe_ev.size() < 8 + 2 * (size_t)MAX_CHUNKS) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->pipe_ev.push_back(e); }
   cudaStream_t S0 = ctx->stream, S1 = ctx->s_h2d, S2 = ctx->s_d2h;
   cudaEvent_t* ev = ctx->pipe_ev.data();
   const size_t nc = (size_t)ctx->nc;
@@ -995,7 +1013,7 @@ int mmb_step_host_begin(mmb_context* ctx, const double* shifts_host, int ncomp, 
       for (int k = 0; k < C; ++k) {
         const size_t lo = (size_t)ctx->dof_lo[k], hi = k == C - 1 ? (size_t)n_old : (size_t)ctx->dof_lo[k + 1];
         if (hi > lo) CK(cudaMemcpyAsync(ctx->dofs_old.p + lo * ncomp, dofs_old_host + lo * ncomp, (hi - lo) * ncomp * sizeof(double), cudaMemcpyHostToDevice, S1));
-        CK(cudaEventRecord(ev[16 + k], S1));
+        CK(cudaEventRecord(ev[8 + MAX_CHUNKS + k], S1));
       }
     } else {
       CK(cudaMemcpyAsync(ctx->dofs_old.p, dofs_old_host, (size_t)n_old * ncomp * sizeof(double), cudaMemcpyHostToDevice, S1));
@@ -1043,6 +1061,12 @@ int mmb_step_host_finish(mmb_context* ctx, double* dofs_new_host, uint8_t* valid
   CK(cudaStreamWaitEvent(S2, ev[4], 0));
   if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, nc, cudaMemcpyDeviceToHost, S2));
   if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, nc, cudaMemcpyDeviceToHost, S2));
+  if (ctx->dim == 2) {                                             // legality of the moved mesh, evaluated on x (+) shift so
+    TRY(do_legality(ctx, true));                                   // that its flags leave before the projection's DOFs
+    CK(cudaEventRecord(ev[5], S0));
+    CK(cudaStreamWaitEvent(S2, ev[5], 0));
+    if (edge_flags_host && ctx->ne) CK(cudaMemcpyAsync(edge_flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, S2));
+  }
   if (ncomp && ctx->nnew) {
     if (!pipe_dofs) CK(cudaStreamWaitEvent(S0, ev[2], 0));         // old DOFs have landed (monolithic upload / all ranges)
     const bool chunked = ctx->chunks_ok && dofs_new_host;
@@ -1051,7 +1075,7 @@ int mmb_step_host_finish(mmb_context* ctx, double* dofs_new_host, uint8_t* valid
     for (int k = 0; k < C; ++k) {
       const int64_t i0 = chunked ? ctx->chunk_i[k] : 0, i1 = chunked ? ctx->chunk_i[k + 1] : ctx->nnew;
       int nb = 0;
-      if (pipe_dofs) CK(cudaStreamWaitEvent(S0, ev[16 + k], 0));   // this chunk's home range (and the remote DOFs) have landed
+      if (pipe_dofs) CK(cudaStreamWaitEvent(S0, ev[8 + MAX_CHUNKS + k], 0));   // this chunk's home range (and the remote DOFs) have landed
       TRY(project_range(ctx, ncomp, i0, i1, pb, &nb));
       pb += nb;
       if (dofs_new_host) {
@@ -1070,10 +1094,6 @@ int mmb_step_host_finish(mmb_context* ctx, double* dofs_new_host, uint8_t* valid
     CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, S2));
   }
   TRY(do_move(ctx));
-  if (ctx->dim == 2) TRY(do_legality(ctx));
-  CK(cudaEventRecord(ev[5], S0));
-  CK(cudaStreamWaitEvent(S2, ev[5], 0));
-  if (edge_flags_host && ctx->ne) CK(cudaMemcpyAsync(edge_flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, S2));
   CK(cudaEventRecord(ev[6], S2));
   if (reduce_vector) {                                             // sharded caller: counts + mass for the SUM all-reduce
     CK(ctx->reduce_vec.ensure(16));
