@@ -1484,6 +1484,79 @@ k_count_interface_elements(const int32_t* __restrict__ facets, int64_t n_entries
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_entries) atomicAdd(v_ifcount + facets[i], 1);
 }
+// ---- 3-D refinement candidates: an edge has many cells, so inserted_ becomes an open-addressing table keyed by the
+// (min,max) vertex pair whose value is the lowest claiming cell index (atomicMin => independent of the thread order)
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+__device__ __forceinline__ int pick4(int i, int x0, int x1, int x2, int x3) { return i == 0 ? x0 : (i == 1 ? x1 : (i == 2 ? x2 : x3)); }
+// the two vertices (id order) of DUNE tetrahedron edge e: 0:(0,1) 1:(0,2) 2:(1,2) 3:(0,3) 4:(1,3) 5:(2,3)
+__device__ __forceinline__ int2 tet_edge_vertices(const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1,
+                                                  const int32_t* __restrict__ cv2, const int32_t* __restrict__ cv3,
+                                                  const uint8_t* __restrict__ perm, int64_t c, int e) {
+  const int v0 = cv0[c], v1 = cv1[c], v2 = cv2[c], v3 = cv3[c];
+  const unsigned p = perm[c];
+  const int ia = (e == 2 || e == 4) ? 1 : (e == 5 ? 2 : 0);
+  const int ib = e == 0 ? 1 : ((e == 1 || e == 2) ? 2 : 3);
+  const int ta = (p >> (2 * ia)) & 3, tb = (p >> (2 * ib)) & 3;
+  return make_int2(pick4(ta, v0, v1, v2, v3), pick4(tb, v0, v1, v2, v3));
+}
+__global__ void __launch_bounds__(256)
+k_refine3d_claim(const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2,
+                 const int32_t* __restrict__ cv3, const uint8_t* __restrict__ perm, const int8_t* __restrict__ mark,
+                 const uint8_t* __restrict__ longest, const uint8_t* __restrict__ v_if,
+                 const unsigned long long* __restrict__ iface_keys, int n_keys, int64_t nc,
+                 unsigned long long* __restrict__ tab_key, int32_t* __restrict__ tab_val, unsigned mask, int32_t* __restrict__ slot) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  int sl = -1;
+  if (mark[c] == 1) {
+    const int2 ab = tet_edge_vertices(cv0, cv1, cv2, cv3, perm, c, longest[c]);
+    const unsigned long long key = ((unsigned long long)(unsigned)min(ab.x, ab.y) << 32) | (unsigned)max(ab.x, ab.y);
+    bool iface = false;                                     // isInterface(edge) in 3-D: an edge of an interface triangle
+    if (v_if[ab.x] && v_if[ab.y] && n_keys > 0) {
+      int lo = 0, hi = n_keys - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned long long km = iface_keys[mid];
+        if (km == key) { iface = true; break; }
+        if (km < key) lo = mid + 1; else hi = mid - 1;
+      }
+    }
+    if (!iface) {
+      unsigned h = (unsigned)mix64(key) & mask;
+      for (;;) {
+        const unsigned long long prev = atomicCAS(tab_key + h, ~0ull, key);
+        if (prev == ~0ull || prev == key) { atomicMin(tab_val + h, (int)c); sl = (int)h; break; }
+        h = (h + 1) & mask;
+      }
+    }
+  }
+  slot[c] = sl;
+}
+__global__ void __launch_bounds__(256)
+k_refine3d_flag(const int32_t* __restrict__ slot, const int32_t* __restrict__ tab_val, int64_t nc, uint8_t* __restrict__ flag) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int sl = slot[c];
+  flag[c] = (sl >= 0 && tab_val[sl] == (int)c) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+k_refinement_points3d(const double* __restrict__ x, const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1,
+                      const int32_t* __restrict__ cv2, const int32_t* __restrict__ cv3, const uint8_t* __restrict__ perm,
+                      const uint8_t* __restrict__ longest, const int32_t* __restrict__ cells, int64_t n,
+                      double* __restrict__ out, int2* __restrict__ edge_vertices) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cells[i];
+  const int2 ab = tet_edge_vertices(cv0, cv1, cv2, cv3, perm, c, longest[c]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double a = x[3 * (int64_t)ab.x + k], b = x[3 * (int64_t)ab.y + k];
+    out[3 * i + k] = a + 0.5 * (b - a);                     // edge.geometry().center() = origin + J^T (1/2)
+  }
+  if (edge_vertices) edge_vertices[i] = ab;
+}
 __global__ void __launch_bounds__(256)
 k_flag_interface_vertices(const int32_t* __restrict__ facets, int64_t n_entries, uint8_t* __restrict__ v_if) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -61,7 +61,8 @@ struct mmb_context {
   DBuf<int32_t> wl, list_out;
   DBuf<uint32_t> block_count;
   DBuf<int32_t> tile_lo_cells, tile_lo_edges;
-  DBuf<int32_t> cell_nb; bool have_nb = false; DBuf<uint8_t> v_if, cand_flag; DBuf<unsigned long long> facet_keys;
+  DBuf<int32_t> cell_nb; bool have_nb = false; DBuf<uint8_t> v_if, cand_flag; DBuf<unsigned long long> facet_keys; int64_t n_facet_keys = 0;
+  DBuf<unsigned long long> ht_key; DBuf<int32_t> ht_val, ht_slot;   // inserted_ of the 3-D candidate loop
   DBuf<uint8_t> v_bnd; DBuf<int32_t> v_ifcount, v_level, first_claim, first_seg, chosen; bool cand_ready = false, have_levels = false;
   bool hp_active = false, hp_pipe_dofs = false; int hp_ncomp = 0;   // host-buffer step in flight (begin .. finish)
   DBuf<Counters> counters;
@@ -172,7 +173,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->orient.release(); ctx->mark.release(); ctx->imark.release(); ctx->edges.release();
   ctx->wl.release(); ctx->list_out.release(); ctx->block_count.release(); ctx->counters.release();
   ctx->tile_lo_cells.release(); ctx->tile_lo_edges.release();
-  ctx->cell_nb.release(); ctx->v_if.release(); ctx->cand_flag.release(); ctx->facet_keys.release();
+  ctx->cell_nb.release(); ctx->v_if.release(); ctx->cand_flag.release(); ctx->facet_keys.release(); ctx->ht_key.release(); ctx->ht_val.release(); ctx->ht_slot.release();
   ctx->v_bnd.release(); ctx->v_ifcount.release(); ctx->v_level.release(); ctx->first_claim.release(); ctx->first_seg.release(); ctx->chosen.release();
   ctx->seg_leaf.release(); ctx->box2.release(); ctx->seg_hint.release(); ctx->ticket.release(); ctx->tri_leaf.release(); ctx->box3.release();
   ctx->new_off.release(); ctx->new_cell.release(); ctx->old_idx.release(); ctx->old_xy.release();
@@ -314,19 +315,24 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
     CK(cudaStreamSynchronize(ctx->stream));   // `sorted` is a stack-owned staging buffer
   }
   ctx->have_nb = false; ctx->cand_ready = false; ctx->have_levels = false;
-  if (dim == 2) {
-    // per-vertex interface flag + sorted (min,max) facet keys: MMesh::isInterface(edge) on the device (mmesh.hh:607-621)
-    CK(ctx->v_if.ensure(nv + 1)); CK(ctx->cand_flag.ensure((size_t)std::max(ctx->nc_pad, ns) + 4)); CK(ctx->facet_keys.ensure(ns + 1));
+  {
+    // per-vertex interface flag + sorted (min,max) keys of the interface edges: MMesh::isInterface(edge) on the device
+    // (2-D: the facets themselves, mmesh.hh:607-621; 3-D: the three edges of every interface triangle, :624-645)
+    const int64_t nk = dim == 2 ? ns : 3 * ns;
+    CK(ctx->v_if.ensure(nv + 1)); CK(ctx->cand_flag.ensure((size_t)std::max(ctx->nc_pad, ns) + 4)); CK(ctx->facet_keys.ensure(nk + 1));
     CK(cudaMemsetAsync(ctx->v_if.p, 0, (size_t)nv, ctx->stream));
+    ctx->n_facet_keys = nk;
     if (ns) {
-      LAUNCH("flag_interface_vertices", k_flag_interface_vertices, grid_for(2 * ns, 256), 256, ctx->facets.p, 2 * ns, ctx->v_if.p);
-      std::vector<unsigned long long> keys((size_t)ns);
+      LAUNCH("flag_interface_vertices", k_flag_interface_vertices, grid_for(dim * ns, 256), 256, ctx->facets.p, dim * ns, ctx->v_if.p);
+      std::vector<unsigned long long> keys; keys.reserve((size_t)nk);
+      auto key = [](int32_t a, int32_t b) { const unsigned x = (unsigned)std::min(a, b), y = (unsigned)std::max(a, b); return ((unsigned long long)x << 32) | y; };
       for (int64_t s2 = 0; s2 < ns; ++s2) {
-        const unsigned a = (unsigned)facets_host[2 * s2], b = (unsigned)facets_host[2 * s2 + 1];
-        keys[(size_t)s2] = ((unsigned long long)std::min(a, b) << 32) | std::max(a, b);
+        const int32_t* f = facets_host + (size_t)s2 * dim;
+        if (dim == 2) keys.push_back(key(f[0], f[1]));
+        else { keys.push_back(key(f[0], f[1])); keys.push_back(key(f[0], f[2])); keys.push_back(key(f[1], f[2])); }
       }
       std::sort(keys.begin(), keys.end());
-      CK(cudaMemcpy(ctx->facet_keys.p, keys.data(), (size_t)ns * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(ctx->facet_keys.p, keys.data(), (size_t)nk * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     }
   }
   if (dim == 2) {
@@ -806,10 +812,25 @@ int mmb_project_interface_p0(mmb_context* ctx, int64_t nnew, const double* new_l
 }
 int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host, double* points_host, int32_t* edge_vertices_host) {
   if (!ctx) return MMB_ERR_INVALID_ARG;
-  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "refinement points need an uploaded 2-D mesh with marks");
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "refinement points need an uploaded mesh with marks");
   REQUIRE(n >= 0 && (n == 0 || (cells_host && points_host)), MMB_ERR_INVALID_ARG, "mmb_refinement_points: bad arguments");
   if (n == 0) return MMB_OK;
+  for (int64_t i = 0; i < n; ++i)
+    REQUIRE(cells_host[i] >= 0 && cells_host[i] < ctx->nc, MMB_ERR_INVALID_ARG, "mmb_refinement_points: cell index out of range");
   CK(ctx->list_out.ensure(n));
+  if (ctx->dim == 3) {
+    DBuf<double> out3; DBuf<int2> ev3;
+    CK(out3.ensure(3 * (size_t)n)); CK(ev3.ensure(n));
+    CK(cudaMemcpyAsync(ctx->list_out.p, cells_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("refinement_points3d", k_refinement_points3d, grid_for(n, 256), 256, ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->cv[3].p,
+           ctx->perm.p, ctx->longest.p, ctx->list_out.p, n, out3.p, ev3.p);
+    cudaMemcpyAsync(points_host, out3.p, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (edge_vertices_host) cudaMemcpyAsync(edge_vertices_host, ev3.p, n * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+    out3.release(); ev3.release();
+    if (e3 != cudaSuccess) { ctx->err = cudaGetErrorString(e3); return MMB_ERR_CUDA; }
+    return MMB_OK;
+  }
   DBuf<double2> out; DBuf<int2> ev;
   CK(out.ensure(n)); CK(ev.ensure(n));
   CK(cudaMemcpyAsync(ctx->list_out.p, cells_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -836,6 +857,21 @@ int mmb_upload_neighbours(mmb_context* ctx, const int32_t* cell_nb_host) {
 }
 int mmb_refinement_candidates(mmb_context* ctx, int32_t* cells_host, int64_t cap, int64_t* n_total) {
   if (!ctx) return MMB_ERR_INVALID_ARG;
+  if (ctx->mesh_ok && ctx->dim == 3) {
+    // size the table from the number of marked cells (every marked cell claims at most one edge)
+    int64_t n_marked = 0;
+    TRY(compact_flags(ctx, (const uint8_t*)ctx->mark.p, ctx->nc, 1, nullptr, 0, &n_marked));
+    size_t T = 1024; while (T < 2 * (size_t)n_marked + 16) T <<= 1;
+    REQUIRE(T <= (1ull << 31), MMB_ERR_CAPACITY, "refinement candidates: too many marked cells");
+    CK(ctx->ht_key.ensure(T)); CK(ctx->ht_val.ensure(T)); CK(ctx->ht_slot.ensure((size_t)ctx->nc + 1));
+    CK(cudaMemsetAsync(ctx->ht_key.p, 0xff, T * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->ht_val.p, 0x7f, T * sizeof(int32_t), ctx->stream));
+    LAUNCH("refine3d_claim", k_refine3d_claim, grid_for(ctx->nc, 256), 256, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->cv[3].p, ctx->perm.p,
+           ctx->mark.p, ctx->longest.p, ctx->v_if.p, ctx->facet_keys.p, (int)ctx->n_facet_keys, ctx->nc, ctx->ht_key.p, ctx->ht_val.p,
+           (unsigned)(T - 1), ctx->ht_slot.p);
+    LAUNCH("refine3d_flag", k_refine3d_flag, grid_for(ctx->nc, 256), 256, ctx->ht_slot.p, ctx->ht_val.p, ctx->nc, ctx->cand_flag.p);
+    return compact_flags(ctx, ctx->cand_flag.p, ctx->nc, 1, cells_host, cap, n_total);
+  }
   REQUIRE(ctx->mesh_ok && ctx->dim == 2 && ctx->have_nb, MMB_ERR_STATE, "refinement candidates need a 2-D mesh with neighbours (mmb_upload_neighbours) and marks");
   LAUNCH("refine_candidates", k_refine_candidates, grid_for(ctx->nc, 256), 256, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p,
          ctx->mark.p, ctx->longest.p, ctx->cell_nb.p, ctx->v_if.p, ctx->facet_keys.p, (int)ctx->ns, ctx->nc, ctx->cand_flag.p);

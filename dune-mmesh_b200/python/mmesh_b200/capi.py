@@ -324,7 +324,7 @@ class Context:
 
     def refinement_points(self, cells):
         cells = _i32(cells)
-        pts = np.empty((cells.shape[0], 2))
+        pts = np.empty((cells.shape[0], self.dim))
         ev = np.empty((cells.shape[0], 2), np.int32)
         self._ck(lib().mmb_refinement_points(self._h, C.c_int64(cells.shape[0]), _p(cells), _p(pts), _p(ev)))
         return pts, ev

@@ -136,12 +136,14 @@ int mmb_project_interface_p0(mmb_context* ctx, int64_t nnew, const double* new_l
                              int64_t npairs, const double* old_len_host, const int32_t* old_idx_host, int64_t n_old,
                              const double* dofs_old_host, double* dofs_new_host);
 /* LongestEdgeRefinement::refinement (longestedgerefinement.hh:41-57) for the listed cells (after mmb_mark_elements):
-   centre of the longest edge and, optionally, its two vertex indices (id order). */
+   centre of the longest edge ([n][dim]) and, optionally, its two vertex indices (id order).  2-D and 3-D. */
 int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host, double* points_host, int32_t* edge_vertices_host);
 
 /* Refinement candidates of MMesh::adapt() (mmesh.hh:828-851): the cells (index order) whose longest edge enters insert_,
    i.e. marked +1, edge not an interface edge, edge id not yet inserted by an earlier cell.  Needs the face neighbours
-   (cell_nb[c][k] = index of face->neighbor(k), -1 for the infinite face).  Feed the result to mmb_refinement_points. */
+   (cell_nb[c][k] = index of face->neighbor(k), -1 for the infinite face).  Feed the result to mmb_refinement_points.
+   3-D meshes need no neighbours: an edge has many cells, so inserted_ is a device hash table keyed by the edge's vertex
+   pair holding the lowest claiming cell; isInterface(edge) = edge of an interface triangle (mmesh.hh:624-645). */
 int mmb_upload_neighbours(mmb_context* ctx, const int32_t* cell_nb_host);
 int mmb_refinement_candidates(mmb_context* ctx, int32_t* cells_host, int64_t cap, int64_t* n_total);
 

@@ -683,6 +683,35 @@ void orc_adapt_candidates_2d(const double* xy, int64_t nv, const int32_t* cells,
   if (n_rem_segs) *n_rem_segs = nrs;
   free(v_if); free(v_bnd); free(v_cnt); free(iface.slot); free(inserted.slot); free(removed.slot);
 }
+/* 3-D bulk loop of adapt() (mmesh.hh:828-851; coarsening never fires in 3-D, ratioindicator.hh:151-156).
+   isInterface(edge) in 3-D = the edge belongs to an interface triangle (mmesh.hh:624-645). */
+void orc_refine_candidates_3d(const int32_t* cells, const uint8_t* perm, int64_t nc, const int8_t* mark,
+                              const uint8_t* longest_edge, const int32_t* tris, int64_t ns,
+                              int32_t* ins_cells, int32_t* ins_edge_vertices, int64_t* n_ins) {
+  static const int EV[6][2] = { { 0, 1 }, { 0, 2 }, { 1, 2 }, { 0, 3 }, { 1, 3 }, { 2, 3 } };
+  keyset iface, inserted;
+  keyset_init(&iface, 3 * ns); keyset_init(&inserted, nc);
+  for (int64_t t = 0; t < ns; ++t) {
+    const int32_t* q = tris + 3 * t;
+    keyset_insert(&iface, edge_key(q[0], q[1])); keyset_insert(&iface, edge_key(q[0], q[2])); keyset_insert(&iface, edge_key(q[1], q[2]));
+  }
+  int64_t ni = 0;
+  for (int64_t c = 0; c < nc; ++c) {
+    if (mark[c] != 1) continue;
+    int k[4];
+    for (int t = 0; t < 4; ++t) k[t] = cells[4 * c + ((perm[c] >> (2 * t)) & 3)];
+    const int e = longest_edge[c];
+    const int a = k[EV[e][0]], b = k[EV[e][1]];
+    if (keyset_has(&iface, edge_key(a, b))) continue;
+    if (keyset_insert(&inserted, edge_key(a, b))) {
+      ins_cells[ni] = (int32_t)c;
+      if (ins_edge_vertices) { ins_edge_vertices[2 * ni] = a; ins_edge_vertices[2 * ni + 1] = b; }
+      ++ni;
+    }
+  }
+  *n_ins = ni;
+  free(iface.slot); free(inserted.slot);
+}
 /* 3-D: 6 edges in DUNE tetrahedron edge order; coarsening disabled (ratioindicator.hh:151-156) so only the
    refine count decides; volume / circumradius cannot influence the result and are not evaluated. */
 void orc_mark_3d(const double* xyz, const double* dist, const int32_t* cells, const uint8_t* perm, int64_t nc,

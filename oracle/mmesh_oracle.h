@@ -138,6 +138,11 @@ void orc_adapt_candidates_2d(const double* xy, int64_t nv, const int32_t* cells,
                              int32_t* ins_segs, int64_t* n_ins_segs, int32_t* rem_segs, int32_t* rem_seg_vertices,
                              int64_t* n_rem_segs);
 
+/* 3-D bulk loop of adapt() (mmesh.hh:828-851): cells whose longest edge enters insert_ (+ its two vertices, id order) */
+void orc_refine_candidates_3d(const int32_t* cells, const uint8_t* perm, int64_t nc, const int8_t* mark,
+                              const uint8_t* longest_edge, const int32_t* tris, int64_t ns,
+                              int32_t* ins_cells, int32_t* ins_edge_vertices, int64_t* n_ins);
+
 /* OpenMP threads used by the batch loops (the reference is single-threaded per rank; 1 by default) */
 void orc_set_threads(int n);
 int orc_num_threads(void);

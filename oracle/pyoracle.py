@@ -241,6 +241,20 @@ def adapt_candidates_2d(xy, cells, perm, cell_nb, mark, longest_edge, segs, imar
                 remove_segs=rems[:n[3].value].copy(), remove_seg_vertices=remsv[:n[3].value].copy())
 
 
+def refine_candidates_3d(cells, perm, mark, longest_edge, tris):
+    cells, tris = _i32(cells), _i32(tris).reshape(-1, 3)
+    perm = np.ascontiguousarray(perm, np.uint8)
+    mark = np.ascontiguousarray(mark, np.int8)
+    longest_edge = np.ascontiguousarray(longest_edge, np.uint8)
+    nc = cells.shape[0]
+    ins = np.empty(nc, np.int32)
+    ev = np.empty((nc, 2), np.int32)
+    n = C.c_int64()
+    lib().orc_refine_candidates_3d(_p(cells), _p(perm), C.c_int64(nc), _p(mark), _p(longest_edge), _p(tris), C.c_int64(tris.shape[0]),
+                                   _p(ins), _p(ev), C.byref(n))
+    return ins[:n.value].copy(), ev[:n.value].copy()
+
+
 def cell_geometry_2d(xy, cell, perm):
     xy, cell = _f64(xy), _i32(cell)
     ctr = np.empty(2)

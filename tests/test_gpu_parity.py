@@ -274,6 +274,14 @@ def test_3d_path(gpu_ctx_factory, oracle):
     rm, rle, rc = oracle.mark(m.xyz, rd, m.cells, m.perm, oracle.Params.from_buffer_copy(bytes(prm)), oracle.distance_max(rd), dim=3)
     assert np.array_equal(marks, rm) and np.array_equal(le, rle) and tuple(counts) == tuple(rc)
     assert 0 < rc[0] < m.nc
+    # insertion candidates of adapt() in 3-D (mmesh.hh:828-851): edge-id dedup over all cells around an edge
+    want_cells, want_ev = oracle.refine_candidates_3d(m.cells, m.perm, rm, rle, m.tris)
+    got_cells = ctx.refinement_candidates()
+    assert got_cells.tolist() == want_cells.tolist() and 0 < len(want_cells) < rc[0]
+    pts, ev = ctx.refinement_points(got_cells)
+    assert np.array_equal(ev, want_ev)
+    a, b = m.xyz[ev[:, 0]], m.xyz[ev[:, 1]]
+    assert np.array_equal(pts, a + 0.5 * (b - a))
     ctx.move_vertices(s)
     assert np.array_equal(ctx.download_coords(), oracle.move(m.xyz, s))
     # P0 trace / skeleton transfer

@@ -103,3 +103,32 @@ def test_adapt_candidates_against_set_emulation(oracle):
     for key in want:
         assert got[key].tolist() == want[key], key
     assert len(want["remove_cells"]) > 0 and len(want["insert_cells"]) > 0
+
+
+def test_refine_candidates_3d_against_set_emulation(oracle):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "dune-mmesh_b200", "python"))
+    from mmesh_b200 import synth
+    m = synth.lattice3d(8)
+    rd = oracle.distance_3d(m.xyz, m.tris)
+    prm = oracle.Params.default()
+    prm.minH, prm.maxH, prm.factor = 0.25 * m.h, 1.3 * m.h, 1.5
+    marks, le, counts = oracle.mark(m.xyz, rd, m.cells, m.perm, prm, oracle.distance_max(rd), dim=3)
+    EV3 = [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3)]
+    iface = set()
+    for t in m.tris.tolist():
+        for i, j in ((0, 1), (0, 2), (1, 2)):
+            iface.add((min(t[i], t[j]), max(t[i], t[j])))
+    inserted, want, want_ev = set(), [], []
+    for c in range(m.nc):
+        if marks[c] != 1:
+            continue
+        k = [int(m.cells[c][(int(m.perm[c]) >> (2 * t)) & 3]) for t in range(4)]
+        a, b = k[EV3[le[c]][0]], k[EV3[le[c]][1]]
+        key = (min(a, b), max(a, b))
+        if key in iface or key in inserted:
+            continue
+        inserted.add(key); want.append(c); want_ev.append([a, b])
+    got, ev = oracle.refine_candidates_3d(m.cells, m.perm, marks, le, m.tris)
+    assert got.tolist() == want and ev.tolist() == want_ev
+    assert 0 < len(want) < counts[0]
