@@ -250,6 +250,32 @@ class MMesh {
     return mass;
   }
 
+  //! One whole time step of the user loop (doc/examples/moving.py:231-252) when no TDS edit intervenes, as a single
+  //! pipelined call on host buffers: markElements() -> ensureVertexMovement(shifts) (numeric part) -> adapt(handle)
+  //! numeric part on the uploaded pairs (ncomp = 0 skips it) -> moveVertices(shifts) -> edge legality of the moved mesh.
+  //! Afterwards getMark/longestEdge/validity()/edgeFlags() hold the step's fields.
+  mmb_step_result step(const std::vector<Coordinate>& shifts, int ncomp = 0, const std::vector<double>* dofsOld = nullptr,
+                       std::vector<double>* dofsNew = nullptr) {
+    requireSize(shifts);
+    indicator_.push();
+    const std::size_t nc = snap_->cells.size();
+    marks_.resize(nc); longest_.resize(nc); valid_.resize(nc); orient_.resize(nc); edgeFlags_.resize(snap_->edges.size());
+    if (ncomp && dofsNew) dofsNew->resize(nc * (std::size_t)ncomp);
+    mmb_step_result r{};
+    const int rc = mmb_adapt_step_host(ctx_, shifts[0].data(), ncomp, (ncomp && dofsOld) ? (int64_t)dofsOld->size() / ncomp : 0,
+                                       (ncomp && dofsOld) ? dofsOld->data() : nullptr, (ncomp && dofsNew) ? dofsNew->data() : nullptr,
+                                       marks_.data(), longest_.data(), valid_.data(), orient_.data(),
+                                       edgeFlags_.empty() ? nullptr : edgeFlags_.data(), &r);
+    if (rc == MMB_ERR_INVALID_CELL_3D)
+      throw GridError("Vertices could not be moved, because the removal of vertices is not supported in 3D!");
+    check(rc);
+    refineMarked_ = r.n_refine; coarsenMarked_ = r.n_coarsen;
+    return r;
+  }
+  const std::vector<uint8_t>& validity() const { return valid_; }          // !(signedVolume_ <= 0) per cell (mmesh.hh:1102)
+  const std::vector<int8_t>& orientation() const { return orient_; }      // exact CGAL orientation sign per cell
+  const std::vector<uint8_t>& edgeFlags() const { return edgeFlags_; }    // 1 legal, 0 illegal, 2 hull edge
+
   //! per-edge in-circle flags (CGAL Delaunay_triangulation_2::is_valid loop, :663-681)
   std::vector<uint8_t> edgeLegality() {
     std::vector<uint8_t> f(snap_->edges.size());
@@ -284,7 +310,8 @@ class MMesh {
   const Snapshot<dim>* snap_ = nullptr;
   RatioIndicator<dim> indicator_;
   std::vector<int8_t> marks_, imarks_;
-  std::vector<uint8_t> longest_, valid_;
+  std::vector<uint8_t> longest_, valid_, edgeFlags_;
+  std::vector<int8_t> orient_;
   std::vector<int32_t> removed_;
   std::vector<Coordinate> full_;
   int64_t refineMarked_ = 0, coarsenMarked_ = 0;

@@ -76,6 +76,25 @@ int main(int argc, char** argv) {
     shifts.pop_back();
     try { grid.moveVertices(shifts); std::printf("sizecheck missing\n"); }
     catch (const InvalidStateException&) { std::printf("sizecheck ok\n"); }
+    {   // the same step as ONE pipelined call on a fresh grid: identical fields
+      MMesh<2> g2(0);
+      s.interfaceVertices.clear();
+      g2.setSnapshot(s);
+      g2.indicator().init();
+      g2.indicator().maxH() *= 0.45;
+      g2.indicator().minH() *= 3.0;
+      shifts.resize(nv);
+      std::ifstream in2(argv[1]);
+      { std::size_t a, b, c, d; in2 >> a >> b >> c >> d; double t; for (std::size_t i = 0; i < 2 * nv; ++i) in2 >> t; for (auto& p : shifts) in2 >> p[0] >> p[1]; }
+      const mmb_step_result r = g2.step(shifts);
+      std::printf("step_counts %lld %lld %lld %lld\nstep_marks", (long long)r.n_refine, (long long)r.n_coarsen, (long long)r.n_invalid, (long long)r.n_illegal);
+      for (std::size_t c = 0; c < nc; ++c) std::printf(" %d", g2.getMark(c));
+      std::printf("\nstep_valid");
+      for (uint8_t f : g2.validity()) std::printf(" %d", (int)f);
+      std::printf("\nstep_legal");
+      for (uint8_t f : g2.edgeFlags()) std::printf(" %d", (int)f);
+      std::printf("\n");
+    }
   } catch (const std::exception& e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

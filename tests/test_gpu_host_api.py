@@ -79,6 +79,11 @@ def test_host_class_user_loop(oracle, tmp_path):
     legal, _ = oracle.legality(oracle.move(m.xy, s), None, m.edges)
     assert np.array_equal(np.array(lines["legal"], int), legal)
     assert lines["preAdapt"] == ["0"] and lines["sizecheck"] == ["ok"]
+    # the fused step() call returns the same fields as the member-by-member loop
+    assert np.array_equal(np.array(lines["step_marks"], int), marks)
+    assert np.array_equal(np.array(lines["step_valid"], int), valid)
+    assert np.array_equal(np.array(lines["step_legal"], int), legal)
+    assert [int(v) for v in lines["step_counts"]] == [int(counts[0]), int(counts[1]), int(ninv), int((legal == 0).sum())]
     # after the (large) move the mesh has inverted cells => ensureInterfaceMovement's pre-check throws (mmesh.hh:926-930)
     _, _, ninv_moved = oracle.trial_validate(oracle.move(m.xy, s), None, m.cells)
     assert lines["ifmove"][0] == ("GridError" if ninv_moved > 0 else "ok")
