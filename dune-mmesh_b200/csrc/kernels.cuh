@@ -782,10 +782,11 @@ __device__ __forceinline__ double2 line_isect(double ax, double ay, double bx, d
 // One clip edge (q1 -> q2) of polygoncutting.hh:17-96 applied to the polygon load(0..n-1), n <= NMAX; the result
 // goes to store(0..m-1), m <= n + n/2 is returned.  Same case analysis, operand order and IEEE operations as the
 // reference, but split into three passes so that the lanes of a warp stay together:
-//   1. side value of every vertex, case code of every edge (outside->inside, inside->outside, drop, keep),
-//   2. the crossing points (a convex polygon has at most one edge of each crossing kind),
-//   3. emission in edge order (pure data movement; further crossings of a kind -- only possible through the
-//      epsilon band -- are computed in place).
+//   1. side value of every vertex, reduced to the three comparison bits the case analysis needs,
+//   2. case masks of the edges by bit operations, the crossing points (a convex polygon has at most one edge of each
+//      crossing kind),
+//   3. emission in edge order, fully unrolled and predicated (pure data movement; further crossings of a kind -- only
+//      possible through the epsilon band -- are computed in place).
 template <int NMAX, class Load, class Store>
 __device__ __forceinline__ int clip_stage(Load load, int n, double q1x, double q1y, double q2x, double q2y, double eps,
                                           Store store) {
@@ -795,42 +796,43 @@ __device__ __forceinline__ int clip_stage(Load load, int n, double q1x, double q
   const double ndQx = -dQx;
   const double iQx = q1x - q2x, iQy = q1y - q2y;
   const double fq = q1x * q2y - q1y * q2x;
-  double f[NMAX];
-#pragma unroll
-  for (int i = 0; i < NMAX; ++i) {
-    f[i] = 0.0;
-    if (i < n) { double x, y; load(i, x, y); f[i] = ndQx * y + dQy * x + q2xq1; }
-  }
-  unsigned codes = 0;           // 2 bits per edge: 0 keep second point, 1 X + second point, 2 X only, 3 nothing
-  int e1 = -1, e2 = -1;
+  // pass 1: side value of every vertex, kept only as three comparison bits (f > eps, f < -eps, f >= -eps: the three
+  // tests of polygoncutting.hh:63-89; NaN makes all of them false exactly as in the reference's if-chain)
+  unsigned Pm = 0, Nm = 0, Gm = 0;
 #pragma unroll
   for (int i = 0; i < NMAX; ++i) {
     if (i < n) {
-      const double first = f[i];
-      double second = f[0];
-      if (i + 1 < NMAX) { if (i + 1 < n) second = f[i + 1 < NMAX ? i + 1 : 0]; }
-      unsigned c = 0;
-      if (first > eps && second < -eps) { c = 1; if (e1 < 0) e1 = i; }
-      else if (first < -eps && second > eps) { c = 2; if (e2 < 0) e2 = i; }
-      else if (first >= -eps && second > eps) c = 3;
-      codes |= c << (2 * i);
+      double x, y; load(i, x, y);
+      const double f = ndQx * y + dQy * x + q2xq1;
+      Pm |= (f > eps ? 1u : 0u) << i; Nm |= (f < -eps ? 1u : 0u) << i; Gm |= (f >= -eps ? 1u : 0u) << i;
     }
   }
+  // pass 2: case of every edge (i, i+1 mod n) from the bits of its end points, with the priority of the reference's
+  // if / else-if chain (the cases are disjoint anyway for eps >= 0):
+  //   c1: first > eps  && second < -eps     c2: first < -eps && second > eps     c3: first >= -eps && second > eps
+  const unsigned Pj = (Pm >> 1) | ((Pm & 1u) << (n - 1)), Nj = (Nm >> 1) | ((Nm & 1u) << (n - 1));
+  const unsigned c1 = Pm & Nj, c2 = Nm & Pj & ~c1, c3 = Gm & Pj & ~(c1 | c2);
+  const int e1 = (int)__ffs(c1) - 1, e2 = (int)__ffs(c2) - 1;      // a convex polygon has at most one edge of each kind
   double2 X1 = make_double2(0.0, 0.0), X2 = X1;
   if (e1 >= 0) { double ax, ay, bx, by; load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by); X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
   if (e2 >= 0) { double ax, ay, bx, by; load(e2, ax, ay); load(e2 + 1 == n ? 0 : e2 + 1, bx, by); X2 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+  // pass 3: emission in edge order (pure data movement, predicated): c1 -> X, second; c2 -> X; c3 -> nothing;
+  // otherwise -> second.  Further crossings of a kind (only possible through the epsilon band) are computed in place.
+  const unsigned isx = c1 | c2, keep = ~(c2 | c3);
   int m = 0;
-  for (int i = 0; i < n; ++i) {
-    const unsigned c = (codes >> (2 * i)) & 3u;
-    if (c == 3u) continue;
-    double bx, by;
-    load(i + 1 == n ? 0 : i + 1, bx, by);
-    if (c != 0u) {
-      double2 X = c == 1u ? X1 : X2;
-      if (i != (c == 1u ? e1 : e2)) { double ax, ay; load(i, ax, ay); X = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
-      store(m, X.x, X.y); ++m;
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      const unsigned bit = 1u << i;
+      const int j = i + 1 == n ? 0 : i + 1;
+      if (isx & bit) {
+        const bool k1 = (c1 & bit) != 0u;
+        double2 X = k1 ? X1 : X2;
+        if (i != (k1 ? e1 : e2)) { double ax, ay, bx, by; load(i, ax, ay); load(j, bx, by); X = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+        store(m, X.x, X.y); ++m;
+      }
+      if (keep & bit) { double bx, by; load(j, bx, by); store(m, bx, by); ++m; }
     }
-    if (c <= 1u) { store(m, bx, by); ++m; }
   }
   return m;
 }
