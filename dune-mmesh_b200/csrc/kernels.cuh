@@ -842,7 +842,7 @@ __device__ __forceinline__ int clip_stage(Load load, int n, double q1x, double q
 // q, q+4, ... and the per-pair partial sums are added in pair order).  The polygons of the three clip stages
 // (<= 4, <= 6, <= 9 vertices) live in shared memory in [slot][thread] layout (bank = thread => conflict free).
 constexpr int PROJ_THREADS = 128;
-template <int NCOMP, int LPC, int MINB>
+template <int NCOMP, int LPC, int MINB, int UNR = 0>
 __global__ void __launch_bounds__(PROJ_THREADS, MINB)
 k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1,
           const int32_t* __restrict__ cv2, const uint8_t* __restrict__ perm, const long long* __restrict__ new_off,
@@ -911,10 +911,19 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
       const double od = (cy[1] - cy[0]) * (cx[2] - cx[1]) - (cx[1] - cx[0]) * (cy[2] - cy[1]);
       const int o = (fabs(od) < 2147483648.0) ? (int)od : 0;
       const bool sw = o > 0;
+      int nC = 3;
       sP[0][tid] = make_double2(cx[0], cy[0]);
       sP[1][tid] = sw ? make_double2(cx[2], cy[2]) : make_double2(cx[1], cy[1]);
       sP[2][tid] = sw ? make_double2(cx[1], cy[1]) : make_double2(cx[2], cy[2]);
-      int nC = 3;
+      if (UNR == 1) {                                       // one instance per clip edge, sized for its input (3, <= 4, <= 6)
+        auto ldP = [&](int k, double& x, double& y) { const double2 v = sP[k][tid]; x = v.x; y = v.y; };
+        auto ldQ = [&](int k, double& x, double& y) { const double2 v = sQ[k][tid]; x = v.x; y = v.y; };
+        auto stP = [&](int k, double x, double y) { sP[k][tid] = make_double2(x, y); };
+        auto stQ = [&](int k, double x, double y) { sQ[k][tid] = make_double2(x, y); };
+        { const double2 q1 = sE[0][tid], q2 = sE[1][tid]; nC = clip_stage<3>(ldP, nC, q1.x, q1.y, q2.x, q2.y, prm.clip_eps, stQ); }
+        { const double2 q1 = sE[1][tid], q2 = sE[2][tid]; nC = clip_stage<4>(ldQ, nC, q1.x, q1.y, q2.x, q2.y, prm.clip_eps, stP); }
+        { const double2 q1 = sE[2][tid], q2 = sE[3][tid]; nC = clip_stage<6>(ldP, nC, q1.x, q1.y, q2.x, q2.y, prm.clip_eps, stQ); }
+      } else
 #pragma unroll 1
       for (int st = 0; st < 3; ++st) {                      // one code instance for the three clip edges
         const double2* in = (st == 1) ? &sQ[0][tid] : &sP[0][tid];
@@ -943,10 +952,9 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
         }
       }
       // fan (points[0], points[j-1], points[j]), cutsettriangulation.hh:57-61
-      double fx = 0, fy = 0, fu = 0, ff1 = 0, ff2 = 0, px = 0, py = 0, pu = 0, pf1 = 0, pf2 = 0;
-      for (int j = 0; j < nC; ++j) {
-        const double2 P = sC[j][tid];
-        double uj = 0, f1 = 0, f2 = 0;
+      // (the first two points are peeled: the loop body then has no position tests)
+      auto eval = [&](const double2 P, double& uj, double& f1, double& f2) {
+        uj = 0.0; f1 = 0.0; f2 = 0.0;
         if (NCOMP == 3) {
           const double d0 = P.x - gO.ox, d1 = P.y - gO.oy;
           uj = u0 + (d0 * gx + d1 * gy);                       // affine old function: u0 + grad . (x - o)
@@ -954,9 +962,19 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
           f1 = e0 * gK.i00 + e1 * gK.i10;                      // barycentric coordinates in the new cell
           f2 = e0 * gK.i01 + e1 * gK.i11;
         }
-        if (j == 0) { fx = P.x; fy = P.y; fu = uj; ff1 = f1; ff2 = f2; }
-        else if (j >= 2) {
-          const double a00 = px - fx, a01 = py - fy, a10 = P.x - fx, a11 = P.y - fy;
+      };
+      const double2 F = sC[0][tid];
+      double2 Pp = sC[1][tid];
+      double fu, ff1, ff2, pu, pf1, pf2;
+      eval(F, fu, ff1, ff2);
+      eval(Pp, pu, pf1, pf2);
+      const double fx = F.x, fy = F.y;
+      for (int j = 2; j < nC; ++j) {
+        const double2 P = sC[j][tid];
+        double uj, f1, f2;
+        eval(P, uj, f1, f2);
+        {
+          const double a00 = Pp.x - fx, a01 = Pp.y - fy, a10 = P.x - fx, a11 = P.y - fy;
           const double aT = fabs(a00 * a11 - a10 * a01) * 0.5;
           if (aT > prm.drop_area) {                                     // cutsettriangulation.hh:60
             cov += aT; npc++;
@@ -976,7 +994,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
             }
           }
         }
-        px = P.x; py = P.y; pu = uj; pf1 = f1; pf2 = f2;
+        Pp = P; pu = uj; pf1 = f1; pf2 = f2;
       }
       }
     }

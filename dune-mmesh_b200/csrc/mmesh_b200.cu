@@ -720,7 +720,7 @@ static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, in
   unsigned nb;
   if (ncomp == 1) {
     nb = grid_for(i1 - i0, PROJ_THREADS);
-    LAUNCH("project_p0", (k_project<1, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS);
+    LAUNCH("project_p0", (k_project<1, 1, 4, 1>), nb, PROJ_THREADS, PROJ_ARGS);
   } else {
     const int var = proj_variant();
     const int lpc = (var == 1 || var == 4) ? 4 : 1;
@@ -731,7 +731,8 @@ static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, in
       case 4: LAUNCH("project_p1", (k_project<3, 4, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 5: LAUNCH("project_p1", (k_project<3, 1, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 6: LAUNCH("project_p1", (k_project<3, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      default: LAUNCH("project_p1", (k_project<3, 1, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 9: LAUNCH("project_p1", (k_project<3, 1, 5, 0>), nb, PROJ_THREADS, PROJ_ARGS); break;   // one looped clip-stage instance
+      default: LAUNCH("project_p1", (k_project<3, 1, 5, 1>), nb, PROJ_THREADS, PROJ_ARGS); break;
     }
   }
   *nblocks = (int)nb;
