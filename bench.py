@@ -305,7 +305,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
-                "note": "project_p1 is fp64-pipe/issue bound (ncu: fp64 pipe 34 %, issue 56 %, 19/32 active lanes), not HBM bound; see DESIGN.md section 4"}
+                "note": "project_p1 is fp64-pipe/issue bound (ncu: fp64 pipe 43 %, issue 55 %, 20/32 active lanes, DRAM traffic = algorithmic bytes), not HBM bound; see DESIGN.md section 4"}
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
     e2e = None
