@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "predicates.cuh"
+#include "clip.cuh"
 
 namespace mmb {
 
@@ -770,72 +771,7 @@ __device__ __forceinline__ void aff2_local(const Aff2& g, double x, double y, do
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// ---- shared-memory Sutherland-Hodgman, organised in convergent passes ------------------------------------------
-// lineIntersectionPoint, polygoncutting.hh:100-114 (iQ = q1 - q2, fq = q1 x q2 hoisted per clip edge)
-__device__ __forceinline__ double2 line_isect(double ax, double ay, double bx, double by, double iQx, double iQy, double fq) {
-  double dPx = ax - bx, dPy = ay - by;
-  const double scale = dPx * iQy - iQx * dPy;
-  const double fp = ax * by - ay * bx;
-  dPx *= fq; dPy *= fq;
-  return make_double2((iQx * fp - dPx) / scale, (iQy * fp - dPy) / scale);
-}
-// One clip edge (q1 -> q2) of polygoncutting.hh:17-96 applied to the polygon load(0..n-1), n <= NMAX; the result
-// goes to store(0..m-1), m <= n + n/2 is returned.  Same case analysis, operand order and IEEE operations as the
-// reference, but split into three passes so that the lanes of a warp stay together:
-//   1. side value of every vertex, reduced to the three comparison bits the case analysis needs,
-//   2. case masks of the edges by bit operations, the crossing points (a convex polygon has at most one edge of each
-//      crossing kind),
-//   3. emission in edge order, fully unrolled and predicated (pure data movement; further crossings of a kind -- only
-//      possible through the epsilon band -- are computed in place).
-template <int NMAX, class Load, class Store>
-__device__ __forceinline__ int clip_stage(Load load, int n, double q1x, double q1y, double q2x, double q2y, double eps,
-                                          Store store) {
-  if (n <= 0) return 0;
-  const double dQx = q2x - q1x, dQy = q2y - q1y;
-  const double q2xq1 = q1y * q2x - q1x * q2y;
-  const double ndQx = -dQx;
-  const double iQx = q1x - q2x, iQy = q1y - q2y;
-  const double fq = q1x * q2y - q1y * q2x;
-  // pass 1: side value of every vertex, kept only as three comparison bits (f > eps, f < -eps, f >= -eps: the three
-  // tests of polygoncutting.hh:63-89; NaN makes all of them false exactly as in the reference's if-chain)
-  unsigned Pm = 0, Nm = 0, Gm = 0;
-#pragma unroll
-  for (int i = 0; i < NMAX; ++i) {
-    if (i < n) {
-      double x, y; load(i, x, y);
-      const double f = ndQx * y + dQy * x + q2xq1;
-      Pm |= (f > eps ? 1u : 0u) << i; Nm |= (f < -eps ? 1u : 0u) << i; Gm |= (f >= -eps ? 1u : 0u) << i;
-    }
-  }
-  // pass 2: case of every edge (i, i+1 mod n) from the bits of its end points, with the priority of the reference's
-  // if / else-if chain (the cases are disjoint anyway for eps >= 0):
-  //   c1: first > eps  && second < -eps     c2: first < -eps && second > eps     c3: first >= -eps && second > eps
-  const unsigned Pj = (Pm >> 1) | ((Pm & 1u) << (n - 1)), Nj = (Nm >> 1) | ((Nm & 1u) << (n - 1));
-  const unsigned c1 = Pm & Nj, c2 = Nm & Pj & ~c1, c3 = Gm & Pj & ~(c1 | c2);
-  const int e1 = (int)__ffs(c1) - 1, e2 = (int)__ffs(c2) - 1;      // a convex polygon has at most one edge of each kind
-  double2 X1 = make_double2(0.0, 0.0), X2 = X1;
-  if (e1 >= 0) { double ax, ay, bx, by; load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by); X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
-  if (e2 >= 0) { double ax, ay, bx, by; load(e2, ax, ay); load(e2 + 1 == n ? 0 : e2 + 1, bx, by); X2 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
-  // pass 3: emission in edge order (pure data movement, predicated): c1 -> X, second; c2 -> X; c3 -> nothing;
-  // otherwise -> second.  Further crossings of a kind (only possible through the epsilon band) are computed in place.
-  const unsigned isx = c1 | c2, keep = ~(c2 | c3);
-  int m = 0;
-#pragma unroll
-  for (int i = 0; i < NMAX; ++i) {
-    if (i < n) {
-      const unsigned bit = 1u << i;
-      const int j = i + 1 == n ? 0 : i + 1;
-      if (isx & bit) {
-        const bool k1 = (c1 & bit) != 0u;
-        double2 X = k1 ? X1 : X2;
-        if (i != (k1 ? e1 : e2)) { double ax, ay, bx, by; load(i, ax, ay); load(j, bx, by); X = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
-        store(m, X.x, X.y); ++m;
-      }
-      if (keep & bit) { double bx, by; load(j, bx, by); store(m, bx, by); ++m; }
-    }
-  }
-  return m;
-}
+// (line_isect / clip_stage: clip.cuh, shared with the CPU unit test of the clip arithmetic)
 
 // Conservative projection old -> new.  LPC lanes cooperate on one new cell (LPC = 1: one thread walks the pairs
 // sequentially, so every bit of the P0 accumulation follows the reference order; LPC = 4: lane q clips pairs

@@ -838,6 +838,14 @@ int orc_sutherland_hodgman(const double* subj6, const double* clip6, double eps,
   for (int i = 0; i < n; ++i) { out[2 * i] = o[i][0]; out[2 * i + 1] = o[i][1]; }
   return n;
 }
+void orc_sutherland_hodgman_batch(const double* subj, const double* clip, int64_t n, double eps, double* out18, int32_t* count) {
+  for (int64_t i = 0; i < n; ++i) {
+    double o[2 * MAXPOLY];
+    const int m = orc_sutherland_hodgman(subj + 6 * i, clip + 6 * i, eps, o);
+    count[i] = m;
+    for (int k = 0; k < 2 * m && k < 18; ++k) out18[18 * i + k] = o[k];
+  }
+}
 /* polygoncutting.hh:121-137 polygonArea */
 double orc_polygon_area(const double* pts, int n) {
   if (n < 3) return 0.0;

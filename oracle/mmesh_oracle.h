@@ -143,6 +143,9 @@ void orc_refine_candidates_3d(const int32_t* cells, const uint8_t* perm, int64_t
                               const uint8_t* longest_edge, const int32_t* tris, int64_t ns,
                               int32_t* ins_cells, int32_t* ins_edge_vertices, int64_t* n_ins);
 
+/* many triangle pairs at once (point lists padded to 9 points) */
+void orc_sutherland_hodgman_batch(const double* subj, const double* clip, int64_t n, double eps, double* out18, int32_t* count);
+
 /* OpenMP threads used by the batch loops (the reference is single-threaded per rank; 1 by default) */
 void orc_set_threads(int n);
 int orc_num_threads(void);

@@ -281,6 +281,15 @@ def sutherland_hodgman(subj, clip, eps=1e-14):
     return out[:2 * n].reshape(n, 2).copy()
 
 
+def sutherland_hodgman_batch(subj, clip, eps=1e-14):
+    subj, clip = _f64(subj).reshape(-1, 6), _f64(clip).reshape(-1, 6)
+    n = subj.shape[0]
+    out = np.zeros((n, 18))
+    cnt = np.zeros(n, np.int32)
+    lib().orc_sutherland_hodgman_batch(_p(subj), _p(clip), C.c_int64(n), C.c_double(eps), _p(out), _p(cnt))
+    return out, cnt
+
+
 def polygon_area(pts):
     pts = _f64(pts)
     return lib().orc_polygon_area(_p(pts), C.c_int(pts.shape[0]))
