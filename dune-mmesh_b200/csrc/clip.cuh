@@ -35,8 +35,8 @@ MMB_HD double2 line_isect(double ax, double ay, double bx, double by, double iQx
 //   1. side value of every vertex, reduced to the three comparison bits the case analysis needs,
 //   2. case masks of the edges by bit operations, the crossing points (a convex polygon has at most one edge of each
 //      crossing kind),
-//   3. emission in edge order, fully unrolled and predicated (pure data movement; further crossings of a kind -- only
-//      possible through the epsilon band -- are computed in place).
+//   3. emission in edge order, fully unrolled and predicated (pure data movement); several crossings of one kind -- only
+//      possible through the epsilon band -- take a generic loop that computes the further ones in place.
 template <int NMAX, class Load, class Store>
 MMB_HD int clip_stage(Load load, int n, double q1x, double q1y, double q2x, double q2y, double eps,
                                           Store store) {
@@ -66,16 +66,27 @@ MMB_HD int clip_stage(Load load, int n, double q1x, double q1y, double q2x, doub
   double2 X1 = make_double2(0.0, 0.0), X2 = X1;
   if (e1 >= 0) { double ax, ay, bx, by; load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by); X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
   if (e2 >= 0) { double ax, ay, bx, by; load(e2, ax, ay); load(e2 + 1 == n ? 0 : e2 + 1, bx, by); X2 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
-  // pass 3: emission in edge order (pure data movement, predicated): c1 -> X, second; c2 -> X; c3 -> nothing;
-  // otherwise -> second.  Further crossings of a kind (only possible through the epsilon band) are computed in place.
-  const unsigned isx = c1 | c2, keep = ~(c2 | c3);
+  // pass 3: emission in edge order (pure data movement): c1 -> X, second; c2 -> X; c3 -> nothing; otherwise -> second.
+  const unsigned keep = ~(c2 | c3);
   int m = 0;
+  if (((c1 & (c1 - 1u)) | (c2 & (c2 - 1u))) == 0u) {
+    // at most one crossing of each kind (always, for a convex polygon outside the epsilon band): unrolled, predicated
 #pragma unroll
-  for (int i = 0; i < NMAX; ++i) {
-    if (i < n) {
+    for (int i = 0; i < NMAX; ++i) {
+      if (i < n) {
+        const unsigned bit = 1u << i;
+        if (c1 & bit) { store(m, X1.x, X1.y); ++m; }
+        if (c2 & bit) { store(m, X2.x, X2.y); ++m; }
+        if (keep & bit) { double bx, by; load(i + 1 == n ? 0 : i + 1, bx, by); store(m, bx, by); ++m; }
+      }
+    }
+  } else {
+    // several crossings of one kind (only through the epsilon band / degenerate input): the others are computed in place
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
       const unsigned bit = 1u << i;
       const int j = i + 1 == n ? 0 : i + 1;
-      if (isx & bit) {
+      if ((c1 | c2) & bit) {
         const bool k1 = (c1 & bit) != 0u;
         double2 X = k1 ? X1 : X2;
         if (i != (k1 ? e1 : e2)) { double ax, ay, bx, by; load(i, ax, ay); load(j, bx, by); X = line_isect(ax, ay, bx, by, iQx, iQy, fq); }

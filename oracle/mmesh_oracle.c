@@ -803,33 +803,50 @@ static inline void line_isect(const double* p1, const double* p2, const double* 
   double ix = dQx - dPx, iy = dQy - dPy;
   out[0] = ix / scale; out[1] = iy / scale;
 }
+/* one clip edge (c0 -> c1) of polygoncutting.hh:31-93 applied to a polygon of nin points; returns the point count, -1 on
+   overflow of MAXPOLY */
+static int sh_clip_edge(const double in[][2], int nin, const double* c0, const double* c1, double eps, double out[][2]) {
+  int nout = 0;
+  for (int ii = 0; ii < nin; ++ii) {
+    const int in2 = (ii + 1) % nin;
+    double dQx = c1[0] - c0[0], dQy = c1[1] - c0[1];
+    double q2xq1 = c0[1] * c1[0] - c0[0] * c1[1];
+    double first = -dQx * in[ii][1] + dQy * in[ii][0] + q2xq1;
+    double second = -dQx * in[in2][1] + dQy * in[in2][0] + q2xq1;
+    if (first > eps && second < -eps) {
+      line_isect(in[ii], in[in2], c0, c1, out[nout]); nout++;
+      out[nout][0] = in[in2][0]; out[nout][1] = in[in2][1]; nout++;
+    } else if (first < -eps && second > eps) {
+      line_isect(in[ii], in[in2], c0, c1, out[nout]); nout++;
+    } else if (first >= -eps && second > eps) {
+      continue;
+    } else {
+      out[nout][0] = in[in2][0]; out[nout][1] = in[in2][1]; nout++;
+    }
+    if (nout > MAXPOLY - 2) return -1; /* cannot happen for triangle/triangle (bound 9) */
+  }
+  return nout;
+}
 /* polygoncutting.hh:17-96 sutherlandHodgman; returns point count (capacity MAXPOLY, rigorous bound 9) */
 static int sh_clip(const double subj[3][2], const double clip[3][2], double eps, double out[MAXPOLY][2]) {
   double in[MAXPOLY][2]; int nout = 3;
   for (int i = 0; i < 3; ++i) { out[i][0] = subj[i][0]; out[i][1] = subj[i][1]; }
   for (int ci = 0; ci < 3; ++ci) {
     const int cn = (ci + 1) % 3;
-    int nin = nout; memcpy(in, out, sizeof(double) * 2 * (size_t)nin); nout = 0;
-    for (int ii = 0; ii < nin; ++ii) {
-      const int in2 = (ii + 1) % nin;
-      double dQx = clip[cn][0] - clip[ci][0], dQy = clip[cn][1] - clip[ci][1];
-      double q2xq1 = clip[ci][1] * clip[cn][0] - clip[ci][0] * clip[cn][1];
-      double first = -dQx * in[ii][1] + dQy * in[ii][0] + q2xq1;
-      double second = -dQx * in[in2][1] + dQy * in[in2][0] + q2xq1;
-      if (first > eps && second < -eps) {
-        line_isect(in[ii], in[in2], clip[ci], clip[cn], out[nout]); nout++;
-        out[nout][0] = in[in2][0]; out[nout][1] = in[in2][1]; nout++;
-      } else if (first < -eps && second > eps) {
-        line_isect(in[ii], in[in2], clip[ci], clip[cn], out[nout]); nout++;
-      } else if (first >= -eps && second > eps) {
-        continue;
-      } else {
-        out[nout][0] = in[in2][0]; out[nout][1] = in[in2][1]; nout++;
-      }
-      if (nout > MAXPOLY - 2) return -1; /* cannot happen for triangle/triangle (bound 9) */
-    }
+    int nin = nout; memcpy(in, out, sizeof(double) * 2 * (size_t)nin);
+    nout = sh_clip_edge(in, nin, clip[ci], clip[cn], eps, out);
+    if (nout < 0) return -1;
   }
   return nout;
+}
+/* one clip edge on a general polygon (<= 6 points in, <= 9 out): unit-test hook for the product's clip stage */
+int orc_clip_edge(const double* poly, int n, const double* q1, const double* q2, double eps, double* out) {
+  double in[MAXPOLY][2], o[MAXPOLY][2];
+  if (n < 0 || n > 6) return -1;
+  for (int i = 0; i < n; ++i) { in[i][0] = poly[2 * i]; in[i][1] = poly[2 * i + 1]; }
+  const int m = n > 0 ? sh_clip_edge(in, n, q1, q2, eps, o) : 0;
+  for (int i = 0; i < m; ++i) { out[2 * i] = o[i][0]; out[2 * i + 1] = o[i][1]; }
+  return m;
 }
 int orc_sutherland_hodgman(const double* subj6, const double* clip6, double eps, double* out) {
   double s[3][2], c[3][2], o[MAXPOLY][2];

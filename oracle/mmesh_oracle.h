@@ -143,6 +143,8 @@ void orc_refine_candidates_3d(const int32_t* cells, const uint8_t* perm, int64_t
                               const uint8_t* longest_edge, const int32_t* tris, int64_t ns,
                               int32_t* ins_cells, int32_t* ins_edge_vertices, int64_t* n_ins);
 
+/* one clip edge q1 -> q2 (polygoncutting.hh:31-93) on a general polygon of n <= 6 points; out holds <= 9 points */
+int orc_clip_edge(const double* poly, int n, const double* q1, const double* q2, double eps, double* out);
 /* many triangle pairs at once (point lists padded to 9 points) */
 void orc_sutherland_hodgman_batch(const double* subj, const double* clip, int64_t n, double eps, double* out18, int32_t* count);
 

@@ -290,6 +290,15 @@ def sutherland_hodgman_batch(subj, clip, eps=1e-14):
     return out, cnt
 
 
+def clip_edge(poly, q1, q2, eps=1e-14):
+    """One clip edge of polygoncutting.hh:31-93 on a general polygon (<= 6 points)."""
+    poly, q1, q2 = _f64(poly), _f64(q1), _f64(q2)
+    out = np.zeros(24)
+    lib().orc_clip_edge.restype = C.c_int
+    n = lib().orc_clip_edge(_p(poly), C.c_int(poly.shape[0]), _p(q1), _p(q2), C.c_double(eps), _p(out))
+    return out[:2 * max(n, 0)].reshape(-1, 2).copy(), n
+
+
 def polygon_area(pts):
     pts = _f64(pts)
     return lib().orc_polygon_area(_p(pts), C.c_int(pts.shape[0]))

@@ -20,6 +20,17 @@ int hc_clip(const double* subj6, const double* clip6, double eps, double* out) {
   for (int k = 0; k < n; ++k) { out[2 * k] = Q[k].x; out[2 * k + 1] = Q[k].y; }
   return n;
 }
+// one clip stage on a general (possibly non-convex) polygon of n <= 6 points: several crossings of one kind occur, which
+// the triangle/triangle chain above practically never produces
+int hc_clip_edge(const double* poly, int n, const double* q1, const double* q2, double eps, double* out) {
+  double2 P[6], Q[9];
+  for (int k = 0; k < n; ++k) P[k] = make_double2(poly[2 * k], poly[2 * k + 1]);
+  auto ldP = [&](int k, double& x, double& y) { x = P[k].x; y = P[k].y; };
+  auto stQ = [&](int k, double x, double y) { Q[k] = make_double2(x, y); };
+  const int m = mmb::clip_stage<6>(ldP, n, q1[0], q1[1], q2[0], q2[1], eps, stQ);
+  for (int k = 0; k < m; ++k) { out[2 * k] = Q[k].x; out[2 * k + 1] = Q[k].y; }
+  return m;
+}
 void hc_clip_batch(const double* subj, const double* clip, long n, double eps, double* out /*[n][18]*/, int* count) {
   for (long i = 0; i < n; ++i) count[i] = hc_clip(subj + 6 * i, clip + 6 * i, eps, out + 18 * i);
 }

@@ -30,6 +30,7 @@ def hc():
                         out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
         return out, cnt
 
+    run.lib = L
     return run
 
 
@@ -65,3 +66,28 @@ def test_product_clip_stages_match_oracle(hc, oracle, eps):
         assert np.array_equal(cnt, rcnt)
         assert np.array_equal(out.view(np.int64), ref.view(np.int64))          # same bits, same order
         assert len(set(cnt.tolist())) >= 4
+
+
+def test_clip_stage_on_non_convex_polygons(hc, oracle):
+    """Random (mostly non-convex) polygons of 3..6 points cross the clip line several times: the generic emission path of
+    clip_stage (more than one crossing of a kind) must reproduce the reference loop as well."""
+    rng = np.random.default_rng(77)
+    L = hc.lib
+    L.hc_clip_edge.restype = C.c_int
+    multi = 0
+    for it in range(20000):
+        n = int(rng.integers(3, 7))
+        poly = rng.integers(0, 9, (n, 2)).astype(np.float64) / 8.0 if it % 3 == 0 else rng.uniform(0, 1, (n, 2))
+        q1, q2 = rng.uniform(0, 1, 2), rng.uniform(0, 1, 2)
+        if it % 3 == 0:
+            q1, q2 = np.array([0.5, 0.0]), np.array([0.5, 1.0])        # lattice points exactly on the clip line
+        eps = [1e-14, 0.0, 1e-2][it % 3]
+        ref, m = oracle.clip_edge(poly, q1, q2, eps)
+        out = np.zeros(24)
+        poly_c, q1_c, q2_c = np.ascontiguousarray(poly), np.ascontiguousarray(q1), np.ascontiguousarray(q2)
+        got = L.hc_clip_edge(poly_c.ctypes.data_as(C.c_void_p), C.c_int(n), q1_c.ctypes.data_as(C.c_void_p),
+                             q2_c.ctypes.data_as(C.c_void_p), C.c_double(eps), out.ctypes.data_as(C.c_void_p))
+        assert got == m, (it, got, m)
+        assert np.array_equal(out[:2 * m].view(np.int64), ref.reshape(-1).view(np.int64)), it
+        multi += int(m > n + 1)                                        # more than two crossings happened
+    assert multi > 100
