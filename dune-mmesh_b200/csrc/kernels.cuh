@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include "predicates.cuh"
 #include "clip.cuh"
+#include "geom.cuh"
 
 namespace mmb {
 
@@ -25,10 +26,7 @@ struct Counters {
   unsigned long long pad_[2];
 };
 
-struct DevParams {
-  double minH, maxH, factor, distProportion, edgeRatio, radiusRatio, clip_eps, drop_area;
-  int clip_translate;
-};
+// (DevParams: geom.cuh)
 
 __device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
 __device__ __forceinline__ double4 ldg4(const double4* p) {
@@ -328,7 +326,7 @@ k_pred_exact(int which, const double* __restrict__ pts, const int32_t* __restric
 //     Plane (dune/mmesh/cgal/triangulationwrapper.hh:14-40); min over ALL facets (distance.hh:42-59,133-140) is
 //     obtained with an AABB tree whose culling is conservative, so the minimum has the brute-force bits.
 // ------------------------------------------------------------------------------------------------------
-struct SegLeaf { double c0x, c0y, c1x, c1y, n0, n1; };   // facet corners (AffineGeometry::corner) + Plane normal
+// (SegLeaf, seg_leaf_make, seg_distance: geom.cuh)
 
 // AABB tree over the facets in Morton order of their (upload-time) midpoints: implicit heap, node i in [1, 2L),
 // children 2i / 2i+1, leaves at L + s.  Boxes are float4 (minx, miny, maxx, maxy) rounded OUTWARD, so every fp32
@@ -350,15 +348,7 @@ k_bvh_build2d(const double2* __restrict__ xy, const int2* __restrict__ segs_sort
   if (t < W && i < ns) {
     const int2 s = segs_sorted[i];
     const double2 v0 = ldg2(xy + s.x), v1 = ldg2(xy + s.y);
-    SegLeaf f;
-    f.c0x = v0.x; f.c0y = v0.y;
-    f.c1x = v0.x + 1.0 * (v1.x - v0.x);                  // corner(1) = origin + J^T e_1
-    f.c1y = v0.y + 1.0 * (v1.y - v0.y);
-    double n0 = f.c0x - f.c1x, n1 = f.c0y - f.c1y;       // Plane: n_ = a - b
-    { const double tt = n0; n0 = n1; n1 = tt; }          // std::swap(n_[0], n_[1])
-    n0 *= -1.0;
-    double nn = 0.0; nn += n0 * n0; nn += n1 * n1; nn = sqrt(nn);
-    f.n0 = n0 / nn; f.n1 = n1 / nn;
+    const SegLeaf f = seg_leaf_make(v0.x, v0.y, v1.x, v1.y);
     leaf[i] = f;
     b = make_float4(__double2float_rd(fmin(f.c0x, f.c1x)), __double2float_rd(fmin(f.c0y, f.c1y)),
                     __double2float_ru(fmax(f.c0x, f.c1x)), __double2float_ru(fmax(f.c0y, f.c1y)));
@@ -391,21 +381,6 @@ k_bvh_build2d(const double2* __restrict__ xy, const int2* __restrict__ segs_sort
     __syncthreads();
   }
   if (t == 0) *ticket = 0;
-}
-__device__ __forceinline__ double seg_distance(const SegLeaf& f, double px, double py) {
-  {  // i = 0: vi = c0, vj = c1
-    const double ax = f.c0x - f.c1x, ay = f.c0y - f.c1y, bx = px - f.c0x, by = py - f.c0y;
-    double sgn = 0.0; sgn += ax * bx; sgn += ay * by;
-    if (sgn >= 0) { double n2 = 0.0; n2 += bx * bx; n2 += by * by; return sqrt(n2); }
-  }
-  {  // i = 1: vi = c1, vj = c0
-    const double ax = f.c1x - f.c0x, ay = f.c1y - f.c0y, bx = px - f.c1x, by = py - f.c1y;
-    double sgn = 0.0; sgn += ax * bx; sgn += ay * by;
-    if (sgn >= 0) { double n2 = 0.0; n2 += bx * bx; n2 += by * by; return sqrt(n2); }
-  }
-  const double dx = px - f.c0x, dy = py - f.c0y;
-  double sd = 0.0; sd += f.n0 * dx; sd += f.n1 * dy;
-  return fabs(sd);
 }
 struct DistQuery {
   double px, py, best, diag;
@@ -511,54 +486,7 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
 //     (+ AffineGeometry of dune-geometry).  One evaluation per cell (the reference evaluates twice,
 //     mmesh.hh:741-742).
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double edge_len2d(double2 a, double2 b) {
-  const double jx = b.x - a.x, jy = b.y - a.y;
-  double s = 0.0; s += jx * jx; s += jy * jy;
-  return sqrt(s);
-}
-__device__ __forceinline__ int indicator2d(const double2 c0, const double2 c1, const double2 c2, double d0, double d1,
-                                           double d2, const DevParams& prm, double maxDist, int& longest) {
-  int refine = 0, coarse = 0;
-  double minE = 1e100, maxE = -1e100, sumE = 0.0;
-  double dist = 0.0; dist += d0; dist += d1; dist += d2; dist /= 3;
-  dist = (dist < maxDist) ? dist : maxDist;
-  const double l = dist / maxDist;
-  const double minH = (1. - l) * prm.minH + l * prm.factor * prm.minH;
-  const double maxH = (1. - l) * prm.maxH + l * prm.factor * prm.maxH;
-  const double len[3] = { edge_len2d(c0, c1), edge_len2d(c0, c2), edge_len2d(c1, c2) };   // DUNE edge order
-  double longestLen = -1e100; longest = -1;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    if (len[i] < minH) coarse++;
-    if (len[i] > maxH) refine++;
-    minE = (len[i] < minE) ? len[i] : minE;
-    maxE = (maxE < len[i]) ? len[i] : maxE;
-    sumE += len[i];
-    if (len[i] > longestLen) { longestLen = len[i]; longest = i; }
-  }
-  const double edgeRatio = maxE / minE;
-  if (edgeRatio > prm.edgeRatio) coarse++;
-  const double j00 = c1.x - c0.x, j01 = c1.y - c0.y, j10 = c2.x - c0.x, j11 = c2.y - c0.y;
-  const double vol = fabs(j00 * j11 - j10 * j01) * 0.5;
-  const double g1x = (c0.x + 1.0 * j00) + 0.0 * j10, g1y = (c0.y + 1.0 * j01) + 0.0 * j11;   // corner(1)
-  const double g2x = (c0.x + 0.0 * j00) + 1.0 * j10, g2y = (c0.y + 0.0 * j01) + 1.0 * j11;   // corner(2)
-  const double innerRadius = 2 * vol / sumE;
-  const double dqx = g1x - c0.x, dqy = g1y - c0.y, drx = g2x - c0.x, dry = g2y - c0.y;
-  const double r2 = drx * drx + dry * dry;
-  const double q2 = dqx * dqx + dqy * dqy;
-  const double den = 2 * det2(dqx, dqy, drx, dry);
-  const double dcx = det2(dry, dqy, r2, q2) / den;
-  const double dcy = -det2(drx, dqx, r2, q2) / den;
-  const double ccx = dcx + c0.x, ccy = dcy + c0.y;
-  const double ox = ccx - c0.x, oy = ccy - c0.y;
-  double o2 = 0.0; o2 += ox * ox; o2 += oy * oy;
-  const double outerRadius = sqrt(o2);
-  const double radiusRatio = outerRadius / (innerRadius * 2);
-  if (radiusRatio > prm.radiusRatio) coarse++;
-  if (coarse > 0) return -1;
-  if (refine > 0) return 1;
-  return 0;
-}
+// (edge_len2d, indicator2d: geom.cuh)
 __global__ void __launch_bounds__(256)
 k_mark2d(const double2* __restrict__ xy, const double* __restrict__ dist, const int32_t* __restrict__ cv0,
          const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2, const uint8_t* __restrict__ perm, int64_t nc,
