@@ -7,7 +7,9 @@
 // C-ABI (include/mmesh_b200.h).  A host adapter that owns a live Dune::MMesh fills `Snapshot` from the CGAL
 // triangulation after every TDS edit (INTEGRATION.md shows the loops) and forwards the calls below.
 #pragma once
+#include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -48,6 +50,138 @@ struct AdaptCandidates {
   std::vector<int32_t> insertSegments;                    // interface elements to bisect
   std::vector<int32_t> removeSegments, removeSegmentVertices;
 };
+
+// ---- ensureInterfaceMovement, the branch for cells that invert under the interface movement (mmesh.hh:935-1078) ----
+// Sequential and rare, therefore host logic: the device reports the inverted cells of the trial movement
+// (mmb_trial_move_validate / mmb_invalid_cells), this function walks them in element order exactly like the reference:
+// non-interface corners are scheduled for removal; a cell whose corners are all interface vertices is resolved through
+// its single interface edge (intersection with the interface element ending in the third vertex -> insertion point, third
+// vertex moved back), by removing a removable interface vertex, or it is an error (GridError, same messages).
+struct InterfaceInsertion {
+  std::array<int32_t, 2> edge;        // ip.edge: the interface edge of the inverted cell (vertex indices, id order)
+  std::array<double, 2> point;        // ip.point = lineIntersectionPoint(interface edge, crossing interface element)
+  int32_t v0;                         // ip.v0 = the third vertex
+  int64_t insertionLevel;             // thirdVertex.insertionLevel() + 1
+  int32_t crossingSegment;            // facet index of the crossing interface element
+  bool componentIsInterfaceEdge;      // ip.connectedcomponent: the longer of (interface edge, crossing element)
+};
+struct InterfaceMovementOutcome {
+  bool change = false;
+  std::vector<int32_t> removed;       // vertices appended to remove_ (in order)
+  std::vector<InterfaceInsertion> inserted;
+};
+inline InterfaceMovementOutcome resolveInterfaceMovement2d(const Snapshot<2>& s, std::vector<std::array<double, 2>> ishifts,
+                                                           const std::vector<int32_t>& invalidCellsOfTrialMove,
+                                                           const std::vector<int32_t>& alreadyRemoved = {}) {
+  using P = std::array<double, 2>;
+  InterfaceMovementOutcome out;
+  const std::size_t nv = s.x.size(), nc = s.cells.size();
+  if (ishifts.size() != s.interfaceVertices.size()) throw InvalidStateException("shifts.size() != number of interface vertices");
+  std::vector<P> xt(s.x.begin(), s.x.end());                                     // moveInterface(shifts), mmesh.hh:933
+  std::vector<int32_t> ivIndex(nv, -1);
+  for (std::size_t i = 0; i < ishifts.size(); ++i) {
+    const std::size_t v = (std::size_t)s.interfaceVertices[i];
+    ivIndex[v] = (int32_t)i;
+    xt[v] = P{ s.x[v][0] + ishifts[i][0], s.x[v][1] + ishifts[i][1] };
+  }
+  auto isIf = [&](int32_t v) { return !s.vflags.empty() && (s.vflags[(std::size_t)v] & 1); };
+  auto bflag = [&](int32_t v) { return !s.vflags.empty() && (s.vflags[(std::size_t)v] & 2); };
+  // incident interface elements per vertex (facet indices, facet order) and the set of interface edges
+  std::vector<std::vector<int32_t>> incident(nv);
+  for (std::size_t f = 0; f < s.facets.size(); ++f) { incident[(std::size_t)s.facets[f][0]].push_back((int32_t)f); incident[(std::size_t)s.facets[f][1]].push_back((int32_t)f); }
+  auto interfaceFacetOf = [&](int32_t a, int32_t b) -> int32_t {                 // isInterface(edge), mmesh.hh:607-621
+    if (!isIf(a) || !isIf(b)) return -1;
+    for (int32_t f : incident[(std::size_t)a]) { const auto& q = s.facets[(std::size_t)f]; if ((q[0] == a && q[1] == b) || (q[0] == b && q[1] == a)) return f; }
+    return -1;
+  };
+  std::vector<int32_t> removedSet(alreadyRemoved);
+  auto removeOnce = [&](int32_t v) {                                             // removed_.insert(id).second
+    for (int32_t r : removedSet) if (r == v) return;
+    removedSet.push_back(v); out.removed.push_back(v); out.change = true;
+  };
+  auto corner1 = [](const P& c0, const P& c1) { return P{ c0[0] + 1.0 * (c1[0] - c0[0]), c0[1] + 1.0 * (c1[1] - c0[1]) }; };   // AffineGeometry::corner(1)
+  auto length = [](const P& a, const P& b) { const double jx = b[0] - a[0], jy = b[1] - a[1]; double q = 0.0; q += jx * jx; q += jy * jy; return std::sqrt(q); };
+  auto invalidNow = [&](std::size_t c) {                                         // signedVolume_ <= 0, TDS order (mmesh.hh:1169-1173)
+    const P &p = xt[(std::size_t)s.cells[c][0]], &q = xt[(std::size_t)s.cells[c][1]], &r = xt[(std::size_t)s.cells[c][2]];
+    const double area = ((q[0] - p[0]) * (r[1] - p[1]) - (r[0] - p[0]) * (q[1] - p[1])) / 2;
+    return area <= 0.0;
+  };
+  std::vector<uint8_t> movedBack(nv, 0), pending(nc, 0);
+  std::vector<int32_t> order(invalidCellsOfTrialMove);
+  for (int32_t c : order) pending[(std::size_t)c] = 1;
+  std::vector<std::vector<int32_t>> cellsOf;                                     // built on the first move-back only
+  std::size_t pos = 0;
+  std::sort(order.begin(), order.end());
+  while (pos < order.size()) {
+    const std::size_t c = (std::size_t)order[pos++];
+    const auto& tds = s.cells[c];
+    if ((movedBack[(std::size_t)tds[0]] | movedBack[(std::size_t)tds[1]] | movedBack[(std::size_t)tds[2]]) && !invalidNow(c)) continue;
+    int32_t k[3];
+    for (int j = 0; j < 3; ++j) k[j] = tds[(s.perm[c] >> (2 * j)) & 3];          // subEntity order = id order
+    bool allInterface = true;
+    for (int j = 0; j < 3; ++j) {                                                // mmesh.hh:945-962
+      if (isIf(k[j])) continue;
+      if (bflag(k[j])) continue;                                                 // boundaryFlag(v) == 1
+      removeOnce(k[j]);
+      allInterface = false;
+    }
+    if (!allInterface) continue;
+    static const int EV[3][2] = { { 0, 1 }, { 0, 2 }, { 1, 2 } };
+    int ie = -1; int32_t ifacet = -1;
+    for (int j = 0; j < 3; ++j) {                                                // mmesh.hh:966-980
+      const int32_t f = interfaceFacetOf(k[EV[j][0]], k[EV[j][1]]);
+      if (f < 0) continue;
+      if (ie >= 0)
+        throw GridError("Interface could not be moved because a constrained cell with more than one interface edge would have negative volume!");
+      ie = j; ifacet = f;
+    }
+    if (ie < 0) {                                                                // mmesh.hh:983-1006
+      bool allNonRemovable = true;
+      for (int j = 0; j < 3; ++j)
+        if (incident[(std::size_t)k[j]].size() == 2) { allNonRemovable = false; removeOnce(k[j]); }   // isRemoveable
+      if (allNonRemovable)
+        throw GridError("Interface could not be moved because a constrained cell without any interface edge would have negative volume!");
+      continue;
+    }
+    const int32_t ea = k[EV[ie][0]], eb = k[EV[ie][1]];
+    const int32_t third = k[3 - EV[ie][0] - EV[ie][1]];
+    int32_t crossing = -1, adj = -1;
+    for (int32_t f : incident[(std::size_t)third]) {                             // mmesh.hh:1021-1036
+      if (crossing >= 0) throw GridError("Interface could not be moved because two interfaces cross!");
+      crossing = f;
+      adj = s.facets[(std::size_t)f][0] == third ? s.facets[(std::size_t)f][1] : s.facets[(std::size_t)f][0];
+    }
+    (void)adj; (void)ifacet;
+    if (crossing < 0) throw GridError("Interface could not be moved because two interfaces cross!");   // unreachable: third is an interface vertex
+    const P c0 = xt[(std::size_t)ea], c1 = corner1(c0, xt[(std::size_t)eb]);     // iegeo.corner(0/1)
+    const P ce0 = xt[(std::size_t)s.facets[(std::size_t)crossing][0]], ce1 = corner1(ce0, xt[(std::size_t)s.facets[(std::size_t)crossing][1]]);
+    // PolygonCutting::lineIntersectionPoint(c0, c1, ce0, ce1), polygoncutting.hh:100-114
+    P dP{ c0[0] - c1[0], c0[1] - c1[1] }, dQ{ ce0[0] - ce1[0], ce0[1] - ce1[1] };
+    const double scale = dP[0] * dQ[1] - dQ[0] * dP[1];
+    const double fq = ce0[0] * ce1[1] - ce0[1] * ce1[0], fp = c0[0] * c1[1] - c0[1] * c1[0];
+    dP[0] *= fq; dP[1] *= fq; dQ[0] *= fp; dQ[1] *= fp;
+    const P x{ (dQ[0] - dP[0]) / scale, (dQ[1] - dP[1]) / scale };
+    double dot = 0.0; dot += (c0[0] - x[0]) * (c1[0] - x[0]); dot += (c0[1] - x[1]) * (c1[1] - x[1]);
+    if (dot > 0.) continue;                                                      // intersection not inside the interface edge
+    InterfaceInsertion ip;
+    ip.edge = { ea, eb }; ip.point = x; ip.v0 = third;
+    ip.insertionLevel = (s.insertionLevel.empty() ? 0 : (int64_t)s.insertionLevel[(std::size_t)third]) + 1;
+    ip.crossingSegment = crossing;
+    ip.componentIsInterfaceEdge = length(c0, c1) > length(ce0, ce1);             // volume() of the two 1-d geometries
+    out.inserted.push_back(ip); out.change = true;
+    // move the third vertex back (mmesh.hh:1072-1076) and re-examine the later cells around it
+    const std::size_t idx = (std::size_t)ivIndex[(std::size_t)third];
+    xt[(std::size_t)third] = P{ xt[(std::size_t)third][0] - ishifts[idx][0], xt[(std::size_t)third][1] - ishifts[idx][1] };
+    ishifts[idx] = P{ 0.0, 0.0 };
+    movedBack[(std::size_t)third] = 1;
+    if (cellsOf.empty()) { cellsOf.resize(nv); for (std::size_t cc = 0; cc < nc; ++cc) for (int j = 0; j < 3; ++j) cellsOf[(std::size_t)s.cells[cc][j]].push_back((int32_t)cc); }
+    bool added = false;
+    for (int32_t cc : cellsOf[(std::size_t)third])
+      if ((std::size_t)cc > c && !pending[(std::size_t)cc]) { pending[(std::size_t)cc] = 1; order.push_back(cc); added = true; }
+    if (added) std::sort(order.begin() + (std::ptrdiff_t)pos, order.end());
+  }
+  return out;
+}
 
 template <int dim> class MMesh;
 
@@ -173,6 +307,21 @@ class MMesh {
     std::vector<int32_t> bad((std::size_t)ninv);
     if (ninv > 0) check(mmb_invalid_cells(ctx_, bad.data(), ninv, &ninv));
     return bad;
+  }
+
+  //! The whole of ensureInterfaceMovement in 2-D (mmesh.hh:920-1088): validity of the current mesh and the inverted cells of the
+  //! trial movement on the device, then the reference's element loop over those cells on the host (removals, intersection
+  //! insertion points, GridError for unresolvable constrained cells).  Scheduled removals are appended to removed().
+  InterfaceMovementOutcome resolveInterfaceMovement(const std::vector<Coordinate>& ishifts) {
+    if constexpr (dim == 2) {
+      const std::vector<int32_t> bad = ensureInterfaceMovement(ishifts);
+      InterfaceMovementOutcome o = resolveInterfaceMovement2d(*snap_, ishifts, bad, removed_);
+      for (int32_t v : o.removed) removed_.push_back(v);
+      return o;
+    } else {
+      ensureInterfaceMovement(ishifts);                  // throws GridError on an inverted cell (mmesh.hh:938-942)
+      return InterfaceMovementOutcome{};
+    }
   }
 
   //! mmesh.hh:736-751 (bulk loop on the device, interface loop on the device, counters like :725-731)
