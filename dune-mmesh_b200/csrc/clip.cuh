@@ -37,15 +37,17 @@ MMB_HD double2 line_isect(double ax, double ay, double bx, double by, double iQx
 //      crossing kind),
 //   3. emission in edge order, fully unrolled and predicated (pure data movement); several crossings of one kind -- only
 //      possible through the epsilon band -- take a generic loop that computes the further ones in place.
-template <int NMAX, class Load, class Store>
-MMB_HD int clip_stage(Load load, int n, double q1x, double q1y, double q2x, double q2y, double eps,
-                                          Store store) {
+// The clip edge enters through three numbers: dQ = q2 - q1 and q2xq1 = q1y*q2x - q1x*q2y (clip_edge_constants).  The other
+// quantities of the reference are exact negations of these (IEEE subtraction is anti-commutative, the products are
+// rounded separately): q1 - q2 = -dQ and q1x*q2y - q1y*q2x = -q2xq1, so they need not be stored per clip edge.
+// CAP = capacity of the output polygon: a result with more than CAP points writes nothing and returns -1 (the caller
+// sends that pair through the generic path); CAP >= NMAX + NMAX/2 can never trigger.
+template <int NMAX, int CAP, class Load, class Store>
+MMB_HD int clip_stage_core(Load load, int n, double dQx, double dQy, double q2xq1, double eps, Store store) {
   if (n <= 0) return 0;
-  const double dQx = q2x - q1x, dQy = q2y - q1y;
-  const double q2xq1 = q1y * q2x - q1x * q2y;
   const double ndQx = -dQx;
-  const double iQx = q1x - q2x, iQy = q1y - q2y;
-  const double fq = q1x * q2y - q1y * q2x;
+  const double iQx = -dQx, iQy = -dQy;
+  const double fq = -q2xq1;
   // pass 1: side value of every vertex, kept only as three comparison bits (f > eps, f < -eps, f >= -eps: the three
   // tests of polygoncutting.hh:63-89; NaN makes all of them false exactly as in the reference's if-chain)
   unsigned Pm = 0, Nm = 0, Gm = 0;
@@ -64,10 +66,29 @@ MMB_HD int clip_stage(Load load, int n, double q1x, double q1y, double q2x, doub
   const unsigned c1 = Pm & Nj, c2 = Nm & Pj & ~c1, c3 = Gm & Pj & ~(c1 | c2);
   const int e1 = mmb_ffs(c1) - 1, e2 = mmb_ffs(c2) - 1;      // a convex polygon has at most one edge of each kind
   double2 X1 = make_double2(0.0, 0.0), X2 = X1;
-  if (e1 >= 0) { double ax, ay, bx, by; load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by); X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
-  if (e2 >= 0) { double ax, ay, bx, by; load(e2, ax, ay); load(e2 + 1 == n ? 0 : e2 + 1, bx, by); X2 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+  if ((e1 | e2) >= 0) {
+    // the usual case when the clip line cuts the polygon: it enters and leaves, one crossing of each kind.  Both points
+    // are computed in one block so that their four independent divisions overlap (same operations, same bits).
+    double ax, ay, bx, by, cx, cy, dx, dy;
+    load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by);
+    load(e2, cx, cy); load(e2 + 1 == n ? 0 : e2 + 1, dx, dy);
+    X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq);
+    X2 = line_isect(cx, cy, dx, dy, iQx, iQy, fq);
+  } else {
+    if (e1 >= 0) { double ax, ay, bx, by; load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by); X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+    if (e2 >= 0) { double ax, ay, bx, by; load(e2, ax, ay); load(e2 + 1 == n ? 0 : e2 + 1, bx, by); X2 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+  }
   // pass 3: emission in edge order (pure data movement): c1 -> X, second; c2 -> X; c3 -> nothing; otherwise -> second.
   const unsigned keep = ~(c2 | c3);
+  if (CAP < NMAX + NMAX / 2) {
+    const unsigned live = (1u << n) - 1u;
+#if defined(__CUDA_ARCH__)
+    const int total = __popc(c1 & live) + __popc(c2 & live) + __popc(keep & live);
+#else
+    const int total = __builtin_popcount(c1 & live) + __builtin_popcount(c2 & live) + __builtin_popcount(keep & live);
+#endif
+    if (total > CAP) return -1;
+  }
   int m = 0;
   if (((c1 & (c1 - 1u)) | (c2 & (c2 - 1u))) == 0u) {
     // at most one crossing of each kind (always, for a convex polygon outside the epsilon band): unrolled, predicated
@@ -96,6 +117,18 @@ MMB_HD int clip_stage(Load load, int n, double q1x, double q1y, double q2x, doub
     }
   }
   return m;
+}
+
+MMB_HD void clip_edge_constants(double q1x, double q1y, double q2x, double q2y, double& dQx, double& dQy, double& q2xq1) {
+  dQx = q2x - q1x; dQy = q2y - q1y;
+  q2xq1 = q1y * q2x - q1x * q2y;
+}
+// the same stage from the two end points of the clip edge (polygoncutting.hh:26-29)
+template <int NMAX, class Load, class Store>
+MMB_HD int clip_stage(Load load, int n, double q1x, double q1y, double q2x, double q2y, double eps, Store store) {
+  double dQx, dQy, q2xq1;
+  clip_edge_constants(q1x, q1y, q2x, q2y, dQx, dQy, q2xq1);
+  return clip_stage_core<NMAX, NMAX + NMAX / 2>(load, n, dQx, dQy, q2xq1, eps, store);
 }
 
 }  // namespace mmb

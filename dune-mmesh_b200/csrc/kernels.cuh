@@ -12,6 +12,7 @@
 #include "predicates.cuh"
 #include "clip.cuh"
 #include "geom.cuh"
+#include "project.cuh"
 
 namespace mmb {
 
@@ -24,7 +25,9 @@ struct Counters {
   unsigned long long minmax_bits[4];              // indicator init: iface min, iface max, bulk min, bulk max
   double mass_new, covered_area;
   unsigned long long pad_[2];
-};
+  unsigned long long dbg[8];                      // development counters (MMB_DEV_VARIANTS builds only)
+  unsigned long long n_invalid_global;            // what gates the fused step's move: n_invalid of ALL ranks (a sharded caller
+};                                                // all-reduces it; single GPU: a copy of n_invalid)
 
 // (DevParams: geom.cuh)
 
@@ -68,7 +71,11 @@ __device__ __forceinline__ void wl_push(bool pred, int item, int32_t* wl, unsign
 // ------------------------------------------------------------------------------------------------------
 // K6  MMesh::moveVertices (dune/mmesh/grid/mmesh.hh:1421-1430): x <- x (+) s, one IEEE add per component
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_move(double2* __restrict__ x, const double2* __restrict__ s, int64_t n2) {
+// gate != nullptr: the fused step's move, withheld on the device when the trial validity pass found an inverted cell
+// (ensureVertexMovement == true => the reference removes vertices before it moves, mmesh.hh:1109-1134)
+__global__ void __launch_bounds__(256) k_move(double2* __restrict__ x, const double2* __restrict__ s, int64_t n2,
+                                              const Counters* __restrict__ gate) {
+  if (gate != nullptr && gate->n_invalid_global != 0ull) return;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
     double2 a = x[i];
@@ -185,7 +192,9 @@ template <bool SHIFT>
 __global__ void __launch_bounds__(128)
 k_exact_orient2d(const double2* __restrict__ xy, const double2* __restrict__ sh, const int32_t* __restrict__ cv0,
                  const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2, const int32_t* __restrict__ wl,
-                 int64_t own_lo, int64_t own_hi, int8_t* __restrict__ orient, Counters* __restrict__ cnt) {
+                 int64_t own_lo, int64_t own_hi, int8_t* __restrict__ orient, Counters* __restrict__ cnt, int publish) {
+  // the validity pass is complete (stream order): single-GPU contexts publish their own count as the gate of the move
+  if (publish && blockIdx.x == 0 && threadIdx.x == 0) cnt->n_invalid_global = cnt->n_invalid;
   const unsigned long long n = cnt->wl_orient;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   unsigned nnonpos = 0, nexact = 0;
@@ -212,15 +221,18 @@ template <bool SHIFT>
 __global__ void __launch_bounds__(256)
 k_legality(const double2* __restrict__ xy, const double2* __restrict__ sh, const int4* __restrict__ edges, int64_t ne,
            const int32_t* __restrict__ tile_lo, int64_t nv, uint8_t* __restrict__ flag, int32_t* __restrict__ wl,
-           Counters* __restrict__ cnt) {
+           Counters* __restrict__ cnt, int gated) {
   __shared__ double2 sxy[WIN];
   const int lo = tile_lo[blockIdx.x];
+  // SHIFT evaluates the flags on x (+) shift, the coordinates the step's move is about to write; when that move is
+  // withheld (gated, an inverted cell was found) the flags describe the mesh as it stays: x
+  const bool shifted = SHIFT && !(gated && cnt->n_invalid_global != 0ull);
 #pragma unroll
   for (int j = threadIdx.x; j < WIN; j += 256) {
     const int v = lo + j;
     if (v < nv) {
       double2 p = ldg2(xy + v);
-      if (SHIFT) { const double2 q = ldg2(sh + v); p.x = p.x + q.x; p.y = p.y + q.y; }
+      if (shifted) { const double2 q = ldg2(sh + v); p.x = p.x + q.x; p.y = p.y + q.y; }
       sxy[j] = p;
     }
   }
@@ -229,7 +241,7 @@ k_legality(const double2* __restrict__ xy, const double2* __restrict__ sh, const
     const unsigned j = (unsigned)(v - lo);
     if (j < (unsigned)WIN) return sxy[j];
     double2 p = ldg2(xy + v);
-    if (SHIFT) { const double2 q = ldg2(sh + v); p.x = p.x + q.x; p.y = p.y + q.y; }
+    if (shifted) { const double2 q = ldg2(sh + v); p.x = p.x + q.x; p.y = p.y + q.y; }
     return p;
   };
   unsigned nill = 0;
@@ -257,15 +269,16 @@ k_legality(const double2* __restrict__ xy, const double2* __restrict__ sh, const
 template <bool SHIFT>
 __global__ void __launch_bounds__(128)
 k_exact_incircle(const double2* __restrict__ xy, const double2* __restrict__ sh, const int4* __restrict__ edges,
-                 const int32_t* __restrict__ wl, uint8_t* __restrict__ flag, Counters* __restrict__ cnt) {
+                 const int32_t* __restrict__ wl, uint8_t* __restrict__ flag, Counters* __restrict__ cnt, int gated) {
   const unsigned long long n = cnt->wl_incircle;
+  const bool shifted = SHIFT && !(gated && cnt->n_invalid_global != 0ull);
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   unsigned nill = 0, nexact = 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int e = wl[i];
     const int4 q = __ldg(edges + e);
     double2 A = ldg2(xy + q.x), B = ldg2(xy + q.y), C = ldg2(xy + q.z), D = ldg2(xy + q.w);
-    if (SHIFT) {
+    if (shifted) {
       const double2 sa = ldg2(sh + q.x), sb = ldg2(sh + q.y), sc = ldg2(sh + q.z), sd = ldg2(sh + q.w);
       A.x = A.x + sa.x; A.y = A.y + sa.y; B.x = B.x + sb.x; B.y = B.y + sb.y;
       C.x = C.x + sc.x; C.y = C.y + sc.y; D.x = D.x + sd.x; D.y = D.y + sd.y;
@@ -426,17 +439,39 @@ struct DistQuery {
     }
   }
 };
-// Per vertex: start from a hint facet (last step's nearest facet; on a cold start the warp leader's full search
-// seeds its Hilbert-neighbours), then walk leaf -> root testing each sibling subtree once.  The siblings along
-// that path partition all other leaves, so the result is the minimum over ALL facets, like distance.hh:42-59.
+// Per warp of 32 Hilbert-consecutive vertices (a compact patch of the mesh):
+//   1. every lane evaluates its hint facet (last step's nearest facet; on a cold start the warp leader's full search seeds
+//      the others) -> an upper bound per lane; the warp keeps the largest one and the bounding box of its 32 points;
+//   2. the warp walks the tree TOGETHER, level by level (lane pairs test the two children of 16 frontier nodes at a time),
+//      keeping the nodes whose box can be closer to the warp's box than the warp's bound, down to the level whose nodes
+//      hold DIST_GROUP leaves: a short list of candidate groups in shared memory;
+//   3. every lane runs the same flat loop over that list with its own, much tighter bound: group box, then leaf boxes,
+//      then the exact reference arithmetic for the few facets that survive.
+// Culling is conservative at both levels (outward-rounded fp32 boxes, bounds rounded up, a point's distance to a box is
+// never below the distance between the warp's box and that box), so the result is the minimum over ALL facets with the
+// brute-force bits, like distance.hh:42-59.  A frontier that outgrows the list (bounds far larger than the facet
+// spacing: no usable hint anywhere in the warp) falls back to the per-lane walk: hint leaf -> root, each sibling subtree
+// searched once.
+constexpr int DIST_GROUP_LOG = 3;            // candidate groups of 8 leaves
+constexpr int DIST_QCAP = 128;               // frontier / candidate capacity per warp
+__device__ __forceinline__ void dist_lane_walk(DistQuery& q, const SegLeaf* __restrict__ leaf, const float4* __restrict__ box,
+                                               int ns, int L, int h) {
+  for (int node = L + h; node > 1; node >>= 1) {
+    const int sib = node ^ 1;
+    if (!(q.lb2(__ldg(box + sib)) > q.T2f)) q.dfs(leaf, box, ns, L, sib);
+  }
+}
 __global__ void __launch_bounds__(256)
 k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restrict__ leaf,
-             const float4* __restrict__ box, int ns, int L, double* __restrict__ dist, int32_t* __restrict__ hint,
+             const float4* __restrict__ box, int ns, int L, int logL, double* __restrict__ dist, int32_t* __restrict__ hint,
              Counters* __restrict__ cnt) {
+  __shared__ int s_front[8][2][DIST_QCAP];
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const bool live = v < nv && ns > 0;
   DistQuery q;
   q.best = 1e100; q.arg = -1;
+  q.px = q.py = 0.0; q.diag = 0.0; q.pxlo = q.pylo = INFINITY; q.pxhi = q.pyhi = -INFINITY; q.T2f = 0.f;
   if (live) {
     const double2 p = ldg2(xy + v);
     q.px = p.x; q.py = p.y;
@@ -451,30 +486,97 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
   const unsigned cold = __ballot_sync(0xffffffffu, live && h < 0);
   if (cold) {                                            // cold start: one full search per warp seeds the others
     const int leader = __ffs(cold) - 1;
-    if ((threadIdx.x & 31) == leader) q.dfs(leaf, box, ns, L, 1);
+    if (lane == leader) q.dfs(leaf, box, ns, L, 1);
     const int seed = __shfl_sync(0xffffffffu, q.arg, leader);
     if (live && h < 0) h = seed;
   }
-  if (live) {
-    q.eval_leaf(leaf, h);
-    for (int node = L + h; node > 1; node >>= 1) {
-      const int sib = node ^ 1;
-      if (!(q.lb2(__ldg(box + sib)) > q.T2f)) q.dfs(leaf, box, ns, L, sib);
-    }
-    hint[v] = q.arg;
+  if (live) q.eval_leaf(leaf, h);
+  // the warp's bound and box (dead lanes are neutral: T2f = 0, empty box)
+  float U2 = live ? q.T2f : 0.f, bxlo = q.pxlo, bxhi = q.pxhi, bylo = q.pylo, byhi = q.pyhi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    U2 = fmaxf(U2, __shfl_xor_sync(0xffffffffu, U2, o));
+    bxlo = fminf(bxlo, __shfl_xor_sync(0xffffffffu, bxlo, o)); bxhi = fmaxf(bxhi, __shfl_xor_sync(0xffffffffu, bxhi, o));
+    bylo = fminf(bylo, __shfl_xor_sync(0xffffffffu, bylo, o)); byhi = fmaxf(byhi, __shfl_xor_sync(0xffffffffu, byhi, o));
   }
+  const int stop = logL - DIST_GROUP_LOG;                 // level whose nodes hold DIST_GROUP leaves
+  bool flat = __any_sync(0xffffffffu, live) && stop >= 1;
+  int ncur = 1, cb = 0;
+  if (flat) {
+    if (lane == 0) s_front[w][0][0] = 1;
+    __syncwarp();
+    for (int lev = 0; lev < stop && flat; ++lev) {
+      int nnext = 0;
+      for (int base = 0; base < ncur; base += 16) {
+        const int k = base + (lane >> 1);
+        bool pass = false; int child = 0;
+        if (k < ncur) {
+          child = 2 * s_front[w][cb][k] + (lane & 1);
+          const float4 b = __ldg(box + child);
+          const float dx = fmaxf(fmaxf(__fsub_rd(b.x, bxhi), __fsub_rd(bxlo, b.z)), 0.f);
+          const float dy = fmaxf(fmaxf(__fsub_rd(b.y, byhi), __fsub_rd(bylo, b.w)), 0.f);
+          pass = !(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)) > U2);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        const int pos = nnext + __popc(m & ((1u << lane) - 1u));
+        if (pass && pos < DIST_QCAP) s_front[w][cb ^ 1][pos] = child;
+        nnext += __popc(m);
+      }
+      __syncwarp();
+      if (nnext > DIST_QCAP) flat = false;                // frontier outgrew the list: per-lane walk instead
+      ncur = nnext; cb ^= 1;
+    }
+  }
+#ifdef MMB_DEV_VARIANTS
+  unsigned dbg_g = 0, dbg_l = 0, dbg_e = 0;
+#endif
+  if (flat) {
+    if (live) {
+      for (int k = 0; k < ncur; ++k) {
+        const int g = s_front[w][cb][k];
+        if (q.lb2(__ldg(box + g)) > q.T2f) continue;
+#ifdef MMB_DEV_VARIANTS
+        if (__activemask() != 0 && lane == __ffs(__activemask()) - 1) dbg_g++;
+#endif
+        const int s0 = (g << DIST_GROUP_LOG) - L;
+#pragma unroll 1
+        for (int c = 0; c < (1 << DIST_GROUP_LOG); ++c) {
+          const int s = s0 + c;
+          if (s < ns && s != h && !(q.lb2(__ldg(box + L + s)) > q.T2f)) {
+#ifdef MMB_DEV_VARIANTS
+            if (lane == __ffs(__activemask()) - 1) dbg_e++;
+            dbg_l++;
+#endif
+            q.eval_leaf(leaf, s);
+          }
+        }
+      }
+    }
+  } else if (live) {
+    dist_lane_walk(q, leaf, box, ns, L, h);
+  }
+  if (live) hint[v] = q.arg;
   if (v < nv) dist[v] = q.best;
+#ifdef MMB_DEV_VARIANTS
+  {  // per warp: [0] warps, [1] flat warps, [2] sum of candidate groups, [3] group passes (warp union), [4] leaf evals (warp union), [5] leaf evals (lanes)
+    const unsigned gs = warp_sum(dbg_g), es = warp_sum(dbg_e), ls = warp_sum(dbg_l);
+    if (lane == 0 && __any_sync(0xffffffffu, true)) {
+      atomicAdd(&cnt->dbg[0], 1ull); atomicAdd(&cnt->dbg[1], flat ? 1ull : 0ull); atomicAdd(&cnt->dbg[2], flat ? (unsigned long long)ncur : 0ull);
+      atomicAdd(&cnt->dbg[3], (unsigned long long)gs); atomicAdd(&cnt->dbg[4], (unsigned long long)es); atomicAdd(&cnt->dbg[5], (unsigned long long)ls);
+    }
+  }
+#endif
   // Distance::maximum (distance.hh:118-123): max starting from 0.0; non-negative doubles order like integers
   unsigned long long bits = (v < nv) ? (unsigned long long)__double_as_longlong(q.best) : 0ull;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, bits, o); bits = t > bits ? t : bits; }
   __shared__ unsigned long long sm[8];
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = bits;
+  if (lane == 0) sm[w] = bits;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long m = sm[0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) m = sm[w] > m ? sm[w] : m;
+    for (int ww = 1; ww < 8; ++ww) m = sm[ww] > m ? sm[ww] : m;
     atomicMax(&cnt->max_dist_bits, m);
   }
 }
@@ -625,78 +727,6 @@ k_compact_scatter(const uint8_t* __restrict__ flags, int64_t n, uint8_t match, c
 //     dune/mmesh/grid/polygoncutting.hh:17-114.  One thread walks all old children of one new cell in the
 //     reference order, so accumulation order (and therefore every bit of the P0 result) is the reference's.
 // ------------------------------------------------------------------------------------------------------
-constexpr int MAXPOLY = 12;   // rigorous bound for triangle x triangle with the epsilon cases is 9
-struct Poly { double x[MAXPOLY], y[MAXPOLY]; int n; };
-
-// Sutherland-Hodgman, polygoncutting.hh:17-96.  Same case analysis and the same arithmetic as the reference; the
-// side value of a vertex is computed once and reused as `second` of one edge and `first` of the next (identical
-// expression, identical bits), and the q1 x q2 term of lineIntersectionPoint (:100-114) is hoisted per clip edge.
-__device__ __forceinline__ void sh_clip(const double cx[3], const double cy[3], const double ex[3], const double ey[3],
-                                        double eps, Poly& A, Poly& B, Poly*& result) {
-  Poly* in = &B; Poly* out = &A;
-  out->n = 3;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { out->x[i] = cx[i]; out->y[i] = cy[i]; }
-#pragma unroll 1
-  for (int ci = 0; ci < 3; ++ci) {
-    const int cn = ci == 2 ? 0 : ci + 1;
-    const double q1x = ex[ci], q1y = ey[ci], q2x = ex[cn], q2y = ey[cn];
-    const double dQx = q2x - q1x, dQy = q2y - q1y;
-    const double q2xq1 = q1y * q2x - q1x * q2y;
-    const double ndQx = -dQx;
-    const double iQx = q1x - q2x, iQy = q1y - q2y;          // deltaQ of lineIntersectionPoint
-    const double fq = q1x * q2y - q1y * q2x;
-    { Poly* t = in; in = out; out = t; }
-    const int n = in->n;
-    int m = 0;
-    if (n > 0) {
-      const double f0 = ndQx * in->y[0] + dQy * in->x[0] + q2xq1;
-      double first = f0;
-      double ax = in->x[0], ay = in->y[0];
-#pragma unroll 1
-      for (int ii = 0; ii < n; ++ii) {
-        const int i2 = ii + 1 == n ? 0 : ii + 1;
-        const double bx = in->x[i2], by = in->y[i2];
-        const double second = i2 == 0 ? f0 : ndQx * by + dQy * bx + q2xq1;
-        const bool c1 = first > eps && second < -eps;
-        const bool c2 = first < -eps && second > eps;
-        if (c1 || c2) {
-          double dPx = ax - bx, dPy = ay - by;
-          const double scale = dPx * iQy - iQx * dPy;
-          const double fp = ax * by - ay * bx;
-          dPx *= fq; dPy *= fq;
-          out->x[m] = (iQx * fp - dPx) / scale; out->y[m] = (iQy * fp - dPy) / scale; ++m;
-          if (c1) { out->x[m] = bx; out->y[m] = by; ++m; }
-        } else if (!(first >= -eps && second > eps)) {
-          out->x[m] = bx; out->y[m] = by; ++m;
-        }
-        first = second; ax = bx; ay = by;
-        if (m > MAXPOLY - 2) { m = 0; break; }
-      }
-    }
-    out->n = m;
-  }
-  result = out;
-}
-struct Aff2 { double ox, oy, i00, i01, i10, i11, vol; };
-__device__ __forceinline__ Aff2 aff2_make(double c0x, double c0y, double c1x, double c1y, double c2x, double c2y) {
-  const double a00 = c1x - c0x, a01 = c1y - c0y, a10 = c2x - c0x, a11 = c2y - c0y;
-  const double det = a00 * a11 - a10 * a01;
-  const double detInv = 1.0 / det;
-  Aff2 g;
-  g.ox = c0x; g.oy = c0y;
-  g.i00 = a11 * detInv; g.i10 = -a10 * detInv; g.i01 = -a01 * detInv; g.i11 = a00 * detInv;
-  g.vol = fabs(det) * 0.5;
-  return g;
-}
-__device__ __forceinline__ void aff2_local(const Aff2& g, double x, double y, double& xi, double& eta) {
-  const double d0 = x - g.ox, d1 = y - g.oy;
-  double l0 = 0.0, l1 = 0.0;
-  l0 += d0 * g.i00; l1 += d0 * g.i01;
-  l0 += d1 * g.i10; l1 += d1 * g.i11;
-  xi = l0; eta = l1;
-}
-
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // (line_isect / clip_stage: clip.cuh, shared with the CPU unit test of the clip arithmetic)
@@ -714,8 +744,12 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
           const int32_t* __restrict__ old_idx, const double* __restrict__ dofs_old, double* __restrict__ dofs_new,
           DevParams prm, double* __restrict__ part_mass, double* __restrict__ part_cov, Counters* __restrict__ cnt) {
   __shared__ double2 sP[6][PROJ_THREADS];      // subject triangle, then output of clip edge 1 (<= 6)
-  __shared__ double2 sQ[9][PROJ_THREADS];      // outputs of clip edges 0 (<= 4) and 2 (<= 9)
-  __shared__ double2 sE[4][PROJ_THREADS];      // the new cell's TDS-order corners e0, e1, e2, e0: clip edge st = (sE[st], sE[st+1])
+  __shared__ double2 sQ[UNR >= 2 ? 6 : 9][PROJ_THREADS];      // outputs of clip edges 0 (<= 4) and 2 (<= 9; UNR >= 2: <= 6, else generic path)
+  // UNR < 2: the new cell's TDS-order corners e0, e1, e2, e0 (clip edge st = (sE[st], sE[st+1]));
+  // UNR >= 2: per clip edge st the constants dQx, dQy, q2xq1 (rows 3 st ..), hoisted out of the pair loop
+  __shared__ double sCell[UNR >= 2 ? 9 : 8][PROJ_THREADS];
+  double2 (*sE)[PROJ_THREADS] = reinterpret_cast<double2 (*)[PROJ_THREADS]>(&sCell[0][0]);
+  double (*sEC)[PROJ_THREADS] = sCell;
   __shared__ double2 sG[3][PROJ_THREADS];      // the new cell's inverse affine map (origin, J^-T rows), used by the fan only
   const int tid = threadIdx.x;
   const int64_t gid = (int64_t)blockIdx.x * PROJ_THREADS + tid;
@@ -746,8 +780,18 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
       sG[0][tid] = make_double2(gK.ox, gK.oy); sG[1][tid] = make_double2(gK.i00, gK.i01); sG[2][tid] = make_double2(gK.i10, gK.i11);
     }
   }
-  sE[0][tid] = make_double2(ex[0], ey[0]); sE[1][tid] = make_double2(ex[1], ey[1]);
-  sE[2][tid] = make_double2(ex[2], ey[2]); sE[3][tid] = make_double2(ex[0], ey[0]);
+  if (UNR >= 2) {
+#pragma unroll
+    for (int st = 0; st < 3; ++st) {
+      const int sn = st == 2 ? 0 : st + 1;
+      double dQx, dQy, q2xq1;
+      clip_edge_constants(ex[st], ey[st], ex[sn], ey[sn], dQx, dQy, q2xq1);
+      sEC[3 * st][tid] = dQx; sEC[3 * st + 1][tid] = dQy; sEC[3 * st + 2][tid] = q2xq1;
+    }
+  } else {
+    sE[0][tid] = make_double2(ex[0], ey[0]); sE[1][tid] = make_double2(ex[1], ey[1]);
+    sE[2][tid] = make_double2(ex[2], ey[2]); sE[3][tid] = make_double2(ex[0], ey[0]);
+  }
   double acc0 = 0.0; bool initialize = true;     // P0 running value (reference order)
   double R1 = 0.0, R2 = 0.0, U = 0.0;            // P1 totals over pairs
   long long maxr = live ? (p1 - p0 + LPC - 1) / LPC : 0;
@@ -779,7 +823,15 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
       sP[0][tid] = make_double2(cx[0], cy[0]);
       sP[1][tid] = sw ? make_double2(cx[2], cy[2]) : make_double2(cx[1], cy[1]);
       sP[2][tid] = sw ? make_double2(cx[1], cy[1]) : make_double2(cx[2], cy[2]);
-      if (UNR == 1) {                                       // one instance per clip edge, sized for its input (3, <= 4, <= 6)
+      if (UNR >= 2) {                                       // clip-edge constants hoisted per new cell (sEC)
+        auto ldP = [&](int k, double& x, double& y) { const double2 v = sP[k][tid]; x = v.x; y = v.y; };
+        auto ldQ = [&](int k, double& x, double& y) { const double2 v = sQ[k][tid]; x = v.x; y = v.y; };
+        auto stP = [&](int k, double x, double y) { sP[k][tid] = make_double2(x, y); };
+        auto stQ = [&](int k, double x, double y) { sQ[k][tid] = make_double2(x, y); };
+        nC = clip_stage_core<3, 4>(ldP, nC, sEC[0][tid], sEC[1][tid], sEC[2][tid], prm.clip_eps, stQ);
+        nC = clip_stage_core<4, 6>(ldQ, nC, sEC[3][tid], sEC[4][tid], sEC[5][tid], prm.clip_eps, stP);
+        nC = clip_stage_core<6, 6>(ldP, nC, sEC[6][tid], sEC[7][tid], sEC[8][tid], prm.clip_eps, stQ);
+      } else if (UNR == 1) {                                // one instance per clip edge, sized for its input (3, <= 4, <= 6)
         auto ldP = [&](int k, double& x, double& y) { const double2 v = sP[k][tid]; x = v.x; y = v.y; };
         auto ldQ = [&](int k, double& x, double& y) { const double2 v = sQ[k][tid]; x = v.x; y = v.y; };
         auto stP = [&](int k, double x, double y) { sP[k][tid] = make_double2(x, y); };
@@ -799,7 +851,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
                            [&](int k, double x, double y) { out[k * PROJ_THREADS] = make_double2(x, y); });
       }
       auto& sC = sQ;
-      if (nC >= 3) {                                        // cutsettriangulation.hh:55 `if (points.size() < 3) return;`
+      if (nC >= 3 || nC < 0) {                              // cutsettriangulation.hh:55 `if (points.size() < 3) return;`
       // old DOFs and the old cell's geometry are needed only now (about every second neighbour pair is empty)
       double u0 = 0.0, u1 = 0.0, u2 = 0.0, gx = 0.0, gy = 0.0;
       Aff2 gO, gK;
@@ -827,6 +879,19 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
           f2 = e0 * gK.i01 + e1 * gK.i11;
         }
       };
+      if (NCOMP == 3 && UNR >= 2) {
+        unsigned np = 0;
+        if (nC >= 3)
+          proj_fan<UNR == 3>([&](int k) { return sC[k][tid]; }, nC, u0, gx, gy, gO.ox, gO.oy, make_double2(gK.ox, gK.oy),
+                             make_double2(gK.i00, gK.i01), make_double2(gK.i10, gK.i11), prm.drop_area, r1, r2, u, cov, np);
+        else {                                              // the polygon outgrew its slots: degenerate input only
+          ProjArgs pa; pa.xy = xy; pa.cv0 = cv0; pa.cv1 = cv1; pa.cv2 = cv2; pa.perm = perm; pa.old_xy = old_xy; pa.old_idx = old_idx;
+          pa.dofs_old = dofs_old; pa.prm = prm;
+          const ProjPartial g = proj_pair_generic<UNR == 3>(pa, K, pr);
+          r1 = g.r1; r2 = g.r2; u = g.u; cov += g.cov; np = g.npc;
+        }
+        npc += np;
+      } else {
       const double2 F = sC[0][tid];
       double2 Pp = sC[1][tid];
       double fu, ff1, ff2, pu, pf1, pf2;
@@ -861,6 +926,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
         Pp = P; pu = uj; pf1 = f1; pf2 = f2;
       }
       }
+      }
     }
     if (NCOMP == 3) {
       if (LPC == 1) { R1 += r1; R2 += r2; U += u; }
@@ -893,6 +959,64 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
     part_mass[blockIdx.x] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
     part_cov[blockIdx.x] = (sc[0] + sc[1]) + (sc[2] + sc[3]);
     atomicAdd(&cnt->n_pieces, (unsigned long long)(sn[0] + sn[1] + sn[2] + sn[3]));
+  }
+}
+// DG-P1 projection, tile form (project.cuh): NT pair slots and NT/4 new cells per CTA; phases A-E separated by barriers.
+template <int NT, int MINB, bool FMA>
+__global__ void __launch_bounds__(NT, MINB)
+k_project_tile(const ProjArgs a, double* __restrict__ part_mass, double* __restrict__ part_cov, Counters* __restrict__ cnt) {
+  extern __shared__ __align__(16) unsigned char proj_smem[];
+  ProjTile<NT>& T = *reinterpret_cast<ProjTile<NT>*>(proj_smem);
+  constexpr int NCELL = NT / 4;
+  const int t = threadIdx.x, lane = t & 31;
+  const int64_t i0 = a.i_begin + (int64_t)blockIdx.x * NCELL;
+  const int ncell = (int)((a.nnew - i0) < NCELL ? (a.nnew - i0) : NCELL);
+  const long long p_lo = a.new_off[i0];
+  const int np_tile = (int)(a.new_off[i0 + ncell] - p_lo);
+  bool four = true;
+  if (t < ncell) four = proj_cell_setup<NT>(T, a, t, i0 + t, p_lo) == 4;
+  if (t == 0) T.ndense = 0;
+  const bool uniform = __syncthreads_and(four) != 0;               // every cell of the tile has four pairs: transposed columns
+  for (int cl = 0; cl < np_tile; cl += NT) {
+    const int np = (np_tile - cl) < NT ? (np_tile - cl) : NT;
+    if (!uniform) { if (t < ncell) proj_paint<NT>(T, t, cl); __syncthreads(); }
+    if (t < np) proj_load_pair<NT>(T, a, t, p_lo + cl + t, uniform);    // coalesced: thread t reads pair cl + t
+    __syncthreads();
+    int j = t; bool live = t < np;
+    if (uniform) { const int q = t / NCELL, c = t - q * NCELL; j = 4 * c + q; live = c < ncell; }
+    bool keep = false;
+    if (live) keep = proj_clip_column<NT>(T, a, proj_column<NT>(uniform, j), uniform ? (j >> 2) : T.owner[j]);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);           // C: warp-aggregated append to the dense list
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&T.ndense, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (keep) T.dense[base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+    }
+    __syncthreads();
+    const int nd = T.ndense;
+    if (t < nd) { const int jd = T.dense[t]; proj_integrate<NT, FMA>(T, a, jd, p_lo + cl + jd, uniform); }
+    __syncthreads();
+    if (t == 0) T.ndense = 0;
+    if (t < ncell) proj_gather<NT>(T, t, cl, uniform);
+    if (cl + NT < np_tile) __syncthreads();                        // the next chunk overwrites the columns
+  }
+  double mass = 0.0, cov = 0.0; unsigned npc = 0;
+  if (t < ncell) { mass = proj_finish<NT>(T, a, t); cov = T.acc[3][t]; npc = (unsigned)T.npc[t]; }
+  // deterministic two-level sums: fixed-shape shuffle tree per warp, fixed order over the warps
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mass += __shfl_xor_sync(0xffffffffu, mass, o); cov += __shfl_xor_sync(0xffffffffu, cov, o); }
+  npc = warp_sum(npc);
+  __shared__ double sm[NT / 32], sc[NT / 32]; __shared__ unsigned sn[NT / 32];
+  if (lane == 0) { sm[t >> 5] = mass; sc[t >> 5] = cov; sn[t >> 5] = npc; }
+  __syncthreads();
+  if (t == 0) {
+    double M = sm[0], C = sc[0]; unsigned N = sn[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) { M += sm[w]; C += sc[w]; N += sn[w]; }
+    part_mass[blockIdx.x] = M; part_cov[blockIdx.x] = C;
+    if (N) atomicAdd(&cnt->n_pieces, (unsigned long long)N);
   }
 }
 // pairwise (fixed shape) reduction of the per-block partial sums; one block
@@ -978,7 +1102,8 @@ template <bool SHIFT>
 __global__ void __launch_bounds__(128)
 k_exact_orient3d(const double* __restrict__ x, const double* __restrict__ sh, const int32_t* __restrict__ cv0,
                  const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2, const int32_t* __restrict__ cv3,
-                 const int32_t* __restrict__ wl, int8_t* __restrict__ orient, Counters* __restrict__ cnt) {
+                 const int32_t* __restrict__ wl, int8_t* __restrict__ orient, Counters* __restrict__ cnt, int publish) {
+  if (publish && blockIdx.x == 0 && threadIdx.x == 0) cnt->n_invalid_global = cnt->n_invalid;
   const unsigned long long n = cnt->wl_orient;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   unsigned nnonpos = 0, nexact = 0;
@@ -1475,6 +1600,7 @@ __global__ void k_reduce_vector(const Counters* __restrict__ c, double* __restri
     v[6] = (double)c->n_exact_incircle; v[7] = (double)c->n_pieces; v[8] = c->mass_new; v[9] = c->covered_area;
   }
 }
+
 
 // AoS -> SoA transposition of the uploaded cell table
 __global__ void __launch_bounds__(256)

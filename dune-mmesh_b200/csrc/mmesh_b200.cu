@@ -48,6 +48,7 @@ struct mmb_context {
   cudaStream_t stream = nullptr; bool own_stream = false;
   std::string err;
   int64_t nv = 0, nc = 0, ne = 0, ns = 0, nc_pad = 0;
+  bool sharded = false;             // one of several ranks: the gate of the fused step's move comes from an all-reduce
   int64_t own_lo = 0, own_hi = 0;   // owned cell range (counts); halo cells outside it are evaluated but not counted
   DBuf<int32_t> halo_send_idx, halo_recv_idx; DBuf<double2> halo_send, halo_recv; int64_t n_halo_send = 0, n_halo_recv = 0;
   DBuf<double> reduce_vec;
@@ -200,6 +201,16 @@ int mmb_synchronize(mmb_context* ctx) {
   return MMB_OK;
 }
 int64_t mmb_launch_count(const mmb_context* ctx) { return ctx ? ctx->launches : 0; }
+#ifdef MMB_DEV_VARIANTS
+// development counters of the last kernels (instrumented builds only; not part of the C-ABI header)
+int mmb_dev_counters(mmb_context* ctx, unsigned long long out[8]) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  if (cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return MMB_ERR_CUDA;
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 8; ++i) out[i] = ctx->h_counters->dbg[i];
+  return MMB_OK;
+}
+#endif
 
 int mmb_set_params(mmb_context* ctx, const mmb_params* p) {
   if (!ctx || !p) return MMB_ERR_INVALID_ARG;
@@ -389,10 +400,12 @@ static int stage_shifts(mmb_context* ctx, const double* shifts_host) {
 }
 
 // ---- move ---------------------------------------------------------------------------------------------
-static int do_move(mmb_context* ctx) {
+// gated = the move of the fused step under move_policy 0: withheld on the device when the trial validity pass of this
+// step found an inverted cell (counters.n_invalid_global)
+static int do_move(mmb_context* ctx, bool gated = false) {
   const int64_t n2 = ((int64_t)ctx->nv * ctx->dim + 1) / 2;
   LAUNCH("move", k_move, std::min<unsigned>(grid_for(n2, 256), ctx->num_sms * 16), 256, (double2*)ctx->x.p,
-         (const double2*)ctx->shift.p, n2);
+         (const double2*)ctx->shift.p, n2, gated && ctx->prm.move_policy == 0 ? ctx->counters.p : (const Counters*)nullptr);
   ctx->dist_valid = false;
   return MMB_OK;
 }
@@ -408,6 +421,7 @@ int mmb_move_vertices(mmb_context* ctx, const double* shifts_host) {
 // ---- trial move + validity ------------------------------------------------------------------------------
 static int do_validate(mmb_context* ctx, bool with_shift) {
   Counters* c = ctx->counters.p;
+  const int publish = ctx->sharded ? 0 : 1;      // sharded: the caller all-reduces n_invalid into n_invalid_global
   const unsigned fb = ctx->num_sms * 4;
   if (ctx->dim == 2) {
     const int64_t nc4 = ctx->nc_pad / 4;
@@ -421,10 +435,10 @@ static int do_validate(mmb_context* ctx, bool with_shift) {
              ctx->own_lo, ctx->own_hi, (uint32_t*)ctx->valid_fp.p, (uint32_t*)ctx->orient.p, ctx->wl.p, c);
     if (with_shift)
       LAUNCH("exact_orient2d", k_exact_orient2d<true>, fb, 128, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->own_lo, ctx->own_hi, ctx->orient.p, c);
+             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->own_lo, ctx->own_hi, ctx->orient.p, c, publish);
     else
       LAUNCH("exact_orient2d", k_exact_orient2d<false>, fb, 128, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->own_lo, ctx->own_hi, ctx->orient.p, c);
+             ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->wl.p, ctx->own_lo, ctx->own_hi, ctx->orient.p, c, publish);
   } else {
     if (with_shift)
       LAUNCH("validate3d", k_validate3d<true>, grid_for(ctx->nc, 256), 256, ctx->x.p, ctx->shift.p, ctx->cv[0].p, ctx->cv[1].p,
@@ -434,10 +448,10 @@ static int do_validate(mmb_context* ctx, bool with_shift) {
              ctx->cv[2].p, ctx->cv[3].p, ctx->nc, ctx->valid_fp.p, ctx->orient.p, ctx->wl.p, c);
     if (with_shift)
       LAUNCH("exact_orient3d", k_exact_orient3d<true>, fb, 128, ctx->x.p, ctx->shift.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p,
-             ctx->cv[3].p, ctx->wl.p, ctx->orient.p, c);
+             ctx->cv[3].p, ctx->wl.p, ctx->orient.p, c, publish);
     else
       LAUNCH("exact_orient3d", k_exact_orient3d<false>, fb, 128, ctx->x.p, ctx->shift.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p,
-             ctx->cv[3].p, ctx->wl.p, ctx->orient.p, c);
+             ctx->cv[3].p, ctx->wl.p, ctx->orient.p, c, publish);
   }
   return MMB_OK;
 }
@@ -504,17 +518,18 @@ int mmb_marked_cells(mmb_context* ctx, int which, int32_t* cells_host, int64_t c
 // so the flags are bit-identical to running after the move); the pipelined host step uses it to get the flags out early
 static int do_legality(mmb_context* ctx, bool shifted = false) {
   if (ctx->ne == 0) return MMB_OK;
+  const int gated = ctx->prm.move_policy == 0 ? 1 : 0;    // a withheld move leaves x in place: flags on x then
   if (shifted) {
     LAUNCH("legality", k_legality<true>, grid_for(ctx->ne, TILE), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-           (const int4*)ctx->edges.p, ctx->ne, ctx->tile_lo_edges.p, ctx->nv, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p);
+           (const int4*)ctx->edges.p, ctx->ne, ctx->tile_lo_edges.p, ctx->nv, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p, gated);
     LAUNCH("exact_incircle", k_exact_incircle<true>, ctx->num_sms * 4, 128, (const double2*)ctx->x.p,
-           (const double2*)ctx->shift.p, (const int4*)ctx->edges.p, ctx->wl.p, ctx->edge_flag.p, ctx->counters.p);
+           (const double2*)ctx->shift.p, (const int4*)ctx->edges.p, ctx->wl.p, ctx->edge_flag.p, ctx->counters.p, gated);
     return MMB_OK;
   }
   LAUNCH("legality", k_legality<false>, grid_for(ctx->ne, TILE), 256, (const double2*)ctx->x.p, (const double2*)ctx->shift.p,
-         (const int4*)ctx->edges.p, ctx->ne, ctx->tile_lo_edges.p, ctx->nv, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p);
+         (const int4*)ctx->edges.p, ctx->ne, ctx->tile_lo_edges.p, ctx->nv, ctx->edge_flag.p, ctx->wl.p, ctx->counters.p, 0);
   LAUNCH("exact_incircle", k_exact_incircle<false>, ctx->num_sms * 4, 128, (const double2*)ctx->x.p,
-         (const double2*)ctx->shift.p, (const int4*)ctx->edges.p, ctx->wl.p, ctx->edge_flag.p, ctx->counters.p);
+         (const double2*)ctx->shift.p, (const int4*)ctx->edges.p, ctx->wl.p, ctx->edge_flag.p, ctx->counters.p, 0);
   return MMB_OK;
 }
 int mmb_legality(mmb_context* ctx, uint8_t* flags_host, int64_t* n_illegal) {
@@ -533,14 +548,18 @@ int mmb_legality(mmb_context* ctx, uint8_t* flags_host, int64_t* n_illegal) {
 // ---- distance -------------------------------------------------------------------------------------------
 static int do_distance(mmb_context* ctx) {
   CK(cudaMemsetAsync(&ctx->counters.p->max_dist_bits, 0, sizeof(unsigned long long), ctx->stream));
+#ifdef MMB_DEV_VARIANTS
+  CK(cudaMemsetAsync(ctx->counters.p->dbg, 0, sizeof(ctx->counters.p->dbg), ctx->stream));
+#endif
   const int ns = (int)ctx->ns, L = ctx->L;
   if (ctx->dim == 2) {
     if (ns) {
       LAUNCH("bvh_build2d", k_bvh_build2d, L < 256 ? 1 : L / 256, 256, (const double2*)ctx->x.p, (const int2*)ctx->facets_sorted.p,
              ns, L, ctx->seg_leaf.p, ctx->box2.p, ctx->ticket.p);
     }
+    int logL = 0; while ((1 << logL) < L) ++logL;
     LAUNCH("distance2d", k_distance2d, grid_for(ctx->nv, 256), 256, (const double2*)ctx->x.p, ctx->nv, ctx->seg_leaf.p,
-           ctx->box2.p, ns, L, ctx->dist.p, ctx->seg_hint.p, ctx->counters.p);
+           ctx->box2.p, ns, L, logL, ctx->dist.p, ctx->seg_hint.p, ctx->counters.p);
   } else {
     if (ns) {
       LAUNCH("bvh_build3d", k_bvh_build3d, L < 256 ? 1 : L / 256, 256, ctx->x.p, ctx->facets_sorted.p, ns, L, ctx->tri_leaf.p,
@@ -713,7 +732,24 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
 }
 #define PROJ_ARGS (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p, ctx->new_off.p, ctx->new_cell.p, \
                   i0, i1, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp, ctx->part_a.p + pb0, ctx->part_b.p + pb0, ctx->counters.p
-static int proj_variant() { static int v = -1; if (v < 0) { const char* e = getenv("MMB_PROJ_VARIANT"); v = e ? atoi(e) : 0; } return v; }
+static int proj_variant() { const char* e = getenv("MMB_PROJ_VARIANT"); return e ? atoi(e) : 0; }   // dev builds only (MMB_DEV_VARIANTS)
+extern "C++" {
+template <int NT, int MINB, bool FMA>
+static int launch_project_tile(mmb_context* ctx, const ProjArgs& pa, int pb0, unsigned* nb_out) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_project_tile<NT, MINB, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProjTile<NT>)));
+    attr_set = true;
+  }
+  const unsigned nb = grid_for(pa.nnew - pa.i_begin, NT / 4);
+  {
+    LaunchScope ls_(ctx, "project_p1");
+    k_project_tile<NT, MINB, FMA><<<nb, NT, sizeof(ProjTile<NT>), ctx->stream>>>(pa, ctx->part_a.p + pb0, ctx->part_b.p + pb0, ctx->counters.p);
+  }
+  *nb_out = nb;
+  return MMB_OK;
+}
+}  // extern "C++"
 // projection of the new cells [i0, i1) of the pair CSR; per-block partial sums go to part_[pb0 ...); returns #blocks
 static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, int pb0, int* nblocks) {
   const DevParams dp = dev_params(ctx->prm);
@@ -722,17 +758,24 @@ static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, in
     nb = grid_for(i1 - i0, PROJ_THREADS);
     LAUNCH("project_p0", (k_project<1, 1, 4, 1>), nb, PROJ_THREADS, PROJ_ARGS);
   } else {
-    const int var = proj_variant();
-    const int lpc = (var == 1 || var == 4) ? 4 : 1;
-    nb = grid_for(lpc * (i1 - i0), PROJ_THREADS);
-    switch (var) {
-      case 1: LAUNCH("project_p1", (k_project<3, 4, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      case 3: LAUNCH("project_p1", (k_project<3, 1, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      case 4: LAUNCH("project_p1", (k_project<3, 4, 5>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      case 5: LAUNCH("project_p1", (k_project<3, 1, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      case 6: LAUNCH("project_p1", (k_project<3, 1, 4>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      case 9: LAUNCH("project_p1", (k_project<3, 1, 5, 0>), nb, PROJ_THREADS, PROJ_ARGS); break;   // one looped clip-stage instance
-      default: LAUNCH("project_p1", (k_project<3, 1, 5, 1>), nb, PROJ_THREADS, PROJ_ARGS); break;
+    ProjArgs pa;
+    pa.xy = (const double2*)ctx->x.p; pa.cv0 = ctx->cv[0].p; pa.cv1 = ctx->cv[1].p; pa.cv2 = ctx->cv[2].p; pa.perm = ctx->perm.p;
+    pa.new_off = ctx->new_off.p; pa.new_cell = ctx->new_cell.p; pa.i_begin = i0; pa.nnew = i1;
+    pa.old_xy = ctx->old_xy.p; pa.old_idx = ctx->old_idx.p; pa.dofs_old = ctx->dofs_old.p; pa.dofs_new = ctx->dofs_new.p; pa.prm = dp;
+    switch (proj_variant()) {
+#ifdef MMB_DEV_VARIANTS
+      case 11: TRY((launch_project_tile<128, 7, true>(ctx, pa, pb0, &nb))); break;
+      case 12: TRY((launch_project_tile<256, 3, false>(ctx, pa, pb0, &nb))); break;
+      case 13: TRY((launch_project_tile<256, 3, true>(ctx, pa, pb0, &nb))); break;
+      case 14: TRY((launch_project_tile<128, 6, true>(ctx, pa, pb0, &nb))); break;
+      case 15: TRY((launch_project_tile<128, 5, true>(ctx, pa, pb0, &nb))); break;
+      case 16: TRY((launch_project_tile<256, 2, true>(ctx, pa, pb0, &nb))); break;
+      case 20: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 1>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 21: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 2>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 22: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
+      case 23: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 6, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
+#endif
+      default: TRY((launch_project_tile<128, 7, false>(ctx, pa, pb0, &nb))); break;
     }
   }
   *nblocks = (int)nb;
@@ -972,7 +1015,7 @@ static int step_core(mmb_context* ctx, const double* shifts_host, int ncomp, int
            (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
   TRY(do_validate(ctx, true));      // ensureVertexMovement (trial move, coordinates untouched)
   if (ncomp) TRY(do_project(ctx, ncomp));   // adapt(handle): old children -> new cells, before the real move
-  TRY(do_move(ctx));                // moveVertices
+  TRY(do_move(ctx, true));          // moveVertices (withheld when a cell would invert, unless move_policy == 1)
   if (ctx->dim == 2) TRY(do_legality(ctx));   // in-circle flags of the moved mesh (input of the next host TDS pass)
   CK(cudaGetLastError());
   return MMB_OK;
@@ -986,9 +1029,15 @@ static int step_result(mmb_context* ctx, mmb_step_result* res) {
     res->n_exact_orient = (int64_t)c.n_exact_orient; res->n_exact_incircle = (int64_t)c.n_exact_incircle;
     res->n_pieces = (int64_t)c.n_pieces; memcpy(&res->max_dist, &c.max_dist_bits, 8);
     res->mass_new = c.mass_new; res->covered_area = c.covered_area;
+    const bool withheld = ctx->prm.move_policy == 0 && c.n_invalid_global > 0;
+    res->moved = withheld ? 0 : 1;
     if (ctx->dim == 3 && c.n_invalid > 0) {
       ctx->err = "Vertices could not be moved, because the removal of vertices is not supported in 3D!";
       return MMB_ERR_INVALID_CELL_3D;
+    }
+    if (withheld) {
+      ctx->err = "moveVertices withheld: the trial move inverts cells (ensureVertexMovement == true); remove the vertices first";
+      return MMB_MOVE_WITHHELD;
     }
   }
   return MMB_OK;
@@ -1011,6 +1060,9 @@ int mmb_step_host_begin(mmb_context* ctx, const double* shifts_host, int ncomp, 
   REQUIRE(ncomp == 0 || ctx->dim == 2, MMB_ERR_INVALID_ARG, "projection is 2-D only (geometryInFather, entity.hh:573-594)");
   REQUIRE(ncomp == 0 || ncomp == 1 || ncomp == 3, MMB_ERR_INVALID_ARG, "ncomp must be 0, 1 (P0) or 3 (DG-P1)");
   REQUIRE(shifts_host || ctx->has_shift, MMB_ERR_STATE, "shifts == NULL but no resident shifts");
+  if (ncomp && ctx->nnew > 0)      // same bound as do_project: the pipelined path launches project_range directly
+    REQUIRE(ctx->max_old_idx < (dofs_old_host ? n_old : ctx->n_old), MMB_ERR_INVALID_ARG,
+            "projection: a pair references an old cell beyond the DOF array");
   if (!ctx->s_h2d) { CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)); }
   while (ctx->pipe_ev.size() < 8 + 2 * (size_t)MAX_CHUNKS) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->pipe_ev.push_back(e); }
   cudaStream_t S0 = ctx->stream, S1 = ctx->s_h2d, S2 = ctx->s_d2h;
@@ -1130,7 +1182,7 @@ int mmb_step_host_finish(mmb_context* ctx, double* dofs_new_host, uint8_t* valid
     CK(cudaStreamWaitEvent(S2, ev[4], 0));
     CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, S2));
   }
-  TRY(do_move(ctx));
+  TRY(do_move(ctx, true));
   CK(cudaEventRecord(ev[6], S2));
   if (reduce_vector) {                                             // sharded caller: counts + mass for the SUM all-reduce
     CK(ctx->reduce_vec.ensure(16));
@@ -1291,7 +1343,7 @@ int mmb_step_phase(mmb_context* ctx, int which, int ncomp) {
     return MMB_OK;
   };
   auto move_legality = [&]() -> int {
-    TRY(do_move(ctx));
+    TRY(do_move(ctx, true));
     if (ctx->dim == 2) TRY(do_legality(ctx));
     CK(ctx->reduce_vec.ensure(16));
     LAUNCH("reduce_vector", k_reduce_vector, 1, 32, ctx->counters.p, ctx->reduce_vec.p);

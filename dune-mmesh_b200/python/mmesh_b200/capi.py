@@ -10,7 +10,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # dune-mmesh_b200/
 _SO = os.environ.get("MMB_LIB") or os.path.join(_PKG, "lib", "libmmesh_b200.so")   # MMB_LIB: instrumented debug builds
 
-MMB_OK, MMB_ERR_INVALID_ARG, MMB_ERR_CUDA, MMB_ERR_NCCL, MMB_ERR_INVALID_CELL_3D, MMB_ERR_CAPACITY, MMB_ERR_STATE = range(7)
+MMB_OK, MMB_ERR_INVALID_ARG, MMB_ERR_CUDA, MMB_ERR_NCCL, MMB_ERR_INVALID_CELL_3D, MMB_ERR_CAPACITY, MMB_ERR_STATE, MMB_MOVE_WITHHELD = range(8)
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "NCCL error", 4: "invalid 3-D cell", 5: "capacity", 6: "state"}
 
 EXPORTS = [
@@ -37,14 +37,14 @@ class GridError(MMeshError):
 class Params(C.Structure):
     _fields_ = [("minH", C.c_double), ("maxH", C.c_double), ("factor", C.c_double), ("distProportion", C.c_double),
                 ("edgeRatio", C.c_double), ("radiusRatio", C.c_double), ("clip_eps", C.c_double),
-                ("drop_area", C.c_double), ("clip_translate", C.c_int32), ("pad_", C.c_int32)]
+                ("drop_area", C.c_double), ("clip_translate", C.c_int32), ("move_policy", C.c_int32)]
 
 
 class StepResult(C.Structure):
     _fields_ = [("n_invalid", C.c_int64), ("n_orient_nonpos", C.c_int64), ("n_illegal", C.c_int64),
                 ("n_refine", C.c_int64), ("n_coarsen", C.c_int64), ("n_exact_orient", C.c_int64),
                 ("n_exact_incircle", C.c_int64), ("n_pieces", C.c_int64), ("max_dist", C.c_double),
-                ("mass_new", C.c_double), ("covered_area", C.c_double)]
+                ("mass_new", C.c_double), ("covered_area", C.c_double), ("moved", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -52,7 +52,7 @@ class StepResult(C.Structure):
 
 def build(force=False):
     """Compile the sm_100a library in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_PKG, "csrc", f) for f in ("mmesh_b200.cu", "kernels.cuh", "predicates.cuh")]
+    srcs = [os.path.join(_PKG, "csrc", f) for f in ("mmesh_b200.cu", "kernels.cuh", "predicates.cuh", "clip.cuh", "geom.cuh", "project.cuh")]
     srcs.append(os.path.join(os.path.dirname(_PKG), "include", "mmesh_b200.h"))
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _PKG, "-s"])
@@ -114,7 +114,7 @@ class Context:
             pass
 
     def _ck(self, rc):
-        if rc == MMB_OK:
+        if rc == MMB_OK or rc == MMB_MOVE_WITHHELD:      # withheld move: not an error, StepResult.moved == 0 says so
             return
         msg = lib().mmb_last_error(self._h).decode()
         raise (GridError if rc == MMB_ERR_INVALID_CELL_3D else MMeshError)(rc, msg)

@@ -35,7 +35,11 @@ typedef enum mmb_status {
   MMB_ERR_NCCL = 3,
   MMB_ERR_INVALID_CELL_3D = 4, /* the DUNE_THROW(GridError) of mmesh.hh:1104-1107 */
   MMB_ERR_CAPACITY = 5,
-  MMB_ERR_STATE = 6            /* e.g. mark before distance update, project before upload */
+  MMB_ERR_STATE = 6,           /* e.g. mark before distance update, project before upload */
+  MMB_MOVE_WITHHELD = 7        /* not an error: the step ran, but ensureVertexMovement found cells that would invert
+                                  (n_invalid > 0), so moveVertices was NOT applied -- the caller removes the vertices
+                                  (mmesh.hh:1109-1124 -> adapt()) and moves afterwards, like the reference's user loop.
+                                  All outputs are filled.  Only with mmb_params.move_policy == 0. */
 } mmb_status;
 
 /* Mutable members of RatioIndicator (ratioindicator.hh:165-182,191-199) + the projection constants that are
@@ -46,7 +50,11 @@ typedef struct mmb_params {
   double clip_eps;                /* 1e-14 */
   double drop_area;               /* 1e-8 */
   int32_t clip_translate;         /* 0 = reference arithmetic (default); 1 = clip relative to the new cell's vertex 0 */
-  int32_t pad_;
+  int32_t move_policy;            /* fused step only.  0 (default) = reference order of the user loop: when the trial move
+                                     inverts a cell, ensureVertexMovement returns true and the vertices are removed BEFORE
+                                     moveVertices (doc/examples/moving.py:231-252), so the step withholds the move (decided on
+                                     the device, no host round trip) and returns MMB_MOVE_WITHHELD; 1 = always move (stress
+                                     runs: the resident mesh may then hold inverted cells). */
 } mmb_params;
 
 /* Scalars produced by one adapt step (all reductions are deterministic: fixed-shape trees, no float atomics). */
@@ -60,6 +68,7 @@ typedef struct mmb_step_result {
   double  max_dist;       /* Distance::maximum() (distance.hh:118-123) */
   double  mass_new;       /* sum_K |K| mean(u_K) over projected cells */
   double  covered_area;   /* sum of kept cut-triangle areas */
+  int64_t moved;          /* 1 = moveVertices was applied, 0 = withheld (see MMB_MOVE_WITHHELD) */
 } mmb_step_result;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
