@@ -110,11 +110,14 @@ class ClockSampler:
 CLOCK_WINDOW_S = 0.25      # nvidia-smi samples every 20 ms: keep the load on for at least this long
 
 
+FLAT_PATCH = 64     # lattice vertices per side that keep exact lattice positions and do not move: work for the exact fallback
+
+
 def make_workload(args):
     from mmesh_b200 import synth
     t0 = time.time()
     if args.config == 3:
-        m = synth.config3(nx=args.nx, ny=args.ny)
+        m = synth.config3(nx=args.nx, ny=args.ny, flat_patch=FLAT_PATCH)
         name = "config3: 2-D %dx%d lattice, %d triangles, Hilbert-sorted, 4 sinusoidal interface polylines" % (args.nx, args.ny, 2 * args.nx * args.ny)
     elif args.config == 2:
         m = synth.config2(n=args.nx)
@@ -123,26 +126,43 @@ def make_workload(args):
         m = synth.config1(n=args.nx)
         name = "config1: 2-D unit square, %d triangles, straight interface" % (2 * args.nx * args.nx)
     s = synth.shifts_uniform(m, 0.3 * m.h, 30)
+    if args.config == 3:
+        s[(m.lat[:, 0] < FLAT_PATCH) & (m.lat[:, 1] < FLAT_PATCH)] = 0.0     # the exactly cocircular patch stays exactly cocircular
     new_off, new_cell, old_xy, old_idx = synth.pairs_self_and_neighbours(m, m.xy - s)
-    c = m.xy[m.cells]
     k = np.stack([np.take_along_axis(m.cells, ((m.perm >> (2 * i)) & 3)[:, None].astype(np.int64), 1)[:, 0] for i in range(3)], 1)
     pk = (m.xy - s)[k]
-    dofs = np.sin(np.pi * pk[..., 0]) * np.sin(np.pi * pk[..., 1])          # DG-P1 nodal values of sin(pi x) sin(pi y)
-    del c
+    dofs = np.sin(np.pi * pk[..., 0]) * np.sin(np.pi * pk[..., 1]) + 2.0    # DG-P1 nodal values of sin(pi x) sin(pi y) + 2 (mass 4 + ...)
+    area = 0.5 * np.abs((pk[:, 1, 0] - pk[:, 0, 0]) * (pk[:, 2, 1] - pk[:, 0, 1]) - (pk[:, 2, 0] - pk[:, 0, 0]) * (pk[:, 1, 1] - pk[:, 0, 1]))
+    mass_old = float(np.sum(area * dofs.mean(axis=1)))
     return dict(mesh=m, shifts=s, new_off=new_off, new_cell=new_cell, old_xy=old_xy, old_idx=old_idx, dofs=np.ascontiguousarray(dofs),
-                name=name, gen_s=time.time() - t0)
+                name=name, gen_s=time.time() - t0, mass_old=mass_old, area_old=float(area.sum()))
 
 
-def cpu_reference_step(O, w, sample_cells, prm, threads):
+def tune_params(prm):
+    """Indicator parameters of the bench: RatioIndicator::init, then maxH halved the way users tune the members directly
+    (test-femadaptation.cc:219-220), so that the step produces refinement marks as well as coarsening marks."""
+    prm.maxH *= 0.5
+    return prm
+
+
+def projection_mode(prm, scale_aware):
+    """scale_aware: clip relative to the new cell, no area cut-off -- the only mode that conserves mass on a mesh whose
+    cells (6e-8) are near the reference's absolute 1e-8 cut-off; else the reference's constants."""
+    prm.clip_translate, prm.drop_area = (1, 0.0) if scale_aware else (0, 1e-8)
+    return prm
+
+
+def cpu_reference_step(O, w, sample_cells, prm, threads, culled=False):
     """The restated reference path on a contiguous Hilbert range of cells (a bounded sample of the workload):
-    brute-force Distance::update for the sample's vertices, marks, trial validity, legality of the sample's edges,
+    Distance::update for the sample's vertices -- the reference's brute-force O(Nv*Ns) loop (distance.hh:42-59,133-140), or
+    the labelled culled variant (grid buckets; same values) --, marks, trial validity, legality of the sample's edges,
     projection of the sample's pairs, moveVertices of the sample's vertices."""
     m = w["mesh"]
     O.set_threads(threads)
     cells = m.cells[:sample_cells]
     vs = np.unique(cells)
     t0 = time.perf_counter()
-    dsub = O.distance_2d_subset(m.xy, vs, m.segs)
+    dsub = O.distance_2d_culled(m.xy, m.segs, vs) if culled else O.distance_2d_subset(m.xy, vs, m.segs)
     dist = np.zeros(m.nv)
     dist[vs] = dsub
     maxd = O.distance_max(dsub)
@@ -159,7 +179,9 @@ def cpu_reference_step(O, w, sample_cells, prm, threads):
 
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path = the restated oracle (the reference itself
-    cannot be compiled here: no Boost/GMP/DUNE), with all host threads, each step a bounded sample of the workload."""
+    cannot be compiled here: no Boost/GMP/DUNE), with all host threads, each step a bounded sample of the workload.
+    The headline value uses the reference's own algorithm (brute-force distance); the labelled culled variant is
+    timed beside it and reported as an extra key."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -167,7 +189,7 @@ def run_reference_arm(args):
     O.build()
     w = make_workload(args)
     m = w["mesh"]
-    prm = O.indicator_init_2d(m.xy, m.edges, m.segs, O.Params.default())
+    prm = projection_mode(tune_params(O.indicator_init_2d(m.xy, m.edges, m.segs, O.Params.default())), True)
     threads = os.cpu_count() or 1
     sample = min(m.nc, args.cpu_sample)                   # each step = this bounded sample, all host threads
     for _ in range(max(0, args.warmup)):
@@ -175,12 +197,17 @@ def run_reference_arm(args):
     ts = [cpu_reference_step(O, w, sample, prm, threads) for _ in range(max(1, args.steps))]
     dt = float(np.mean(ts))
     val = sample / dt
+    sample_c = min(m.nc, 8 * args.cpu_sample)             # the culled variant is much faster: a larger sample for a stable time
+    cpu_reference_step(O, w, sample_c, prm, threads, culled=True)
+    dtc = float(np.mean([cpu_reference_step(O, w, sample_c, prm, threads, culled=True) for _ in range(3)]))
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": max(0, args.warmup),
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": w["name"], "projection": "DG-P1, self+face-neighbour pairs (phi=1)"},
+            "config": {"workload": w["name"], "projection": "DG-P1, self+face-neighbour pairs (phi=1), scale-aware clip"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "first %d cells of the Hilbert order (of %d), brute-force O(Nv*Ns) distance as in the reference" % (sample, m.nc)},
+            "cpu_baseline_culled": {"value": sample_c / dtc, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "first %d cells, CULLED distance (grid buckets + ring search; not the reference's loop, same values)" % sample_c},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -226,7 +253,11 @@ def main():
     m = w["mesh"]
     ctx = capi.Context(dim=2, device=local_rank, stream=stream.cuda_stream)
     ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
-    prm = ctx.indicator_init()
+    prm = tune_params(ctx.indicator_init())
+    # stress policy: the 0.3 h random shifts invert a few cells per step (check.n_invalid); the library default (move_policy 0)
+    # would withhold moveVertices then, as the reference removes vertices first -- the bench has no host TDS pass, so it moves
+    prm.move_policy = 1
+    ctx.set_params(projection_mode(prm, True))
     ctx.upload_pairs(w["new_off"], w["new_cell"], w["old_xy"], w["old_idx"])
     ncomp = 3
     ctx.project(ncomp, w["dofs"], download=False)          # DOFs resident
@@ -237,6 +268,22 @@ def main():
     def step_resident():
         ctx.adapt_step(None, ncomp=ncomp, want_result=False)
         ctx.scale_shifts(-1.0)                              # next step moves back: the mesh stays in place on average
+
+    def timed(steps, per_kernel):
+        ctx.timing_enable(per_kernel)
+        ctx.timing_reset()
+        l0 = ctx.launch_count
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ea.record(stream)
+        for _ in range(steps):
+            step_resident()
+        eb.record(stream)
+        torch.cuda.synchronize()
+        out = (ea.elapsed_time(eb), ctx.launch_count - l0, ctx.timing_get() if per_kernel else {})
+        ctx.timing_enable(False)
+        ctx.timing_reset()
+        return out
 
     for _ in range(args.warmup + (args.warmup & 1)):         # even count: the mesh is back at its start position
         step_resident()
@@ -249,23 +296,9 @@ def main():
     # ---- timed region: K resident steps, CUDA events on the launching stream, per-kernel events inside ----
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ctx.timing_enable(True)
-    ctx.timing_reset()
-    l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     clocks.begin()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_resident()
-    e1.record(stream)
-    torch.cuda.synchronize()
+    ms, launches, per_kernel = timed(args.steps, True)
     clocks.end()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count - l0
-    per_kernel = ctx.timing_get()
-    ctx.timing_enable(False)
-    ctx.timing_reset()
     clock_window = "timed region"
     if clocks.loaded_seconds() < CLOCK_WINDOW_S:             # short timed region: keep the same load on (untimed, an even
         n_ext = int(np.ceil(CLOCK_WINDOW_S / max(ms / args.steps * 1e-3, 1e-6)))   # number of steps) so the sampler sees it
@@ -278,6 +311,22 @@ def main():
     clk["window"] = clock_window
     ms_per_step = ms / args.steps
     value = nc / (ms_per_step * 1e-3)
+
+    # ---- the same step with the reference's projection constants (second line of evidence, not the headline) ----
+    ctx.set_params(projection_mode(ctx.get_params(), False))
+    for _ in range(2):
+        step_resident()
+    k2 = max(2, min(args.steps, 6)) // 2 * 2
+    ms_ref, _, pk_ref = timed(k2, True)
+    res_ref = ctx.adapt_step(None, ncomp=ncomp, want_result=True)
+    ctx.scale_shifts(-1.0)
+    step_resident()
+    ctx.set_params(projection_mode(ctx.get_params(), True))
+    ref_mode = {"ms_per_step": ms_ref / k2, "value": nc / (ms_ref / k2 * 1e-3), "steps": k2,
+                "project_p1_ms": pk_ref["project_p1"][0] / pk_ref["project_p1"][1],
+                "covered_area": res_ref.covered_area, "mass_new": res_ref.mass_new, "n_pieces": res_ref.n_pieces,
+                "note": "clip_translate = 0, drop_area = 1e-8 (polygoncutting.hh:63, cutsettriangulation.hh:60): on this mesh (cell area 6e-8) "
+                        "pieces below the absolute cut-off are dropped, so area and mass are NOT conserved -- the reference's behaviour"}
 
     # ---- roofline of the dominant kernel ----
     peaks = {}
@@ -297,74 +346,110 @@ def main():
     kern.sort(key=lambda k: -k["share"])
     dom = kern[0]
     traffic = None
-    try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this workload
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        if tj.get("cells") == nc:
-            traffic = tj["kernels"].get(dom["kernel"])
-    except Exception:
-        pass
+    for tf in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            if tj.get("cells") == nc and dom["kernel"] in tj["kernels"]:
+                traffic = tj["kernels"][dom["kernel"]]
+                break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
-                "note": "project_p1 is fp64-pipe/issue bound (ncu: fp64 pipe 43 %, issue 55 %, 20/32 active lanes, DRAM traffic = algorithmic bytes), not HBM bound; see DESIGN.md section 4"}
+                "note": "project_p1 is fp64-pipe / issue bound (ncu: fp64 pipe 46 %, issue 54 %, 22/32 active lanes, DRAM traffic = algorithmic "
+                        "bytes), not HBM bound; see DESIGN.md section 4"}
+
+    # ---- cold distance field: first Distance::update after a snapshot upload (no hints yet), as after every TDS edit ----
+    ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
+    ctx.timing_enable(True); ctx.timing_reset()
+    ctx.distance_update()
+    tcold = ctx.timing_get(); ctx.timing_enable(False); ctx.timing_reset()
+    ab = algorithmic_bytes("distance2d", nv, nc, ne, ns, npairs, nnew, ncomp)
+    cold_ms = tcold["distance2d"][0] / tcold["distance2d"][1]
+    kern.append({"kernel": "distance2d_cold", "avg_ms": cold_ms, "share": None, "launches_per_step": 0, "algorithmic_bytes": ab,
+                 "achieved_gbs": ab / (cold_ms * 1e-3) / 1e9, "frac": ab / (cold_ms * 1e-3) / 1e9 / peak,
+                 "note": "first update after mmb_upload_mesh (every TDS edit re-uploads); not part of the timed steps"})
+    ctx.upload_pairs(w["new_off"], w["new_cell"], w["old_xy"], w["old_idx"])
+    ctx.project(ncomp, w["dofs"], download=False)
+    ctx.upload_shifts(w["shifts"])
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
-    e2e = None
+    e2e, e2e_var = None, {}
     if not args.no_e2e:
         L = capi.lib()
         h = ctx._h
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        sh = [pin(w["shifts"]), pin(-w["shifts"])]
-        dofs_in = pin(w["dofs"])
-        dofs_out = torch.empty((nc, ncomp), dtype=torch.float64).pin_memory()
-        marks = torch.empty(nc, dtype=torch.int8).pin_memory()
-        longest = torch.empty(nc, dtype=torch.uint8).pin_memory()
-        valid = torch.empty(nc, dtype=torch.uint8).pin_memory()
-        orient = torch.empty(nc, dtype=torch.int8).pin_memory()
-        eflag = torch.empty(ne, dtype=torch.uint8).pin_memory()
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         res = capi.StepResult()
 
-        def step_e2e(i):
-            rc = L.mmb_adapt_step_host(h, P(sh[i & 1]), ctypes.c_int(ncomp), ctypes.c_int64(nc), P(dofs_in), P(dofs_out), P(marks),
-                                       P(longest), P(valid), P(orient), P(eflag), ctypes.byref(res))
-            ctx._ck(rc)
+        def buffers(kind):
+            mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if kind == "pinned" else (lambda a: torch.from_numpy(np.array(a, copy=True)))
+            b = dict(sh=[mk(w["shifts"]), mk(-w["shifts"])], dofs_in=mk(w["dofs"]), dofs_out=mk(np.empty((nc, ncomp))), marks=mk(np.empty(nc, np.int8)),
+                     longest=mk(np.empty(nc, np.uint8)), valid=mk(np.empty(nc, np.uint8)), orient=mk(np.empty(nc, np.int8)), eflag=mk(np.empty(ne, np.uint8)))
+            if kind == "registered":                          # what a C++ caller does with its std::vector storage
+                for t in b["sh"] + [b[k] for k in ("dofs_in", "dofs_out", "marks", "longest", "valid", "orient", "eflag")]:
+                    ctx._ck(L.mmb_host_register(h, P(t), ctypes.c_int64(t.numel() * t.element_size())))
+            return b
 
-        for i in range(2):
-            step_e2e(i)
+        def run_e2e(b, ke):
+            def step_e2e(i):
+                ctx._ck(L.mmb_adapt_step_host(h, P(b["sh"][i & 1]), ctypes.c_int(ncomp), ctypes.c_int64(nc), P(b["dofs_in"]), P(b["dofs_out"]),
+                                              P(b["marks"]), P(b["longest"]), P(b["valid"]), P(b["orient"]), P(b["eflag"]), ctypes.byref(res)))
+            for i in range(2):
+                step_e2e(i)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            for i in range(ke):
+                step_e2e(i)
+            eb.record(stream)
+            torch.cuda.synchronize()
+            return max(ea.elapsed_time(eb), (time.perf_counter() - t0) * 1e3) / ke
+
         ke = max(2, min(args.steps, 10)) // 2 * 2
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for i in range(ke):
-            step_e2e(i)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / ke
         h2d = nv * 16 + nc * ncomp * 8
         d2h = nc * ncomp * 8 + 4 * nc + ne + ctypes.sizeof(capi.StepResult)
-        e2e = {"value": nc / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+        for kind in ("pinned", "registered", "pageable"):
+            b = buffers(kind)
+            t_ms = run_e2e(b, ke if kind != "pageable" else 2)
+            e2e_var[kind] = {"ms_per_step": t_ms, "value": nc / (t_ms * 1e-3)}
+            if kind == "registered":
+                for t in b["sh"] + [b[k] for k in ("dofs_in", "dofs_out", "marks", "longest", "valid", "orient", "eflag")]:
+                    L.mmb_host_unregister(h, P(t))
+            del b
+        e2e = {"value": e2e_var["pinned"]["value"], "unit": UNIT, "ms_per_step": e2e_var["pinned"]["ms_per_step"], "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": ke,
-               "note": "shifts + old DG-P1 DOFs in; marks, longest-edge, valid_fp, orient_sign, edge flags, new DOFs, scalars out"}
+               "note": "shifts + old DG-P1 DOFs in; marks, longest-edge, valid_fp, orient_sign, edge flags, new DOFs, scalars out; pinned host buffers",
+               "buffers": e2e_var}
 
-    # ---- CPU baseline on a bounded sample ----
-    cpu = None
+    # ---- CPU baseline on a bounded sample: the reference's own algorithm (brute-force distance) and the labelled culled variant ----
+    cpu, cpu_culled = None, None
     if not args.no_cpu_baseline:
         from oracle import pyoracle as O
-        oprm = O.Params.from_buffer_copy(bytes(prm))
+        oprm = O.Params.from_buffer_copy(bytes(ctx.get_params()))
         sample = min(nc, args.cpu_sample)
         dt = cpu_reference_step(O, w, sample, oprm, 1)
         cpu = {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
                "sample": "first %d cells of the Hilbert order (of %d), brute-force O(Nv*Ns) distance as in the reference" % (sample, nc)}
+        sample_c = min(nc, 4 * args.cpu_sample)
+        dtc = cpu_reference_step(O, w, sample_c, oprm, 1, culled=True)
+        cpu_culled = {"value": sample_c / dtc, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dtc,
+                      "sample": "first %d cells, CULLED distance (grid buckets + ring search; not the reference's loop, same values)" % sample_c}
 
+    chk = res_check.asdict()
+    chk.update(mass_old=w["mass_old"], mass_rel_err=abs(res_check.mass_new - w["mass_old"]) / abs(w["mass_old"]),
+               area_rel_err=abs(res_check.covered_area - w["area_old"]) / w["area_old"])
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": w["name"], "cells": nc, "vertices": nv, "edges": ne, "interface_segments": ns,
-                       "projection": "DG-P1, self+face-neighbour pairs (phi=1, %d pairs)" % npairs,
-                       "l2_policy": "inputs larger than L2 (%.2f GB touched per step)" % (sum(k["algorithmic_bytes"] or 0 for k in kern) / 1e9),
+                       "projection": "DG-P1, self+face-neighbour pairs (phi=1, %d pairs), scale-aware clip (clip_translate=1, drop_area=0)" % npairs,
+                       "indicator": "RatioIndicator::init, maxH *= 0.5", "exact_patch": "%dx%d unjittered, unshifted lattice vertices" % (FLAT_PATCH, FLAT_PATCH),
+                       "move_policy": "1 (always move; stress: check.n_invalid cells invert under the 0.3 h shifts)",
+                       "l2_policy": "inputs larger than L2 (%.2f GB touched per step)" % (sum(k["algorithmic_bytes"] or 0 for k in kern if k["share"]) / 1e9),
                        "step": "distance+mark -> trial validate -> project -> move -> legality (+ shifts *= -1)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-            "kernels": kern, "check": res_check.asdict(), "setup_s": w["gen_s"]}
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_culled": cpu_culled, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "kernels": kern, "check": chk, "reference_constants": ref_mode, "setup_s": w["gen_s"]}
     print(json.dumps(line), flush=True)
     ctx.close()
 

@@ -453,6 +453,7 @@ struct DistQuery {
 // spacing: no usable hint anywhere in the warp) falls back to the per-lane walk: hint leaf -> root, each sibling subtree
 // searched once.
 constexpr int DIST_GROUP_LOG = 3;            // candidate groups of 8 leaves
+constexpr int DIST_GROUP = 1 << DIST_GROUP_LOG;
 constexpr int DIST_QCAP = 128;               // frontier / candidate capacity per warp
 __device__ __forceinline__ void dist_lane_walk(DistQuery& q, const SegLeaf* __restrict__ leaf, const float4* __restrict__ box,
                                                int ns, int L, int h) {
@@ -461,11 +462,12 @@ __device__ __forceinline__ void dist_lane_walk(DistQuery& q, const SegLeaf* __re
     if (!(q.lb2(__ldg(box + sib)) > q.T2f)) q.dfs(leaf, box, ns, L, sib);
   }
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restrict__ leaf,
              const float4* __restrict__ box, int ns, int L, int logL, double* __restrict__ dist, int32_t* __restrict__ hint,
              Counters* __restrict__ cnt) {
   __shared__ int s_front[8][2][DIST_QCAP];
+  __shared__ float4 s_gbox[8][DIST_QCAP];                 // boxes of the candidate groups (written by the lane that tested them)
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const bool live = v < nv && ns > 0;
@@ -483,12 +485,15 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
   }
   int h = live ? hint[v] : 0;
   if (h >= ns) h = -1;
-  const unsigned cold = __ballot_sync(0xffffffffu, live && h < 0);
-  if (cold) {                                            // cold start: one full search per warp seeds the others
-    const int leader = __ffs(cold) - 1;
-    if (lane == leader) q.dfs(leaf, box, ns, L, 1);
-    const int seed = __shfl_sync(0xffffffffu, q.arg, leader);
-    if (live && h < 0) h = seed;
+  if (__any_sync(0xffffffffu, live && h < 0)) {
+    // cold start (no hint yet): every lane descends greedily to the leaf whose boxes are nearest at each level -- not
+    // necessarily the nearest facet, but a near one: any facet is a valid upper bound, the search below makes it exact
+    int node = 1;
+    for (int lev = 0; lev < logL; ++lev) {
+      const float dl = q.lb2(__ldg(box + 2 * node)), dr = q.lb2(__ldg(box + 2 * node + 1));
+      node = 2 * node + (dr < dl ? 1 : 0);                // empty boxes (leaves >= ns) have an infinite bound: never chosen
+    }
+    if (live && h < 0) h = min(node - L, ns - 1);
   }
   if (live) q.eval_leaf(leaf, h);
   // the warp's bound and box (dead lanes are neutral: T2f = 0, empty box)
@@ -510,16 +515,17 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
       for (int base = 0; base < ncur; base += 16) {
         const int k = base + (lane >> 1);
         bool pass = false; int child = 0;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < ncur) {
           child = 2 * s_front[w][cb][k] + (lane & 1);
-          const float4 b = __ldg(box + child);
+          b = __ldg(box + child);
           const float dx = fmaxf(fmaxf(__fsub_rd(b.x, bxhi), __fsub_rd(bxlo, b.z)), 0.f);
           const float dy = fmaxf(fmaxf(__fsub_rd(b.y, byhi), __fsub_rd(bylo, b.w)), 0.f);
           pass = !(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)) > U2);
         }
         const unsigned m = __ballot_sync(0xffffffffu, pass);
         const int pos = nnext + __popc(m & ((1u << lane) - 1u));
-        if (pass && pos < DIST_QCAP) s_front[w][cb ^ 1][pos] = child;
+        if (pass && pos < DIST_QCAP) { s_front[w][cb ^ 1][pos] = child; s_gbox[w][pos] = b; }
         nnext += __popc(m);
       }
       __syncwarp();
@@ -533,16 +539,22 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
   if (flat) {
     if (live) {
       for (int k = 0; k < ncur; ++k) {
-        const int g = s_front[w][cb][k];
-        if (q.lb2(__ldg(box + g)) > q.T2f) continue;
+        if (q.lb2(s_gbox[w][k]) > q.T2f) continue;
 #ifdef MMB_DEV_VARIANTS
-        if (__activemask() != 0 && lane == __ffs(__activemask()) - 1) dbg_g++;
+        if (lane == __ffs(__activemask()) - 1) dbg_g++;
 #endif
-        const int s0 = (g << DIST_GROUP_LOG) - L;
-#pragma unroll 1
-        for (int c = 0; c < (1 << DIST_GROUP_LOG); ++c) {
+        const int s0 = (s_front[w][cb][k] << DIST_GROUP_LOG) - L;
+        // the group's leaf boxes in one batch (independent loads), then the exact arithmetic for the survivors only
+        const float4* lb = box + L + s0;
+        unsigned need = 0;
+#pragma unroll
+        for (int c = 0; c < DIST_GROUP; ++c) need |= (!(q.lb2(__ldg(lb + c)) > q.T2f) ? 1u : 0u) << c;
+        while (need) {
+          const int c = __ffs(need) - 1; need &= need - 1;
           const int s = s0 + c;
-          if (s < ns && s != h && !(q.lb2(__ldg(box + L + s)) > q.T2f)) {
+          // (the bound has shrunk since the batch test only if an earlier facet of this group improved it: re-test is not
+          // needed for correctness, an extra exact evaluation never changes the minimum)
+          if (s < ns && s != h) {
 #ifdef MMB_DEV_VARIANTS
             if (lane == __ffs(__activemask()) - 1) dbg_e++;
             dbg_l++;
@@ -560,7 +572,7 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
 #ifdef MMB_DEV_VARIANTS
   {  // per warp: [0] warps, [1] flat warps, [2] sum of candidate groups, [3] group passes (warp union), [4] leaf evals (warp union), [5] leaf evals (lanes)
     const unsigned gs = warp_sum(dbg_g), es = warp_sum(dbg_e), ls = warp_sum(dbg_l);
-    if (lane == 0 && __any_sync(0xffffffffu, true)) {
+    if (lane == 0) {
       atomicAdd(&cnt->dbg[0], 1ull); atomicAdd(&cnt->dbg[1], flat ? 1ull : 0ull); atomicAdd(&cnt->dbg[2], flat ? (unsigned long long)ncur : 0ull);
       atomicAdd(&cnt->dbg[3], (unsigned long long)gs); atomicAdd(&cnt->dbg[4], (unsigned long long)es); atomicAdd(&cnt->dbg[5], (unsigned long long)ls);
     }
@@ -1019,20 +1031,36 @@ k_project_tile(const ProjArgs a, double* __restrict__ part_mass, double* __restr
     if (N) atomicAdd(&cnt->n_pieces, (unsigned long long)N);
   }
 }
-// pairwise (fixed shape) reduction of the per-block partial sums; one block
-__global__ void __launch_bounds__(1024)
-k_reduce_partials(const double* __restrict__ a, const double* __restrict__ b, int n, Counters* __restrict__ cnt) {
-  __shared__ double sa[1024], sb[1024];
+// Fixed-shape reduction of the per-block partial sums (deterministic: the shape depends only on n and the grid).  Every
+// block reduces one contiguous slice; the block that finishes last (ticket) adds the slice sums in slice order.
+constexpr int REDUCE_MAX_BLOCKS = 256;
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ slice_a,
+                  double* __restrict__ slice_b, unsigned* __restrict__ ticket, Counters* __restrict__ cnt) {
+  __shared__ double sa[256], sb[256];
+  __shared__ bool last;
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per, hi = min(n, lo + per);
   double xa = 0.0, xb = 0.0;
-  // thread t sums elements t, t+1024, ... (coalesced; the order is a fixed function of n => deterministic)
-  for (int i = threadIdx.x; i < n; i += 1024) { xa += a[i]; xb += b[i]; }
+  for (int i = lo + threadIdx.x; i < hi; i += 256) { xa += a[i]; xb += b[i]; }
   sa[threadIdx.x] = xa; sb[threadIdx.x] = xb;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
+  for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { cnt->mass_new = sa[0]; cnt->covered_area = sb[0]; }
+  if (threadIdx.x == 0) {
+    slice_a[blockIdx.x] = sa[0]; slice_b[blockIdx.x] = sb[0];
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    double ma = 0.0, mb = 0.0;
+    for (unsigned k = 0; k < gridDim.x; ++k) { ma += __ldcg(slice_a + k); mb += __ldcg(slice_b + k); }
+    cnt->mass_new = ma; cnt->covered_area = mb;
+    *ticket = 0;
+  }
 }
 // MMeshCachingEntity::intersectionVolume (dune/mmesh/grid/cachingentity.hh:154-167): |shoelace(SH(vertex_, new))|
 __global__ void __launch_bounds__(128)
@@ -1570,6 +1598,56 @@ __global__ void __launch_bounds__(256)
 k_flag_interface_vertices(const int32_t* __restrict__ facets, int64_t n_entries, uint8_t* __restrict__ v_if) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_entries) v_if[facets[i]] = 1;
+}
+
+// ---- component numbers of adapt_() (mmesh.hh:1194-1218 with getComponentNumber_ :1919-1941) -----------------------------
+// The reference visits the zones (conflict zone of every insertion, star of every removal) in order, gives a zone the
+// smallest number found on its cells or a fresh one, writes it to all its cells, and repeats the whole pass while a zone saw
+// two different numbers.  Its fix point in closed form: a zone is FRESH iff none of its cells belongs to an earlier zone;
+// fresh zones are numbered consecutively in zone order; every zone / cell ends with the smallest number of its connected
+// group (zones connected through shared cells).  => first-zone-per-cell by atomicMin, an exclusive scan over the fresh
+// flags, then min-label propagation zones <-> cells until nothing changes.
+__global__ void __launch_bounds__(256)
+k_cc_first(const long long* __restrict__ zone_off, const int32_t* __restrict__ zone_cells, int64_t nz, int32_t* __restrict__ cell_first) {
+  const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= nz) return;
+  for (long long e = zone_off[z]; e < zone_off[z + 1]; ++e) atomicMin(cell_first + zone_cells[e], (int)z);
+}
+__global__ void __launch_bounds__(256)
+k_cc_fresh(const long long* __restrict__ zone_off, const int32_t* __restrict__ zone_cells, int64_t nz,
+           const int32_t* __restrict__ cell_first, uint32_t* __restrict__ fresh, uint8_t* __restrict__ fresh_flag) {
+  const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= nz) return;
+  bool f = true;
+  for (long long e = zone_off[z]; e < zone_off[z + 1]; ++e) f = f && (cell_first[zone_cells[e]] == (int)z);
+  fresh[z] = f ? 1u : 0u; fresh_flag[z] = f ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+k_cc_init(const uint32_t* __restrict__ prefix, const uint8_t* __restrict__ fresh_flag, int64_t nz, int base, int32_t* __restrict__ label) {
+  const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (z < nz) label[z] = fresh_flag[z] ? base + (int)prefix[z] : 0x7fffffff;
+}
+__global__ void __launch_bounds__(256)
+k_cc_to_cells(const long long* __restrict__ zone_off, const int32_t* __restrict__ zone_cells, int64_t nz,
+              const int32_t* __restrict__ label, int32_t* __restrict__ cell_label) {
+  const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= nz) return;
+  const int l = label[z];
+  for (long long e = zone_off[z]; e < zone_off[z + 1]; ++e) atomicMin(cell_label + zone_cells[e], l);
+}
+__global__ void __launch_bounds__(256)
+k_cc_to_zones(const long long* __restrict__ zone_off, const int32_t* __restrict__ zone_cells, int64_t nz,
+              const int32_t* __restrict__ cell_label, int32_t* __restrict__ label, int* __restrict__ changed) {
+  const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= nz) return;
+  int m = label[z];
+  for (long long e = zone_off[z]; e < zone_off[z + 1]; ++e) m = min(m, cell_label[zone_cells[e]]);
+  if (m < label[z]) { label[z] = m; *changed = 1; }
+}
+__global__ void __launch_bounds__(256)
+k_cc_finish(int32_t* __restrict__ cell_label, int64_t nc) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nc && cell_label[c] >= 0x7f7f7f7f) cell_label[c] = 0;              // not in any zone (still the memset pattern): componentNumber stays 0
 }
 
 // halo exchange helpers: owned values -> contiguous send buffer, received values -> halo slots

@@ -51,7 +51,7 @@ struct mmb_context {
   bool sharded = false;             // one of several ranks: the gate of the fused step's move comes from an all-reduce
   int64_t own_lo = 0, own_hi = 0;   // owned cell range (counts); halo cells outside it are evaluated but not counted
   DBuf<int32_t> halo_send_idx, halo_recv_idx; DBuf<double2> halo_send, halo_recv; int64_t n_halo_send = 0, n_halo_recv = 0;
-  DBuf<double> reduce_vec;
+  DBuf<double> reduce_vec, red_slices; DBuf<unsigned> red_ticket;
   mmb_params prm{};
   // mesh
   DBuf<double> x, shift, dist;
@@ -181,7 +181,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
   ctx->tr_in.release(); ctx->tr_out.release(); ctx->tr_u.release(); ctx->tr_ug.release();
   ctx->tr_a.release(); ctx->tr_b.release(); ctx->tr_c.release(); ctx->pred_pts.release(); ctx->pred_sign.release();
-  ctx->halo_send_idx.release(); ctx->halo_recv_idx.release(); ctx->halo_send.release(); ctx->halo_recv.release(); ctx->reduce_vec.release();
+  ctx->halo_send_idx.release(); ctx->halo_recv_idx.release(); ctx->halo_send.release(); ctx->halo_recv.release(); ctx->reduce_vec.release(); ctx->red_slices.release(); ctx->red_ticket.release();
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->h_remote_stage) cudaFreeHost(ctx->h_remote_stage);
   ctx->d_remote_idx.release(); ctx->d_remote_stage.release();
@@ -212,6 +212,18 @@ int mmb_dev_counters(mmb_context* ctx, unsigned long long out[8]) {
 }
 #endif
 
+int mmb_host_register(mmb_context* ctx, void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return MMB_ERR_INVALID_ARG;
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); if (ctx) ctx->err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return MMB_ERR_CUDA; }
+  return MMB_OK;
+}
+int mmb_host_unregister(mmb_context* ctx, void* ptr) {
+  if (!ptr) return MMB_ERR_INVALID_ARG;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); if (ctx) ctx->err = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); return MMB_ERR_CUDA; }
+  return MMB_OK;
+}
 int mmb_set_params(mmb_context* ctx, const mmb_params* p) {
   if (!ctx || !p) return MMB_ERR_INVALID_ARG;
   ctx->prm = *p; return MMB_OK;
@@ -732,7 +744,8 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
 }
 #define PROJ_ARGS (const double2*)ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->perm.p, ctx->new_off.p, ctx->new_cell.p, \
                   i0, i1, ctx->old_xy.p, ctx->old_idx.p, ctx->dofs_old.p, ctx->dofs_new.p, dp, ctx->part_a.p + pb0, ctx->part_b.p + pb0, ctx->counters.p
-static int proj_variant() { const char* e = getenv("MMB_PROJ_VARIANT"); return e ? atoi(e) : 0; }   // dev builds only (MMB_DEV_VARIANTS)
+#ifdef MMB_DEV_VARIANTS
+static int proj_variant() { const char* e = getenv("MMB_PROJ_VARIANT"); return e ? atoi(e) : 0; }
 extern "C++" {
 template <int NT, int MINB, bool FMA>
 static int launch_project_tile(mmb_context* ctx, const ProjArgs& pa, int pb0, unsigned* nb_out) {
@@ -750,6 +763,7 @@ static int launch_project_tile(mmb_context* ctx, const ProjArgs& pa, int pb0, un
   return MMB_OK;
 }
 }  // extern "C++"
+#endif
 // projection of the new cells [i0, i1) of the pair CSR; per-block partial sums go to part_[pb0 ...); returns #blocks
 static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, int pb0, int* nblocks) {
   const DevParams dp = dev_params(ctx->prm);
@@ -762,23 +776,34 @@ static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, in
     pa.xy = (const double2*)ctx->x.p; pa.cv0 = ctx->cv[0].p; pa.cv1 = ctx->cv[1].p; pa.cv2 = ctx->cv[2].p; pa.perm = ctx->perm.p;
     pa.new_off = ctx->new_off.p; pa.new_cell = ctx->new_cell.p; pa.i_begin = i0; pa.nnew = i1;
     pa.old_xy = ctx->old_xy.p; pa.old_idx = ctx->old_idx.p; pa.dofs_old = ctx->dofs_old.p; pa.dofs_new = ctx->dofs_new.p; pa.prm = dp;
-    switch (proj_variant()) {
+    // One thread per new cell walking its pairs in order (k_project).  Instrumented builds (-DMMB_DEV_VARIANTS) also carry
+    // the alternatives that were measured slower on B200 (profiles/README.md): the tile kernel of project.cuh (pair slots,
+    // transposed columns, dense list before the fan) and the hoisted-constant / merged-crossing / FMA forms of k_project.
 #ifdef MMB_DEV_VARIANTS
+    switch (proj_variant()) {
+      case 10: TRY((launch_project_tile<128, 7, false>(ctx, pa, pb0, &nb))); break;
       case 11: TRY((launch_project_tile<128, 7, true>(ctx, pa, pb0, &nb))); break;
       case 12: TRY((launch_project_tile<256, 3, false>(ctx, pa, pb0, &nb))); break;
       case 13: TRY((launch_project_tile<256, 3, true>(ctx, pa, pb0, &nb))); break;
-      case 14: TRY((launch_project_tile<128, 6, true>(ctx, pa, pb0, &nb))); break;
-      case 15: TRY((launch_project_tile<128, 5, true>(ctx, pa, pb0, &nb))); break;
-      case 16: TRY((launch_project_tile<256, 2, true>(ctx, pa, pb0, &nb))); break;
-      case 20: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 1>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 21: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 2>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 22: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
-      case 23: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 6, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
-#endif
-      default: TRY((launch_project_tile<128, 7, false>(ctx, pa, pb0, &nb))); break;
+      default: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 1>), nb, PROJ_THREADS, PROJ_ARGS); break;
     }
+#else
+    (void)pa;
+    nb = grid_for(i1 - i0, PROJ_THREADS);
+    LAUNCH("project_p1", (k_project<3, 1, 5, 1>), nb, PROJ_THREADS, PROJ_ARGS);
+#endif
   }
   *nblocks = (int)nb;
+  return MMB_OK;
+}
+static int reduce_partials(mmb_context* ctx, int n) {
+  CK(ctx->red_slices.ensure(2 * REDUCE_MAX_BLOCKS));
+  if (!ctx->red_ticket.p) { CK(ctx->red_ticket.ensure(1)); CK(cudaMemsetAsync(ctx->red_ticket.p, 0, sizeof(unsigned), ctx->stream)); }
+  const int g = std::max(1, std::min(REDUCE_MAX_BLOCKS, (n + 2047) / 2048));
+  LAUNCH("reduce_partials", k_reduce_partials, g, 256, ctx->part_a.p, ctx->part_b.p, n, ctx->red_slices.p, ctx->red_slices.p + REDUCE_MAX_BLOCKS,
+         ctx->red_ticket.p, ctx->counters.p);
   return MMB_OK;
 }
 static int do_project(mmb_context* ctx, int ncomp) {
@@ -786,7 +811,7 @@ static int do_project(mmb_context* ctx, int ncomp) {
   REQUIRE(ctx->max_old_idx < ctx->n_old, MMB_ERR_INVALID_ARG, "projection: a pair references an old cell beyond the DOF array");
   int nb = 0;
   TRY(project_range(ctx, ncomp, 0, ctx->nnew, 0, &nb));
-  LAUNCH("reduce_partials", k_reduce_partials, 1, 1024, ctx->part_a.p, ctx->part_b.p, nb, ctx->counters.p);
+  TRY(reduce_partials(ctx, nb));
   return MMB_OK;
 }
 static int stage_dofs(mmb_context* ctx, int ncomp, int64_t n_old, const double* dofs_old_host) {
@@ -1001,6 +1026,64 @@ int mmb_interface_candidates(mmb_context* ctx, int32_t* insert_segs_host, int64_
   return MMB_OK;
 }
 
+int mmb_component_numbers(mmb_context* ctx, int64_t nz, const int64_t* zone_off_host, const int32_t* zone_cells_host,
+                          int64_t component_count, int32_t* zone_number_host, int32_t* cell_number_host, int64_t* component_count_out) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "component numbers need an uploaded mesh");
+  REQUIRE(nz >= 0 && component_count >= 1 && (nz == 0 || (zone_off_host && zone_number_host)), MMB_ERR_INVALID_ARG, "mmb_component_numbers: bad arguments");
+  const int64_t ne = nz ? zone_off_host[nz] : 0;
+  REQUIRE(nz == 0 || (zone_off_host[0] == 0 && ne >= 0 && (ne == 0 || zone_cells_host)), MMB_ERR_INVALID_ARG, "mmb_component_numbers: malformed CSR");
+  for (int64_t z = 0; z < nz; ++z) REQUIRE(zone_off_host[z + 1] >= zone_off_host[z], MMB_ERR_INVALID_ARG, "mmb_component_numbers: malformed CSR");
+  for (int64_t e = 0; e < ne; ++e) REQUIRE(zone_cells_host[e] >= 0 && zone_cells_host[e] < ctx->nc, MMB_ERR_INVALID_ARG, "mmb_component_numbers: cell index out of range");
+  REQUIRE(component_count + nz < 0x7f7f7f7fll, MMB_ERR_CAPACITY, "mmb_component_numbers: component numbers exceed int32");
+  const size_t nc = (size_t)ctx->nc;
+  DBuf<long long> off; DBuf<int32_t> cells, first, label, clabel; DBuf<uint32_t> fresh; DBuf<uint8_t> fflag; DBuf<int> changed;
+  auto release = [&]() { off.release(); cells.release(); first.release(); label.release(); clabel.release(); fresh.release(); fflag.release(); changed.release(); };
+  auto fail = [&](cudaError_t e) { ctx->err = cudaGetErrorString(e); release(); return (int)MMB_ERR_CUDA; };
+  cudaError_t e;
+  if ((e = off.ensure(nz + 1)) || (e = cells.ensure(ne + 1)) || (e = first.ensure(nc + 1)) || (e = label.ensure(nz + 1)) ||
+      (e = clabel.ensure(nc + 1)) || (e = fresh.ensure(nz + 1)) || (e = fflag.ensure(nz + 1)) || (e = changed.ensure(1))) return fail(e);
+  cudaStream_t S = ctx->stream;
+  cudaMemsetAsync(clabel.p, 0x7f, nc * sizeof(int32_t), S);            // 0x7f7f7f7f: larger than any label; normalised below
+  cudaMemsetAsync(first.p, 0x7f, nc * sizeof(int32_t), S);
+  int64_t count_out = component_count;
+  if (nz) {
+    cudaMemcpyAsync(off.p, zone_off_host, (size_t)(nz + 1) * sizeof(long long), cudaMemcpyHostToDevice, S);
+    if (ne) cudaMemcpyAsync(cells.p, zone_cells_host, (size_t)ne * sizeof(int32_t), cudaMemcpyHostToDevice, S);
+    const unsigned g = grid_for(nz, 256);
+    LAUNCH("cc_first", k_cc_first, g, 256, off.p, cells.p, nz, first.p);
+    LAUNCH("cc_fresh", k_cc_fresh, g, 256, off.p, cells.p, nz, first.p, fresh.p, fflag.p);
+    LAUNCH("compact_scan", k_compact_scan, 1, 1024, fresh.p, (int)nz, &ctx->counters.p->pad_[0]);
+    LAUNCH("cc_init", k_cc_init, g, 256, fresh.p, fflag.p, nz, (int)component_count, label.p);
+    for (int it = 0; it < 1 << 20; ++it) {
+      cudaMemsetAsync(changed.p, 0, sizeof(int), S);
+      LAUNCH("cc_to_cells", k_cc_to_cells, g, 256, off.p, cells.p, nz, label.p, clabel.p);
+      LAUNCH("cc_to_zones", k_cc_to_zones, g, 256, off.p, cells.p, nz, clabel.p, label.p, changed.p);
+      int h = 0;
+      cudaMemcpyAsync(&h, changed.p, sizeof(int), cudaMemcpyDeviceToHost, S);
+      if ((e = cudaStreamSynchronize(S)) != cudaSuccess) return fail(e);
+      if (!h) break;
+    }
+    cudaMemcpyAsync(zone_number_host, label.p, (size_t)nz * sizeof(int32_t), cudaMemcpyDeviceToHost, S);
+    if (fetch_counters(ctx) != MMB_OK) { release(); return MMB_ERR_CUDA; }
+    count_out += (int64_t)ctx->h_counters->pad_[0];
+  }
+  if (cell_number_host) {
+    // cells outside every zone keep componentNumber 0
+    {
+      LaunchScope ls_(ctx, "cc_finish");
+      k_cc_finish<<<grid_for((int64_t)nc, 256), 256, 0, S>>>(clabel.p, (int64_t)nc);
+    }
+    cudaMemcpyAsync(cell_number_host, clabel.p, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, S);
+  }
+  e = cudaStreamSynchronize(S);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(e);
+  if (component_count_out) *component_count_out = count_out;
+  release();
+  return MMB_OK;
+}
+
 // ---- whole step -----------------------------------------------------------------------------------------
 static int step_core(mmb_context* ctx, const double* shifts_host, int ncomp, int64_t n_old, const double* dofs_old_host) {
   REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
@@ -1177,7 +1260,7 @@ int mmb_step_host_finish(mmb_context* ctx, double* dofs_new_host, uint8_t* valid
           CK(cudaMemcpyAsync(dofs_new_host + lo * ncomp, ctx->dofs_new.p + lo * ncomp, (hi - lo) * ncomp * sizeof(double), cudaMemcpyDeviceToHost, S2));
       }
     }
-    LAUNCH("reduce_partials", k_reduce_partials, 1, 1024, ctx->part_a.p, ctx->part_b.p, pb, ctx->counters.p);
+    TRY(reduce_partials(ctx, pb));
   } else if (ncomp && dofs_new_host) {
     CK(cudaStreamWaitEvent(S2, ev[4], 0));
     CK(cudaMemcpyAsync(dofs_new_host, ctx->dofs_new.p, nc * ncomp * sizeof(double), cudaMemcpyDeviceToHost, S2));

@@ -16,30 +16,11 @@
 #include <vector>
 
 #include "../../include/mmesh_b200.h"
+#include "snapshot.hh"
+#include "pairs.hh"
 
 namespace Dune {
 namespace B200 {
-
-// Dune::GridError analogue (mmesh.hh:1104-1107 and friends)
-struct GridError : std::runtime_error { using std::runtime_error::runtime_error; };
-struct InvalidStateException : std::runtime_error { using std::runtime_error::runtime_error; };
-
-template <int dim>
-using GlobalCoordinate = std::array<double, dim>;   // same layout as Dune::FieldVector<double, dim>
-
-// What the adapter extracts from the CGAL triangulation (see include/mmesh_b200.h for the conventions).
-template <int dim>
-struct Snapshot {
-  std::vector<GlobalCoordinate<dim>> x;             // vh->point(), leaf vertex index order
-  std::vector<std::array<int32_t, dim + 1>> cells;  // face->vertex(k)->info().index, TDS order
-  std::vector<uint8_t> perm;                        // ElementInfo::cgalIndex packed
-  std::vector<std::array<int32_t, 4>> edges;        // (a,b,c,d), 2-D only
-  std::vector<std::array<int32_t, dim>> facets;     // interface facets
-  std::vector<uint8_t> vflags;                      // bit0 isInterface, bit1 boundaryFlag == 1 (host-side use only)
-  std::vector<int32_t> interfaceVertices;           // interface leaf vertex index -> bulk vertex index (interface/indexsets.hh:238-277)
-  std::vector<std::array<int32_t, 3>> neighbours;   // 2-D, optional: face->neighbor(k) cell index, -1 = infinite face
-  std::vector<int32_t> insertionLevel;              // optional: VertexInfo::insertionLevel (mmesh.hh:132), default 0
-};
 
 // insert_ / remove_ of MMesh::adapt() before adapt_() (mmesh.hh:826-908), as index lists
 struct AdaptCandidates {
@@ -70,19 +51,24 @@ struct InterfaceMovementOutcome {
   std::vector<int32_t> removed;       // vertices appended to remove_ (in order)
   std::vector<InterfaceInsertion> inserted;
 };
+// xCurrent = the coordinates the mesh has NOW (the snapshot's x is the state at the last TDS edit: after moveVertices /
+// moveInterface / step() the two differ); nullptr = the snapshot's own.
 inline InterfaceMovementOutcome resolveInterfaceMovement2d(const Snapshot<2>& s, std::vector<std::array<double, 2>> ishifts,
                                                            const std::vector<int32_t>& invalidCellsOfTrialMove,
-                                                           const std::vector<int32_t>& alreadyRemoved = {}) {
+                                                           const std::vector<int32_t>& alreadyRemoved = {},
+                                                           const std::vector<std::array<double, 2>>* xCurrent = nullptr) {
   using P = std::array<double, 2>;
   InterfaceMovementOutcome out;
+  const std::vector<P>& x0 = xCurrent ? *xCurrent : s.x;
   const std::size_t nv = s.x.size(), nc = s.cells.size();
   if (ishifts.size() != s.interfaceVertices.size()) throw InvalidStateException("shifts.size() != number of interface vertices");
-  std::vector<P> xt(s.x.begin(), s.x.end());                                     // moveInterface(shifts), mmesh.hh:933
+  if (x0.size() != nv) throw InvalidStateException("current coordinates do not match the snapshot");
+  std::vector<P> xt(x0.begin(), x0.end());                                       // moveInterface(shifts), mmesh.hh:933
   std::vector<int32_t> ivIndex(nv, -1);
   for (std::size_t i = 0; i < ishifts.size(); ++i) {
     const std::size_t v = (std::size_t)s.interfaceVertices[i];
     ivIndex[v] = (int32_t)i;
-    xt[v] = P{ s.x[v][0] + ishifts[i][0], s.x[v][1] + ishifts[i][1] };
+    xt[v] = P{ x0[v][0] + ishifts[i][0], x0[v][1] + ishifts[i][1] };
   }
   auto isIf = [&](int32_t v) { return !s.vflags.empty() && (s.vflags[(std::size_t)v] & 1); };
   auto bflag = [&](int32_t v) { return !s.vflags.empty() && (s.vflags[(std::size_t)v] & 2); };
@@ -94,10 +80,11 @@ inline InterfaceMovementOutcome resolveInterfaceMovement2d(const Snapshot<2>& s,
     for (int32_t f : incident[(std::size_t)a]) { const auto& q = s.facets[(std::size_t)f]; if ((q[0] == a && q[1] == b) || (q[0] == b && q[1] == a)) return f; }
     return -1;
   };
-  std::vector<int32_t> removedSet(alreadyRemoved);
+  std::vector<uint8_t> removedSet(nv, 0);                                        // removed_ (mmesh.hh:1806) as a bitmap
+  for (int32_t r : alreadyRemoved) removedSet[(std::size_t)r] = 1;
   auto removeOnce = [&](int32_t v) {                                             // removed_.insert(id).second
-    for (int32_t r : removedSet) if (r == v) return;
-    removedSet.push_back(v); out.removed.push_back(v); out.change = true;
+    if (removedSet[(std::size_t)v]) return;
+    removedSet[(std::size_t)v] = 1; out.removed.push_back(v); out.change = true;
   };
   auto corner1 = [](const P& c0, const P& c1) { return P{ c0[0] + 1.0 * (c1[0] - c0[0]), c0[1] + 1.0 * (c1[1] - c0[1]) }; };   // AffineGeometry::corner(1)
   auto length = [](const P& a, const P& b) { const double jx = b[0] - a[0], jy = b[1] - a[1]; double q = 0.0; q += jx * jx; q += jy * jy; return std::sqrt(q); };
@@ -247,8 +234,8 @@ class MMesh {
     if (dim == 2 && s.insertionLevel.size() == s.x.size() && !s.x.empty())
       check(mmb_upload_vertex_levels(ctx_, s.insertionLevel.data()));
     marks_.assign(s.cells.size(), 0);
-    refineMarked_ = coarsenMarked_ = 0;
-    removed_.clear();
+    refineMarked_ = coarsenMarked_ = 0; interfaceMarked_ = false;
+    removed_.clear(); removedMask_.assign(s.x.size(), 0);
   }
 
   //! mmesh.hh:1421-1430
@@ -275,9 +262,7 @@ class MMesh {
           const uint8_t fl = snap_->vflags.empty() ? 0 : snap_->vflags[(std::size_t)v];
           if (fl & 1) continue;                      // interface vertex: handled by ensureInterfaceMovement
           if (fl & 2) continue;                      // boundaryFlag(v) == 1
-          bool seen = false;
-          for (int32_t r : removed_) if (r == v) { seen = true; break; }
-          if (!seen) { removed_.push_back(v); change = true; }
+          if (insertRemoved(v)) change = true;       // removed_.insert(id).second (mmesh.hh:1119)
         }
     }
     return change;
@@ -289,10 +274,9 @@ class MMesh {
     scatterInterfaceShifts(ishifts);
     check(mmb_move_vertices(ctx_, full_[0].data()));
   }
-  //! Numeric part of mmesh.hh:920-1088: the current mesh must be valid (:926-930, GridError otherwise); cells that
-  //! invert under the interface movement are returned (the host decides between vertex removal and the
-  //! interface-constrained branch :963-1078, which needs the TDS).
-  std::vector<int32_t> ensureInterfaceMovement(const std::vector<Coordinate>& ishifts) {
+  //! Numeric part of mmesh.hh:920-1088: the current mesh must be valid (:926-930, GridError otherwise); returns the cells
+  //! that invert under the interface movement (the element loop over them, :935-1078, is resolveInterfaceMovement).
+  std::vector<int32_t> invertedCellsUnderInterfaceMovement(const std::vector<Coordinate>& ishifts) {
     std::vector<Coordinate> zero(snap_->x.size(), Coordinate{});
     int64_t ninv = 0;
     int rc = mmb_trial_move_validate(ctx_, zero[0].data(), nullptr, nullptr, &ninv);
@@ -312,17 +296,30 @@ class MMesh {
   //! The whole of ensureInterfaceMovement in 2-D (mmesh.hh:920-1088): validity of the current mesh and the inverted cells of the
   //! trial movement on the device, then the reference's element loop over those cells on the host (removals, intersection
   //! insertion points, GridError for unresolvable constrained cells).  Scheduled removals are appended to removed().
+  //! The loop works on the coordinates the mesh has NOW: they are fetched from the device, because the snapshot's x is
+  //! the state at the last TDS edit and moveVertices / moveInterface / step() have moved the resident mesh since.
   InterfaceMovementOutcome resolveInterfaceMovement(const std::vector<Coordinate>& ishifts) {
     if constexpr (dim == 2) {
-      const std::vector<int32_t> bad = ensureInterfaceMovement(ishifts);
-      InterfaceMovementOutcome o = resolveInterfaceMovement2d(*snap_, ishifts, bad, removed_);
-      for (int32_t v : o.removed) removed_.push_back(v);
+      const std::vector<int32_t> bad = invertedCellsUnderInterfaceMovement(ishifts);
+      InterfaceMovementOutcome o;
+      if (!bad.empty()) {
+        std::vector<Coordinate> xNow(snap_->x.size());
+        check(mmb_download_coords(ctx_, xNow[0].data()));
+        o = resolveInterfaceMovement2d(*snap_, ishifts, bad, removed_, &xNow);
+      }
+      for (int32_t v : o.removed) insertRemoved(v);
+      lastInterfaceOutcome_ = o;
       return o;
     } else {
-      ensureInterfaceMovement(ishifts);                  // throws GridError on an inverted cell (mmesh.hh:938-942)
-      return InterfaceMovementOutcome{};
+      invertedCellsUnderInterfaceMovement(ishifts);      // throws GridError on an inverted cell (mmesh.hh:938-942)
+      lastInterfaceOutcome_ = InterfaceMovementOutcome{};
+      return lastInterfaceOutcome_;
     }
   }
+  //! mmesh.hh:920-1088 with the reference's signature: true when vertices were scheduled for removal or insertion
+  //! points were created (the details are in interfaceMovementOutcome(), the removals also in removed()).
+  bool ensureInterfaceMovement(std::vector<Coordinate> ishifts) { return resolveInterfaceMovement(ishifts).change; }
+  const InterfaceMovementOutcome& interfaceMovementOutcome() const { return lastInterfaceOutcome_; }
 
   //! mmesh.hh:736-751 (bulk loop on the device, interface loop on the device, counters like :725-731)
   bool markElements() {
@@ -336,7 +333,9 @@ class MMesh {
     if (dim == 2 && !snap_->facets.empty()) {
       imarks_.resize(snap_->facets.size());
       check(mmb_mark_interface(ctx_, imarks_.data()));
-      for (int8_t m : imarks_) change |= (m != 0);
+      interfaceMarked_ = false;
+      for (int8_t m : imarks_) interfaceMarked_ |= (m != 0);
+      change |= interfaceMarked_;
     }
     return change;
   }
@@ -364,7 +363,7 @@ class MMesh {
     check(mmb_coarsening_candidates(ctx_, nullptr, nullptr, 0, &n));
     std::vector<int32_t> rc((std::size_t)n), rv((std::size_t)n);
     if (n > 0) check(mmb_coarsening_candidates(ctx_, rc.data(), rv.data(), n, &n));
-    auto seen = [&](int32_t v) { for (int32_t r : removed_) if (r == v) return true; return false; };
+    auto seen = [&](int32_t v) { return removedMask_[(std::size_t)v] != 0; };
     for (std::size_t i = 0; i < rc.size(); ++i)
       if (!seen(rv[i])) { a.removeCells.push_back(rc[i]); a.removeVertices.push_back(rv[i]); }
     if (!snap_->facets.empty()) {
@@ -381,9 +380,58 @@ class MMesh {
   bool preAdapt() const { return coarsenMarked_ > 0 || !removed_.empty(); }          // mmesh.hh:762-765 (bulk part)
   void postAdapt() {                                                                  // mmesh.hh:1456-1474
     std::fill(marks_.begin(), marks_.end(), 0);
-    refineMarked_ = coarsenMarked_ = 0;
+    refineMarked_ = coarsenMarked_ = 0; interfaceMarked_ = false;
+    for (int32_t v : removed_) removedMask_[(std::size_t)v] = 0;
     removed_.clear();
   }
+
+  //! MMesh::adapt() up to the TDS edits (mmesh.hh:826-908): the insert_ / remove_ lists of both candidate loops, built on the
+  //! device from the marks; true when there is something to insert or remove (the reference then runs adapt_(), :910-913,
+  //! whose CGAL edits stay with the host adapter).  The lists are in candidates().
+  bool adapt() {
+    // no mark since the last postAdapt (every ElementInfo::mark is 0): both candidate loops of the reference find nothing
+    candidates_ = (refineMarked_ > 0 || coarsenMarked_ > 0 || interfaceMarked_) ? adaptCandidates() : AdaptCandidates{};
+    return !(candidates_.insertCells.empty() && candidates_.removeCells.empty() && candidates_.insertSegments.empty() &&
+             candidates_.removeSegments.empty() && removed_.empty());
+  }
+  const AdaptCandidates& candidates() const { return candidates_; }
+
+  //! MMesh::adapt(handle) (mmesh.hh:1138-1165) as a drop-in: preAdapt, adapt() (candidate lists on the device), the CGAL TDS
+  //! edits through `edit` (the host adapter applies candidates() + removed() to its triangulation, like adapt_(), and returns
+  //! the snapshot of the edited mesh -- it must outlive this object's use of it, like the one given to setSnapshot), then
+  //! the data transfer: the reference calls handle.prolongLocal(father = old child, son = cut triangle) and
+  //! handle.restrictLocal(father = new element, son = cut triangle, initialize) per cut triangle; here the same transfer is
+  //! one batched device call, so the handle only has to move DOF blocks:
+  //!     int  handle.localDofs()                          1 (FV / P0) or 3 (DG-P1, nodal on id-ordered corners)
+  //!     void handle.gather(oldCellIndex, double* out)    DOFs of a cell of the OLD snapshot (a child of some component)
+  //!     void handle.scatter(newCellIndex, const double*) DOFs of a cell of the NEW snapshot flagged isNew
+  //! Both snapshots need Snapshot::vertexId.  Returns true like the reference.
+  template <class DataHandle, class TdsEdit>
+  bool adapt(DataHandle& handle, TdsEdit&& edit) {
+    static_assert(dim == 2, "adapt(handle): projection is 2-D (geometryInFather, entity.hh:573-594)");
+    preAdapt();
+    adapt();
+    const Snapshot<dim>* oldS = snap_;
+    const Snapshot<dim>& newS = edit(candidates_, removed_);
+    lastPairs_ = buildProjectionPairs(*oldS, oldS->vertexId, newS, newS.vertexId);
+    const int ncomp = handle.localDofs();
+    if (ncomp != 1 && ncomp != 3) throw InvalidStateException("adapt(handle): localDofs() must be 1 (P0) or 3 (DG-P1)");
+    // gather: only the children are read (entity ids of vanished cells, persistentcontainer.hh:33-89 keeps them alive until here)
+    std::vector<double> dofsOld(oldS->cells.size() * (std::size_t)ncomp, 0.0);
+    std::vector<uint8_t> gathered(oldS->cells.size(), 0);
+    for (int32_t o : lastPairs_.oldIndex)
+      if (!gathered[(std::size_t)o]) { gathered[(std::size_t)o] = 1; handle.gather(o, &dofsOld[(std::size_t)o * (std::size_t)ncomp]); }
+    setSnapshot(newS);
+    if (!lastPairs_.newCell.empty()) {
+      setProjectionPairs(lastPairs_.newOff, lastPairs_.newCell, lastPairs_.oldCorners, lastPairs_.oldIndex);
+      std::vector<double> dofsNew;
+      project(ncomp, dofsOld, dofsNew);
+      for (int32_t K : lastPairs_.newCell) handle.scatter(K, &dofsNew[(std::size_t)K * (std::size_t)ncomp]);
+    }
+    postAdapt();
+    return true;
+  }
+  const ProjectionPairs& lastProjectionPairs() const { return lastPairs_; }
 
   //! numeric part of adapt(handle) (mmesh.hh:1138-1165): pairs come from the connected components built by adapt_()
   void setProjectionPairs(const std::vector<int64_t>& newOff, const std::vector<int32_t>& newCell,
@@ -417,10 +465,12 @@ class MMesh {
                                        edgeFlags_.empty() ? nullptr : edgeFlags_.data(), &r);
     if (rc == MMB_ERR_INVALID_CELL_3D)
       throw GridError("Vertices could not be moved, because the removal of vertices is not supported in 3D!");
-    check(rc);
+    if (rc != MMB_MOVE_WITHHELD) check(rc);          // withheld: r.moved == 0, the caller removes vertices first (mmesh.hh:1109-1124)
     refineMarked_ = r.n_refine; coarsenMarked_ = r.n_coarsen;
     return r;
   }
+  //! step() with move_policy 0 (default) withholds moveVertices when the trial move inverts a cell; 1 = always move
+  void setMovePolicy(int policy) { indicator_.sync_(); indicator_.p_.move_policy = policy; indicator_.push(); }
   const std::vector<uint8_t>& validity() const { return valid_; }          // !(signedVolume_ <= 0) per cell (mmesh.hh:1102)
   const std::vector<int8_t>& orientation() const { return orient_; }      // exact CGAL orientation sign per cell
   const std::vector<uint8_t>& edgeFlags() const { return edgeFlags_; }    // 1 legal, 0 illegal, 2 hull edge
@@ -461,9 +511,20 @@ class MMesh {
   std::vector<int8_t> marks_, imarks_;
   std::vector<uint8_t> longest_, valid_, edgeFlags_;
   std::vector<int8_t> orient_;
-  std::vector<int32_t> removed_;
+  bool insertRemoved(int32_t v) {                                                     // removed_.insert(id).second, O(1)
+    if (removedMask_.size() < snap_->x.size()) removedMask_.resize(snap_->x.size(), 0);
+    if (removedMask_[(std::size_t)v]) return false;
+    removedMask_[(std::size_t)v] = 1; removed_.push_back(v);
+    return true;
+  }
+  std::vector<int32_t> removed_;                     // insertion order, like the reference's remove_ vector
+  std::vector<uint8_t> removedMask_;                 // removed_ (std::unordered_set<IdType>, mmesh.hh:1806) as a bitmap
+  AdaptCandidates candidates_;
+  InterfaceMovementOutcome lastInterfaceOutcome_;
+  ProjectionPairs lastPairs_;
   std::vector<Coordinate> full_;
   int64_t refineMarked_ = 0, coarsenMarked_ = 0;
+  bool interfaceMarked_ = false;
 };
 
 template <int dim>

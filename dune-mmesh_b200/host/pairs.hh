@@ -27,7 +27,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "mmesh_b200.hh"
+#include "snapshot.hh"
 
 namespace Dune {
 namespace B200 {

@@ -20,7 +20,7 @@ EXPORTS = [
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
     "mmb_step_host_begin", "mmb_step_host_marks", "mmb_step_host_finish", "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
-    "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
+    "mmb_component_numbers", "mmb_host_register", "mmb_host_unregister", "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
 
@@ -282,6 +282,18 @@ class Context:
         self._ck(lib().mmb_project_interface_p0(self._h, C.c_int64(new_len.shape[0]), _p(new_len), _p(new_off), C.c_int64(old_idx.shape[0]),
                                                 _p(old_len), _p(old_idx), C.c_int64(dofs_old.shape[0]), _p(dofs_old), _p(out)))
         return out
+
+    def component_numbers(self, zone_off, zone_cells, component_count=1):
+        """adapt_()'s component numbering (mmesh.hh:1194-1218, 1919-1941): (zone_number, cell_number, component_count)."""
+        zone_off = np.ascontiguousarray(zone_off, np.int64)
+        zone_cells = _i32(zone_cells)
+        nz = zone_off.shape[0] - 1
+        zn = np.zeros(max(nz, 1), np.int32)
+        cn = np.zeros(self.nc, np.int32)
+        cc = C.c_int64()
+        self._ck(lib().mmb_component_numbers(self._h, C.c_int64(nz), _p(zone_off), _p(zone_cells), C.c_int64(component_count), _p(zn), _p(cn),
+                                             C.byref(cc)))
+        return zn[:nz], cn, cc.value
 
     def upload_neighbours(self, nb):
         nb = _i32(nb)

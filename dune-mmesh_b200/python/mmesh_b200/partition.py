@@ -93,11 +93,15 @@ def make_shard(m, world, rank, new_off=None, new_cell=None, old_xy=None, old_idx
             assert (g2l_v[mine] >= 0).all()
     sh.send_idx = (np.concatenate(send_idx) if send_idx else np.zeros(0, np.int64)).astype(np.int32)
     sh.send_counts = send_counts
-    # projection pairs of the owned new cells
+    # projection pairs of the owned new cells: rows are selected by the cell they belong to, because the CSR of a real
+    # adapt() lists only the isNew cells (rows != cells); new_cell is ascending (element order, mmesh.hh:1143)
     if new_off is not None:
-        p0, p1 = int(new_off[c0]), int(new_off[c1])
-        sh.new_off = (new_off[c0:c1 + 1] - p0).astype(np.int64)
-        sh.new_cell = g2l_c[new_cell[c0:c1]].astype(np.int32)
+        new_cell = np.asarray(new_cell)
+        assert (np.diff(new_cell) > 0).all(), "new_cell must be ascending"
+        r0, r1 = int(np.searchsorted(new_cell, c0)), int(np.searchsorted(new_cell, c1))
+        p0, p1 = int(new_off[r0]), int(new_off[r1])
+        sh.new_off = (new_off[r0:r1 + 1] - p0).astype(np.int64)
+        sh.new_cell = g2l_c[new_cell[r0:r1]].astype(np.int32)
         sh.old_xy = np.ascontiguousarray(old_xy[p0:p1])
         oi = g2l_c[old_idx[p0:p1]]
         assert (oi >= 0).all() and (sh.new_cell >= 0).all()

@@ -79,6 +79,12 @@ const char* mmb_last_error(const mmb_context* ctx);
 void* mmb_stream(const mmb_context* ctx);
 int mmb_synchronize(mmb_context* ctx);
 
+/* Page-lock caller-owned host memory (e.g. the storage of the std::vector<FieldVector<double,dim>> shifts, or of a dune-fem
+   DOF vector) so that the asynchronous copies of mmb_adapt_step_host overlap with the kernels; pageable buffers work too,
+   but the driver then stages every copy.  Thin wrappers over cudaHostRegister / cudaHostUnregister; ctx may be NULL. */
+int mmb_host_register(mmb_context* ctx, void* ptr, int64_t bytes);
+int mmb_host_unregister(mmb_context* ctx, void* ptr);
+
 /* ---- snapshot upload / download (outside the timed path, like the reference's CGAL TDS edits) ------------ */
 int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t nc, const int32_t* cells_host,
                     const uint8_t* perm_host, int64_t ne, const int32_t* edges_host, int64_t ns,
@@ -172,6 +178,17 @@ int mmb_coarsening_candidates(mmb_context* ctx, int32_t* cells_host, int32_t* ve
    earlier interface element already removed it.  Facet rows are the interface elements' vertex order. */
 int mmb_interface_candidates(mmb_context* ctx, int32_t* insert_segs_host, int64_t cap_insert, int64_t* n_insert,
                              int32_t* remove_segs_host, int32_t* remove_vertices_host, int64_t cap_remove, int64_t* n_remove);
+
+/* The component numbering of MMesh::adapt_() before its TDS edits (mmesh.hh:1194-1218): getComponentNumber_ (:1919-1941)
+   applied to every zone -- the conflict zone of each insertion point, then the star of each vertex to remove, in the order of
+   insert_ / remove_ -- and repeated `while (markAgain)`.  zones = CSR over cell indices of the uploaded mesh; component_count =
+   componentCount_ on entry (connectedComponents_.size() + 1, i.e. 1 after postAdapt; all ElementInfo::componentNumber are
+   taken as 0 on entry).  zone_number[k] is what insertComponentIds / removeComponentIds hold (+ 1); cell_number[c] = the
+   cell's componentNumber afterwards (0 = in no zone); *component_count_out = componentCount_ afterwards.  The order-dependent
+   loop is evaluated in closed form on the device (first zone per cell, scan over the fresh zones, min-label propagation). */
+int mmb_component_numbers(mmb_context* ctx, int64_t nz, const int64_t* zone_off_host, const int32_t* zone_cells_host,
+                          int64_t component_count, int32_t* zone_number_host, int32_t* cell_number_host,
+                          int64_t* component_count_out);
 
 /* One whole adapt step on resident data, in the reference's user-loop order (doc/examples/moving.py:231-252):
    markElements (distance + marks) -> ensureVertexMovement (trial validity) -> adapt(handle) projection of the

@@ -387,6 +387,70 @@ void orc_distance_2d_subset(const double* xy, const int32_t* vidx, int64_t nsub,
     dist_sub[i] = cur;
   }
 }
+/* CULLED variant (NOT the reference's loop, which is the brute force above): the same per-pair arithmetic, but the facets are
+   bucketed in a uniform grid and a vertex visits rings of grid cells around its own until the ring distance exceeds its
+   current minimum.  The minimum is taken over a superset of every facet that can attain it, so the values equal the brute
+   force bit for bit; only the cost changes (O(Nv * few) instead of O(Nv * Ns)).  Used as the labelled "culled" CPU baseline. */
+void orc_distance_2d_culled_subset(const double* xy, int64_t nv_all, const int32_t* vidx, int64_t nsub, const int32_t* segs,
+                                   int64_t ns, double* dist_sub) {
+  if (ns == 0) { for (int64_t i = 0; i < nsub; ++i) dist_sub[i] = 1e100; return; }
+  double lo[2] = { 1e300, 1e300 }, hi[2] = { -1e300, -1e300 };
+  for (int64_t v = 0; v < nv_all; ++v) for (int k = 0; k < 2; ++k) { if (xy[2 * v + k] < lo[k]) lo[k] = xy[2 * v + k]; if (xy[2 * v + k] > hi[k]) hi[k] = xy[2 * v + k]; }
+  int R = (int)(2.0 * sqrt((double)ns)); if (R < 1) R = 1; if (R > 4096) R = 4096;
+  double ext = hi[0] - lo[0] > hi[1] - lo[1] ? hi[0] - lo[0] : hi[1] - lo[1];
+  if (!(ext > 0)) ext = 1.0;
+  const double cell = ext / R * (1.0 + 1e-12);
+  const int RX = (int)((hi[0] - lo[0]) / cell) + 1, RY = (int)((hi[1] - lo[1]) / cell) + 1;
+  int64_t* cnt = (int64_t*)calloc((size_t)RX * RY + 1, sizeof(int64_t));
+#define CELLOF(x, k) ((int)(((x) - lo[k]) / cell))
+  for (int pass = 0; pass < 2; ++pass) {
+    static int32_t* items = NULL;
+    if (pass == 1) {
+      int64_t tot = 0;
+      for (int64_t c = 0; c < (int64_t)RX * RY; ++c) { int64_t t = cnt[c]; cnt[c] = tot; tot += t; }
+      cnt[(int64_t)RX * RY] = tot;
+      items = (int32_t*)malloc((size_t)(tot + 1) * sizeof(int32_t));
+    }
+    for (int64_t sgi = 0; sgi < ns; ++sgi) {
+      const double* a = xy + 2 * (int64_t)segs[2 * sgi]; const double* b = xy + 2 * (int64_t)segs[2 * sgi + 1];
+      int x0 = CELLOF(a[0] < b[0] ? a[0] : b[0], 0), x1 = CELLOF(a[0] < b[0] ? b[0] : a[0], 0);
+      int y0 = CELLOF(a[1] < b[1] ? a[1] : b[1], 1), y1 = CELLOF(a[1] < b[1] ? b[1] : a[1], 1);
+      for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) { if (pass == 0) cnt[(int64_t)y * RX + x]++; else items[cnt[(int64_t)y * RX + x]++] = (int32_t)sgi; }
+    }
+    if (pass == 1) {
+      /* cnt now holds the END offsets: shift back to starts */
+      for (int64_t c = (int64_t)RX * RY; c > 0; --c) cnt[c] = cnt[c - 1];
+      cnt[0] = 0;
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+      for (int64_t i = 0; i < nsub; ++i) {
+        const double* vp = xy + 2 * (int64_t)vidx[i];
+        const int cx = CELLOF(vp[0], 0), cy = CELLOF(vp[1], 1);
+        double cur = 1e100;
+        const int rmax = RX > RY ? RX : RY;
+        for (int r = 0; r <= rmax; ++r) {
+          /* everything outside the (2r-1)^2 block around the vertex's cell is at least (r-1) * cell away */
+          if (r >= 1 && cur < (double)(r - 1) * cell * (1.0 - 1e-9)) break;
+          for (int y = cy - r; y <= cy + r; ++y) {
+            if (y < 0 || y >= RY) continue;
+            const int step = (y == cy - r || y == cy + r) ? 1 : 2 * r;
+            for (int x = cx - r; x <= cx + r; x += (step > 0 ? step : 1)) {
+              if (x < 0 || x >= RX) continue;
+              for (int64_t e = cnt[(int64_t)y * RX + x]; e < cnt[(int64_t)y * RX + x + 1]; ++e) {
+                const int64_t sg = items[e];
+                const double d = orc_point_segment_distance(vp, xy + 2 * (int64_t)segs[2 * sg], xy + 2 * (int64_t)segs[2 * sg + 1]);
+                if (d < cur) cur = d;
+              }
+            }
+          }
+        }
+        dist_sub[i] = cur;
+      }
+      free(items); items = NULL;
+    }
+  }
+#undef CELLOF
+  free(cnt);
+}
 /* distance.hh:157-173 (3-D estimate: corners, edge midpoints, centroid) */
 void orc_distance_3d(const double* xyz, int64_t nv, const int32_t* tris, int64_t ns, double* dist) {
 #pragma omp parallel for num_threads(g_threads) schedule(static)
@@ -1055,4 +1119,30 @@ void orc_project_interface_p0(const double* new_len, const int64_t* new_off, int
     }
     dofs_new[i] = acc;
   }
+}
+
+/* mmesh.hh:1194-1218 + 1919-1941: sequential, order dependent -- restated statement by statement */
+int64_t orc_component_numbers(int64_t nz, const int64_t* zone_off, const int32_t* zone_cells, int64_t component_count,
+                              int32_t* zone_number, int32_t* cell_number) {
+  int markAgain = 1;
+  while (markAgain) {                                                      /* :1204 */
+    markAgain = 0;
+    for (int64_t k = 0; k < nz; ++k) {                                     /* :1212-1226: insert_ then remove_, in order */
+      int64_t componentNumber = 0;                                         /* getComponentNumber_, :1922 */
+      for (int64_t e = zone_off[k]; e < zone_off[k + 1]; ++e) {
+        const int32_t num = cell_number[zone_cells[e]];
+        if (num > 0) {                                                     /* :1926 */
+          if (componentNumber != 0 && num != componentNumber) {            /* :1928-1929 */
+            markAgain = 1;
+            componentNumber = num < componentNumber ? num : componentNumber;
+          } else
+            componentNumber = num;
+        }
+      }
+      if (componentNumber == 0) componentNumber = component_count++;       /* :1938 */
+      for (int64_t e = zone_off[k]; e < zone_off[k + 1]; ++e) cell_number[zone_cells[e]] = (int32_t)componentNumber;   /* :1867-1870 */
+      zone_number[k] = (int32_t)componentNumber;
+    }
+  }
+  return component_count;
 }

@@ -152,6 +152,18 @@ void orc_sutherland_hodgman_batch(const double* subj, const double* clip, int64_
 void orc_set_threads(int n);
 int orc_num_threads(void);
 
+/* labelled CULLED variant of Distance::update for a vertex subset (grid buckets + ring search; same values as the brute force) */
+void orc_distance_2d_culled_subset(const double* xy, int64_t nv_all, const int32_t* vidx, int64_t nsub, const int32_t* segs,
+                                   int64_t ns, double* dist_sub);
+
+/* ---- component numbers of adapt_() ------------------------------------------------------------- */
+/* dune/mmesh/grid/mmesh.hh:1194-1218 (the `while (markAgain)` loop over insert_ then remove_) with getComponentNumber_
+   (:1919-1941) and the marking of the zone's elements (:1862-1872, :1889-1903).  zones = CSR over cell indices in the order the
+   reference visits them; cell_number must hold ElementInfo::componentNumber on entry (0 after postAdapt) and holds it on
+   exit; zone_number[k] = the componentNumber the LAST pass returned for zone k; returns componentCount_ afterwards. */
+int64_t orc_component_numbers(int64_t nz, const int64_t* zone_off, const int32_t* zone_cells, int64_t component_count,
+                              int32_t* zone_number, int32_t* cell_number);
+
 #ifdef __cplusplus
 }
 #endif

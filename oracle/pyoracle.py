@@ -162,6 +162,15 @@ def distance_2d_subset(xy, vidx, segs):
     return d
 
 
+def distance_2d_culled(xy, segs, vidx=None):
+    """Labelled CULLED variant (grid buckets + ring search): the brute-force values, bit for bit, at O(Nv) cost."""
+    xy, segs = _f64(xy), _i32(segs)
+    vidx = _i32(np.arange(xy.shape[0]) if vidx is None else vidx)
+    out = np.empty(vidx.shape[0], np.float64)
+    lib().orc_distance_2d_culled_subset(_p(xy), C.c_int64(xy.shape[0]), _p(vidx), C.c_int64(vidx.shape[0]), _p(segs), C.c_int64(segs.shape[0]), _p(out))
+    return out
+
+
 def distance_3d(xyz, tris):
     xyz, tris = _f64(xyz), _i32(tris)
     d = np.empty(xyz.shape[0], np.float64)
@@ -338,3 +347,15 @@ def project_interface_p0(new_len, new_off, old_len, old_idx, dofs_old):
     lib().orc_project_interface_p0(_p(new_len), _p(new_off), C.c_int64(new_len.shape[0]), _p(old_len), _p(old_idx),
                                    _p(dofs_old), _p(out))
     return out
+
+
+def component_numbers(zone_off, zone_cells, nc, component_count=1, cell_number=None):
+    """adapt_()'s component numbering (mmesh.hh:1194-1218, 1919-1941).  Returns (zone_number, cell_number, component_count)."""
+    zone_off = np.ascontiguousarray(zone_off, np.int64)
+    zone_cells = _i32(zone_cells)
+    nz = zone_off.shape[0] - 1
+    zn = np.zeros(max(nz, 1), np.int32)
+    cn = np.zeros(nc, np.int32) if cell_number is None else _i32(cell_number).copy()
+    lib().orc_component_numbers.restype = C.c_int64
+    cc = lib().orc_component_numbers(C.c_int64(nz), _p(zone_off), _p(zone_cells), C.c_int64(component_count), _p(zn), _p(cn))
+    return zn[:nz], cn, int(cc)

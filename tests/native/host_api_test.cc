@@ -70,7 +70,7 @@ int main(int argc, char** argv) {
     // pre-check of ensureInterfaceMovement must throw GridError exactly when the oracle sees an invalid cell
     for (std::size_t v = 0; v < nv; ++v) if (s.vflags[v] & 1) s.interfaceVertices.push_back((int32_t)v);
     std::vector<GlobalCoordinate<2>> ish(s.interfaceVertices.size(), GlobalCoordinate<2>{ 0.0, 1e-3 });
-    try { auto bad = grid.ensureInterfaceMovement(ish); std::printf("ifmove ok %zu\n", bad.size()); }
+    try { auto bad = grid.invertedCellsUnderInterfaceMovement(ish); std::printf("ifmove ok %zu\n", bad.size()); }
     catch (const GridError&) { std::printf("ifmove GridError\n"); }
     // wrong-sized shifts are an error, as the assert at mmesh.hh:1095
     shifts.pop_back();
@@ -87,11 +87,17 @@ int main(int argc, char** argv) {
       std::ifstream in2(argv[1]);
       { std::size_t a, b, c, d; in2 >> a >> b >> c >> d; double t; for (std::size_t i = 0; i < 2 * nv; ++i) in2 >> t; for (auto& p : shifts) in2 >> p[0] >> p[1]; }
       const mmb_step_result r = g2.step(shifts);
-      std::printf("step_counts %lld %lld %lld %lld\nstep_marks", (long long)r.n_refine, (long long)r.n_coarsen, (long long)r.n_invalid, (long long)r.n_illegal);
+      std::printf("step_counts %lld %lld %lld %lld\nstep_moved %lld\nstep_marks", (long long)r.n_refine, (long long)r.n_coarsen, (long long)r.n_invalid, (long long)r.n_illegal, (long long)r.moved);
       for (std::size_t c = 0; c < nc; ++c) std::printf(" %d", g2.getMark(c));
       std::printf("\nstep_valid");
       for (uint8_t f : g2.validity()) std::printf(" %d", (int)f);
       std::printf("\nstep_legal");
+      for (uint8_t f : g2.edgeFlags()) std::printf(" %d", (int)f);
+      std::printf("\n");
+      // the trial move inverts cells, so the default policy withheld moveVertices: a second step with move_policy 1 applies it
+      g2.setMovePolicy(1);
+      const mmb_step_result r1 = g2.step(shifts);
+      std::printf("step1_moved %lld %lld\nstep1_legal", (long long)r1.moved, (long long)r1.n_invalid);
       for (uint8_t f : g2.edgeFlags()) std::printf(" %d", (int)f);
       std::printf("\n");
     }

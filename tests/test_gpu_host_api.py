@@ -82,8 +82,89 @@ def test_host_class_user_loop(oracle, tmp_path):
     # the fused step() call returns the same fields as the member-by-member loop
     assert np.array_equal(np.array(lines["step_marks"], int), marks)
     assert np.array_equal(np.array(lines["step_valid"], int), valid)
-    assert np.array_equal(np.array(lines["step_legal"], int), legal)
-    assert [int(v) for v in lines["step_counts"]] == [int(counts[0]), int(counts[1]), int(ninv), int((legal == 0).sum())]
+    # move_policy 0 (default): the trial move inverts cells => moveVertices withheld on the device, legality describes the
+    # mesh as it stays; the next step with move_policy 1 applies the same shifts
+    legal_unmoved, _ = oracle.legality(m.xy, None, m.edges)
+    assert lines["step_moved"] == ["0"]
+    assert np.array_equal(np.array(lines["step_legal"], int), legal_unmoved)
+    assert [int(v) for v in lines["step_counts"]] == [int(counts[0]), int(counts[1]), int(ninv), int((legal_unmoved == 0).sum())]
+    assert lines["step1_moved"] == ["1", str(int(ninv))]
+    assert np.array_equal(np.array(lines["step1_legal"], int), legal)
     # after the (large) move the mesh has inverted cells => ensureInterfaceMovement's pre-check throws (mmesh.hh:926-930)
     _, _, ninv_moved = oracle.trial_validate(oracle.move(m.xy, s), None, m.cells)
     assert lines["ifmove"][0] == ("GridError" if ninv_moved > 0 else "ok")
+
+
+ADAPT_EXE = os.path.join(ROOT, "tests", "native", "_build", "adapt_handle_test")
+
+
+def build_adapt_exe():
+    os.makedirs(os.path.dirname(ADAPT_EXE), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "dune-mmesh_b200", "host"),
+                           os.path.join(ROOT, "tests", "native", "adapt_handle_test.cc"), "-o", ADAPT_EXE,
+                           "-L", os.path.join(ROOT, "dune-mmesh_b200", "lib"), "-lmmesh_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "dune-mmesh_b200", "lib")])
+
+
+def test_adapt_handle_driver_compiles_and_links():
+    from mmesh_b200 import capi
+    capi.build()
+    build_adapt_exe()
+    assert os.path.exists(ADAPT_EXE)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ncomp", [1, 3])
+def test_adapt_handle_drop_in(oracle, tmp_path, ncomp):
+    """MMesh::adapt(handle) (mmesh.hh:1138-1165) through the C++ host class: old snapshot -> TDS edit (generated
+    insertions / removals) -> new snapshot; pairs from the two snapshots, gather -> device projection -> scatter.
+    Expected values: the oracle's transfer over the pair list of a brute-force overlap search (every vanished cell that
+    overlaps a new cell), which is independent of the product's pair builder."""
+    from mmesh_b200 import synth
+    from adapt_cases import adapt_case
+    build_adapt_exe()
+    case = adapt_case(n=16, seed=21, n_insert=30, n_remove=30)
+    old = case["old"]
+    k = np.stack([np.take_along_axis(old.cells, ((old.perm >> (2 * t)) & 3)[:, None].astype(np.int64), 1)[:, 0] for t in range(3)], 1)
+    pk = old.xy[k]
+    if ncomp == 3:
+        dofs_old = np.sin(np.pi * pk[..., 0]) * np.sin(np.pi * pk[..., 1]) + 2.0
+    else:
+        dofs_old = (np.sin(np.pi * pk[..., 0]) * np.sin(np.pi * pk[..., 1]) + 2.0).mean(axis=1, keepdims=True)
+    ncn = case["new_cells"].shape[0]
+    carried = np.full((ncn, ncomp), -7.0)                      # unchanged cells: whatever the handle holds stays
+    new_edges, _, _ = synth.build_edges(case["new_cells"], case["new_xy"].shape[0])
+    f = tmp_path / "adapt.bin"
+    with open(f, "wb") as out:
+        for (xy, ids, cells, perm, edges) in ((old.xy, case["old_id"], old.cells, old.perm, old.edges),
+                                              (case["new_xy"], case["new_id"], case["new_cells"], case["new_perm"], new_edges)):
+            np.array([xy.shape[0], cells.shape[0], edges.shape[0], 0], np.int64).tofile(out)
+            np.ascontiguousarray(xy, np.float64).tofile(out); np.ascontiguousarray(ids, np.int64).tofile(out)
+            np.ascontiguousarray(cells, np.int32).tofile(out); np.ascontiguousarray(perm, np.uint8).tofile(out)
+            np.ascontiguousarray(edges, np.int32).tofile(out)
+        np.array([ncomp], np.int64).tofile(out)
+        np.ascontiguousarray(dofs_old, np.float64).tofile(out); carried.tofile(out)
+    res = subprocess.run([ADAPT_EXE, str(f)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    lines = {l.split()[0]: l.split()[1:] for l in res.stdout.strip().splitlines()}
+    got = np.array([float(v) for v in lines["dofs"]]).reshape(ncn, ncomp)
+    created = np.nonzero(case["created"])[0]
+    assert int(lines["adapt"][0]) == 1 and int(lines["adapt"][2]) == 1 and int(lines["adapt"][6]) == created.size
+    assert np.array_equal(got[~case["created"]], carried[~case["created"]])
+    # independent pair list: brute-force overlap search, children in ascending old index
+    van = np.nonzero(case["vanished"])[0]
+    newc = case["new_xy"][case["new_cells"]]
+    off, oidx = [0], []
+    for K in created:
+        for o in van:
+            if oracle.intersection_volume(pk[o].reshape(6), newc[K].reshape(6)) > 0.0:
+                oidx.append(o)
+        off.append(len(oidx))
+    oidx = np.array(oidx, np.int32)
+    prm = oracle.Params.default()
+    ref, mass, cov, npc = oracle.project(case["new_xy"], case["new_cells"], case["new_perm"], np.array(off, np.int64), created.astype(np.int32),
+                                         pk[oidx].reshape(-1, 6), oidx, dofs_old, ncn, ncomp, prm)
+    ref = ref.reshape(ncn, ncomp)
+    # accumulation order differs (component order vs ascending index), pieces below the 1e-8 cut-off differ by touching pairs: 1e-12
+    assert np.abs(got[created] - ref[created]).max() <= 1e-12 * np.abs(ref[created]).max()
+    assert int(lines["after"][1]) == 0

@@ -305,12 +305,15 @@ def test_adapt_step_composition(gpu_ctx_factory, oracle):
     ctx = gpu_ctx_factory(2)
     _upload(ctx, m)
     prm = ctx.indicator_init()
+    prm.move_policy = 1                       # always move (the 0.3 h shifts invert a few cells; policy 0 is tested below)
+    ctx.set_params(prm)
     ctx.upload_pairs(new_off, new_cell, old_xy, old_idx)
     rng = np.random.default_rng(5)
     dofs = rng.uniform(size=(m.nc, 3))
     ctx.project(3, dofs, download=False)      # makes the DOFs resident
     ctx.upload_shifts(s)
     res = ctx.adapt_step(None, ncomp=3)
+    assert res.moved == 1
     oprm = oracle.Params.from_buffer_copy(bytes(prm))
     rd = oracle.distance_2d(m.xy, m.segs)
     rm, _, rc = oracle.mark(m.xy, rd, m.cells, m.perm, oprm, oracle.distance_max(rd))
@@ -338,6 +341,7 @@ def test_adapt_step_host_buffers(gpu_ctx_factory, oracle):
         _upload(ctx, m)
         prm = ctx.indicator_init()
         prm.drop_area = 1e-12
+        prm.move_policy = 1
         ctx.set_params(prm)
         ctx.upload_pairs(new_off, new_cell, old_xy, old_idx)
         rng = np.random.default_rng(5)
@@ -359,6 +363,34 @@ def test_adapt_step_host_buffers(gpu_ctx_factory, oracle):
             assert (r.n_refine, r.n_coarsen) == tuple(rc) and r.n_invalid == rn and r.n_illegal == rnill and r.n_pieces == rnpc
             assert abs(r.mass_new - rmass) <= 1e-13 * abs(rmass) and abs(r.covered_area - rcov) <= 1e-13 * rcov
             assert np.array_equal(ctx.download_coords(), oracle.move(m.xy, s))
+
+
+def test_step_withholds_move_when_cells_invert(gpu_ctx_factory, oracle):
+    """Reference order of the user loop (doc/examples/moving.py:231-252): ensureVertexMovement == true => vertices are removed
+    BEFORE moveVertices.  move_policy 0 (default): a step whose trial move inverts a cell leaves the coordinates alone
+    (decided on the device), reports moved == 0 and its edge flags describe the unmoved mesh; a step without inverted
+    cells moves.  Resident and host-buffer steps agree."""
+    from mmesh_b200 import synth
+    m = _mesh1(60)
+    big, small = synth.shifts_uniform(m, 0.45 * m.h, 30), synth.shifts_uniform(m, 0.05 * m.h, 31)
+    assert oracle.trial_validate(m.xy, big, m.cells)[2] > 0 and oracle.trial_validate(m.xy, small, m.cells)[2] == 0
+    for host in (False, True):
+        ctx = gpu_ctx_factory(2)
+        _upload(ctx, m)
+        ctx.indicator_init()
+        assert ctx.get_params().move_policy == 0
+        step = (lambda s: ctx.adapt_step_host(s, 0, None)["result"]) if host else (lambda s: ctx.adapt_step(s, 0))
+        r = step(big)
+        assert r.moved == 0 and r.n_invalid == oracle.trial_validate(m.xy, big, m.cells)[2]
+        assert np.array_equal(ctx.download_coords(), m.xy)
+        assert r.n_illegal == oracle.legality(m.xy, None, m.edges)[1]
+        r = step(small)
+        moved = oracle.move(m.xy, small)
+        assert r.moved == 1 and r.n_invalid == 0 and np.array_equal(ctx.download_coords(), moved)
+        assert r.n_illegal == oracle.legality(moved, None, m.edges)[1]
+        prm = ctx.get_params(); prm.move_policy = 1; ctx.set_params(prm)
+        r = step(big)
+        assert r.moved == 1 and np.array_equal(ctx.download_coords(), oracle.move(moved, big))
 
 
 def test_interface_projection_and_refinement_points(gpu_ctx_factory, oracle):
@@ -525,3 +557,26 @@ def test_adapt_candidate_lists_match_oracle(gpu_ctx_factory, oracle):
             assert rs.tolist() == want["remove_segs"].tolist()
             assert rv.tolist() == want["remove_seg_vertices"].tolist()
             assert len(want["remove_cells"]) > 20
+
+
+def test_component_numbers_like_adapt(gpu_ctx_factory, oracle):
+    """getComponentNumber_ fix point (mmesh.hh:1194-1218, 1919-1941) on the device against the oracle's sequential loop"""
+    from test_oracle_components import random_zones
+    m = _mesh1(40)
+    ctx = gpu_ctx_factory(2)
+    _upload(ctx, m)
+    rng = np.random.default_rng(12)
+    for nz, size in ((0, 3), (1, 3), (50, 4), (3000, 8), (20000, 3)):
+        off, cells = random_zones(rng, m.nc, nz, max_size=size)
+        base = int(rng.integers(1, 9))
+        zn, cn, cc = ctx.component_numbers(off, cells, base)
+        rz, rc, rcc = oracle.component_numbers(off, cells, m.nc, base)
+        assert np.array_equal(zn, rz) and np.array_equal(cn, rc) and cc == rcc
+    # the zones adapt_() really builds: stars of removed vertices and the two cells of split edges (overlapping on purpose)
+    vs = rng.choice(m.nv, 300, replace=False)
+    star = [np.nonzero((m.cells == v).any(axis=1))[0] for v in vs]
+    off = np.concatenate([[0], np.cumsum([len(s) for s in star])]).astype(np.int64)
+    cells = np.concatenate(star).astype(np.int32)
+    zn, cn, cc = ctx.component_numbers(off, cells, 1)
+    rz, rc, rcc = oracle.component_numbers(off, cells, m.nc, 1)
+    assert np.array_equal(zn, rz) and np.array_equal(cn, rc) and cc == rcc and len(set(rz.tolist())) < len(rz)
