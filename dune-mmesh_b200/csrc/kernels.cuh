@@ -462,10 +462,30 @@ __device__ __forceinline__ void dist_lane_walk(DistQuery& q, const SegLeaf* __re
     if (!(q.lb2(__ldg(box + sib)) > q.T2f)) q.dfs(leaf, box, ns, L, sib);
   }
 }
+// Cold start (no hints yet: the first Distance::update after a snapshot upload): a coarse grid over the interface's bounding
+// box, every grid cell holding the facet nearest to its centre (one full search per grid cell, 32 k searches).  A vertex
+// takes its grid cell's facet as the first upper bound -- any facet is a valid one, the search below makes it exact.
+constexpr int SEED_GX = 256, SEED_GY = 128;
+__global__ void __launch_bounds__(128)
+k_distance_seeds(const SegLeaf* __restrict__ leaf, const float4* __restrict__ box, int ns, int L, int32_t* __restrict__ seed) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= SEED_GX * SEED_GY) return;
+  const float4 root = __ldg(box + 1);
+  DistQuery q;
+  q.px = (double)root.x + ((double)root.z - (double)root.x) * (((g % SEED_GX) + 0.5) / SEED_GX);
+  q.py = (double)root.y + ((double)root.w - (double)root.y) * (((g / SEED_GX) + 0.5) / SEED_GY);
+  q.pxlo = __double2float_rd(q.px); q.pxhi = __double2float_ru(q.px);
+  q.pylo = __double2float_rd(q.py); q.pyhi = __double2float_ru(q.py);
+  q.diag = ((double)root.z - (double)root.x) + ((double)root.w - (double)root.y);
+  q.best = 1e100; q.arg = 0;
+  q.set_threshold();
+  q.dfs(leaf, box, ns, L, 1);
+  seed[g] = q.arg;
+}
 __global__ void __launch_bounds__(256, 5)
 k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restrict__ leaf,
              const float4* __restrict__ box, int ns, int L, int logL, double* __restrict__ dist, int32_t* __restrict__ hint,
-             Counters* __restrict__ cnt) {
+             const int32_t* __restrict__ seed, Counters* __restrict__ cnt) {
   __shared__ int s_front[8][2][DIST_QCAP];
   __shared__ float4 s_gbox[8][DIST_QCAP];                 // boxes of the candidate groups (written by the lane that tested them)
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -485,15 +505,15 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
   }
   int h = live ? hint[v] : 0;
   if (h >= ns) h = -1;
-  if (__any_sync(0xffffffffu, live && h < 0)) {
-    // cold start (no hint yet): every lane descends greedily to the leaf whose boxes are nearest at each level -- not
-    // necessarily the nearest facet, but a near one: any facet is a valid upper bound, the search below makes it exact
-    int node = 1;
-    for (int lev = 0; lev < logL; ++lev) {
-      const float dl = q.lb2(__ldg(box + 2 * node)), dr = q.lb2(__ldg(box + 2 * node + 1));
-      node = 2 * node + (dr < dl ? 1 : 0);                // empty boxes (leaves >= ns) have an infinite bound: never chosen
+  if (live && h < 0) {                                   // cold start: the facet nearest to the centre of the vertex's seed-grid cell
+    int sd = 0;
+    if (seed != nullptr) {
+      const float4 root = __ldg(box + 1);
+      const double fx = (q.px - (double)root.x) / ((double)root.z - (double)root.x), fy = (q.py - (double)root.y) / ((double)root.w - (double)root.y);
+      const int gx = min(max((int)(fx * SEED_GX), 0), SEED_GX - 1), gy = min(max((int)(fy * SEED_GY), 0), SEED_GY - 1);   // NaN (degenerate box) -> 0
+      sd = seed[gy * SEED_GX + gx];
     }
-    if (live && h < 0) h = min(node - L, ns - 1);
+    h = min(max(sd, 0), ns - 1);
   }
   if (live) q.eval_leaf(leaf, h);
   // the warp's bound and box (dead lanes are neutral: T2f = 0, empty box)

@@ -4,6 +4,9 @@
 #include "../../include/mmesh_b200.h"
 #include "kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -48,6 +51,9 @@ struct mmb_context {
   cudaStream_t stream = nullptr; bool own_stream = false;
   std::string err;
   int64_t nv = 0, nc = 0, ne = 0, ns = 0, nc_pad = 0;
+  ncclComm_t comm = nullptr; int world = 1, rank = 0; std::vector<int64_t> halo_send_counts, halo_recv_counts;
+  cudaStream_t s_comm = nullptr; std::vector<cudaEvent_t> comm_ev;
+  cudaGraphExec_t step_graph = nullptr; int graph_ncomp = -1; mmb_params graph_prm{}; bool graph_valid = false; int64_t graph_launches = 0; int sharded_steps = 0;
   bool sharded = false;             // one of several ranks: the gate of the fused step's move comes from an all-reduce
   int64_t own_lo = 0, own_hi = 0;   // owned cell range (counts); halo cells outside it are evaluated but not counted
   DBuf<int32_t> halo_send_idx, halo_recv_idx; DBuf<double2> halo_send, halo_recv; int64_t n_halo_send = 0, n_halo_recv = 0;
@@ -71,7 +77,7 @@ struct mmb_context {
   // bvh
   int L = 1;
   DBuf<SegLeaf> seg_leaf; DBuf<float4> box2; DBuf<int32_t> seg_hint; DBuf<unsigned> ticket;
-  DBuf<TriLeaf> tri_leaf; DBuf<Box3> box3;
+  DBuf<TriLeaf> tri_leaf; DBuf<Box3> box3; DBuf<int32_t> seed_grid; bool hints_cold = true;
   // projection
   int64_t nnew = 0, npairs = 0, n_old = 0;
   DBuf<long long> new_off; DBuf<int32_t> new_cell, old_idx; DBuf<double> old_xy, dofs_old, dofs_new, part_a, part_b, pair_vol;
@@ -176,7 +182,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->tile_lo_cells.release(); ctx->tile_lo_edges.release();
   ctx->cell_nb.release(); ctx->v_if.release(); ctx->cand_flag.release(); ctx->facet_keys.release(); ctx->ht_key.release(); ctx->ht_val.release(); ctx->ht_slot.release();
   ctx->v_bnd.release(); ctx->v_ifcount.release(); ctx->v_level.release(); ctx->first_claim.release(); ctx->first_seg.release(); ctx->chosen.release();
-  ctx->seg_leaf.release(); ctx->box2.release(); ctx->seg_hint.release(); ctx->ticket.release(); ctx->tri_leaf.release(); ctx->box3.release();
+  ctx->seg_leaf.release(); ctx->box2.release(); ctx->seg_hint.release(); ctx->ticket.release(); ctx->tri_leaf.release(); ctx->box3.release(); ctx->seed_grid.release();
   ctx->new_off.release(); ctx->new_cell.release(); ctx->old_idx.release(); ctx->old_xy.release();
   ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
   ctx->tr_in.release(); ctx->tr_out.release(); ctx->tr_u.release(); ctx->tr_ug.release();
@@ -185,6 +191,9 @@ int mmb_destroy(mmb_context* ctx) {
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->h_remote_stage) cudaFreeHost(ctx->h_remote_stage);
   ctx->d_remote_idx.release(); ctx->d_remote_stage.release();
+  mmb_comm_destroy(ctx);
+  if (ctx->s_comm) cudaStreamDestroy(ctx->s_comm);
+  for (auto e : ctx->comm_ev) cudaEventDestroy(e);
   if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
@@ -361,6 +370,7 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
   if (dim == 2) {
     CK(ctx->seg_leaf.ensure(L)); CK(ctx->box2.ensure(2 * (size_t)L)); CK(ctx->seg_hint.ensure(nv)); CK(ctx->ticket.ensure(1));
     CK(cudaMemsetAsync(ctx->seg_hint.p, 0xFF, (size_t)nv * sizeof(int32_t), ctx->stream));    // -1: no hint yet
+    ctx->hints_cold = true;
     CK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
   }
   else {
@@ -371,7 +381,7 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   ctx->has_shift = false; ctx->dist_valid = false; ctx->mesh_ok = true;
-  ctx->nnew = ctx->npairs = 0;
+  ctx->nnew = ctx->npairs = 0; ctx->graph_valid = false; ctx->sharded_steps = 0;
   return MMB_OK;
 }
 
@@ -558,8 +568,8 @@ int mmb_legality(mmb_context* ctx, uint8_t* flags_host, int64_t* n_illegal) {
 }
 
 // ---- distance -------------------------------------------------------------------------------------------
-static int do_distance(mmb_context* ctx) {
-  CK(cudaMemsetAsync(&ctx->counters.p->max_dist_bits, 0, sizeof(unsigned long long), ctx->stream));
+static int do_distance(mmb_context* ctx, bool reset_max = true) {
+  if (reset_max) CK(cudaMemsetAsync(&ctx->counters.p->max_dist_bits, 0, sizeof(unsigned long long), ctx->stream));
 #ifdef MMB_DEV_VARIANTS
   CK(cudaMemsetAsync(ctx->counters.p->dbg, 0, sizeof(ctx->counters.p->dbg), ctx->stream));
 #endif
@@ -570,8 +580,14 @@ static int do_distance(mmb_context* ctx) {
              ns, L, ctx->seg_leaf.p, ctx->box2.p, ctx->ticket.p);
     }
     int logL = 0; while ((1 << logL) < L) ++logL;
+    if (ctx->hints_cold && ns) {                               // first update after an upload: no hints yet
+      CK(ctx->seed_grid.ensure(SEED_GX * SEED_GY));
+      LAUNCH("distance_seeds", k_distance_seeds, grid_for(SEED_GX * SEED_GY, 128), 128, ctx->seg_leaf.p, ctx->box2.p, ns, L, ctx->seed_grid.p);
+    }
     LAUNCH("distance2d", k_distance2d, grid_for(ctx->nv, 256), 256, (const double2*)ctx->x.p, ctx->nv, ctx->seg_leaf.p,
-           ctx->box2.p, ns, L, logL, ctx->dist.p, ctx->seg_hint.p, ctx->counters.p);
+           ctx->box2.p, ns, L, logL, ctx->dist.p, ctx->seg_hint.p, ctx->hints_cold ? (const int32_t*)ctx->seed_grid.p : (const int32_t*)nullptr,
+           ctx->counters.p);
+    ctx->hints_cold = false;
   } else {
     if (ns) {
       LAUNCH("bvh_build3d", k_bvh_build3d, L < 256 ? 1 : L / 256, 256, ctx->x.p, ctx->facets_sorted.p, ns, L, ctx->tri_leaf.p,
@@ -700,7 +716,7 @@ int mmb_upload_pairs(mmb_context* ctx, int64_t nnew, const int64_t* new_off_host
     CK(cudaMemcpyAsync(ctx->old_xy.p, old_xy_host, 6 * (size_t)npairs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->nnew = nnew; ctx->npairs = npairs;
+  ctx->nnew = nnew; ctx->npairs = npairs; ctx->graph_valid = false;
   ctx->max_old_idx = -1;
   for (int64_t p = 0; p < npairs; ++p) ctx->max_old_idx = std::max<int64_t>(ctx->max_old_idx, old_idx_host[p]);
   // chunk table for the pipelined host-buffer step: new cells are listed in ascending cell order (element iteration
@@ -1439,6 +1455,191 @@ int mmb_step_phase(mmb_context* ctx, int which, int ncomp) {
   return MMB_OK;
 }
 int mmb_step_phase_rest(mmb_context* ctx, int ncomp) { return mmb_step_phase(ctx, 0, ncomp); }
+
+// ---- NCCL inside the library ---------------------------------------------------------------------------------------
+} // extern "C"
+namespace {
+struct NcclApi {
+  void* h = nullptr; bool ok = false; std::string err;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr; decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr; decltype(&ncclAllReduce) AllReduce = nullptr; decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr; decltype(&ncclGroupStart) GroupStart = nullptr; decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+NcclApi& nccl_api() {
+  static NcclApi a;
+  static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);          // a process that already uses NCCL (torch) gets that copy
+  if (!a.h) { a.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return a; }
+#define NCCL_SYM(name) a.name = (decltype(a.name))dlsym(a.h, "nccl" #name); if (!a.name) { a.err = "libnccl.so.2 lacks nccl" #name; return a; }
+  NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(AllReduce) NCCL_SYM(Send) NCCL_SYM(Recv)
+  NCCL_SYM(GroupStart) NCCL_SYM(GroupEnd) NCCL_SYM(GetErrorString)
+#undef NCCL_SYM
+  a.ok = true;
+  return a;
+}
+}  // namespace
+#define NK(call)                                                                                         \
+  do {                                                                                                   \
+    ncclResult_t r_ = (call);                                                                            \
+    if (r_ != ncclSuccess) { ctx->err = std::string(#call) + ": " + nccl_api().GetErrorString(r_); return MMB_ERR_NCCL; } \
+  } while (0)
+extern "C" {
+
+int mmb_comm_unique_id(uint8_t id_out[128]) {
+  if (!id_out) return MMB_ERR_INVALID_ARG;
+  NcclApi& N = nccl_api();
+  if (!N.ok) return MMB_ERR_NCCL;
+  ncclUniqueId id;
+  if (N.GetUniqueId(&id) != ncclSuccess) return MMB_ERR_NCCL;
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id_out, &id, 128);
+  return MMB_OK;
+}
+int mmb_comm_init(mmb_context* ctx, int world, int rank, const uint8_t id_bytes[128]) {
+  if (!ctx || !id_bytes || world < 1 || rank < 0 || rank >= world) return MMB_ERR_INVALID_ARG;
+  NcclApi& N = nccl_api();
+  if (!N.ok) { ctx->err = N.err; return MMB_ERR_NCCL; }
+  REQUIRE(!ctx->comm, MMB_ERR_STATE, "mmb_comm_init: the context already has a communicator");
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId id; memcpy(&id, id_bytes, 128);
+  NK(N.CommInitRank(&ctx->comm, world, id, rank));
+  ctx->world = world; ctx->rank = rank; ctx->sharded = world > 1;
+  if (!ctx->s_comm) CK(cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking));
+  while (ctx->comm_ev.size() < 10) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->comm_ev.push_back(e); }
+  CK(ctx->reduce_vec.ensure(16));
+  CK(cudaMemsetAsync(ctx->reduce_vec.p, 0, 16 * sizeof(double), ctx->stream));
+  ctx->graph_valid = false; ctx->sharded_steps = 0;
+  return MMB_OK;
+}
+int mmb_comm_destroy(mmb_context* ctx) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  if (ctx->step_graph) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; ctx->graph_valid = false; }
+  if (ctx->comm) { cudaStreamSynchronize(ctx->stream); if (ctx->s_comm) cudaStreamSynchronize(ctx->s_comm); nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ctx->sharded = false; ctx->world = 1; ctx->rank = 0;
+  return MMB_OK;
+}
+int mmb_halo_counts(mmb_context* ctx, const int64_t* send_counts, const int64_t* recv_counts) {
+  if (!ctx || !send_counts || !recv_counts) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->comm, MMB_ERR_STATE, "mmb_halo_counts before mmb_comm_init");
+  int64_t ts = 0, tr = 0;
+  for (int p = 0; p < ctx->world; ++p) { REQUIRE(send_counts[p] >= 0 && recv_counts[p] >= 0, MMB_ERR_INVALID_ARG, "negative halo count"); ts += send_counts[p]; tr += recv_counts[p]; }
+  REQUIRE(ts == ctx->n_halo_send && tr == ctx->n_halo_recv, MMB_ERR_INVALID_ARG, "halo counts do not add up to the lists of mmb_halo_setup");
+  ctx->halo_send_counts.assign(send_counts, send_counts + ctx->world); ctx->halo_recv_counts.assign(recv_counts, recv_counts + ctx->world);
+  ctx->graph_valid = false;
+  return MMB_OK;
+}
+// everything one sharded step puts on the two streams (kernels on ctx->stream, collectives on ctx->s_comm)
+static int sharded_enqueue(mmb_context* ctx, int ncomp) {
+  NcclApi& N = nccl_api();
+  cudaStream_t S0 = ctx->stream, Sc = ctx->s_comm;
+  cudaEvent_t* ev = ctx->comm_ev.data();
+  Counters* c = ctx->counters.p;
+  TRY(zero_counters(ctx));
+  if (ctx->n_halo_send)
+    LAUNCH("halo_pack", k_gather2, grid_for(ctx->n_halo_send, 256), 256, (const double2*)ctx->shift.p, ctx->halo_send_idx.p, ctx->n_halo_send, ctx->halo_send.p);
+  CK(cudaEventRecord(ev[0], S0));
+  CK(cudaStreamWaitEvent(Sc, ev[0], 0));
+  {                                                             // halo exchange of the shifts: grouped point-to-point
+    NK(N.GroupStart());
+    int64_t so = 0, ro = 0;
+    for (int p = 0; p < ctx->world; ++p) {
+      const int64_t ns = ctx->halo_send_counts[(size_t)p], nr = ctx->halo_recv_counts[(size_t)p];
+      if (ns) NK(N.Send(ctx->halo_send.p + so, (size_t)ns * 2, ncclDouble, p, ctx->comm, Sc));
+      if (nr) NK(N.Recv(ctx->halo_recv.p + ro, (size_t)nr * 2, ncclDouble, p, ctx->comm, Sc));
+      so += ns; ro += nr;
+    }
+    NK(N.GroupEnd());
+  }
+  CK(cudaEventRecord(ev[1], Sc));
+  TRY(do_distance(ctx, false));                                 // needs no shifts: runs under the exchange
+  CK(cudaEventRecord(ev[2], S0));
+  CK(cudaStreamWaitEvent(Sc, ev[2], 0));
+  NK(N.AllReduce(&c->max_dist_bits, &c->max_dist_bits, 1, ncclUint64, ncclMax, ctx->comm, Sc));     // non-negative doubles order like integers
+  CK(cudaEventRecord(ev[3], Sc));
+  CK(cudaStreamWaitEvent(S0, ev[1], 0));
+  if (ctx->n_halo_recv)
+    LAUNCH("halo_unpack", k_scatter2, grid_for(ctx->n_halo_recv, 256), 256, (double2*)ctx->shift.p, ctx->halo_recv_idx.p, ctx->n_halo_recv, (const double2*)ctx->halo_recv.p);
+  TRY(do_validate(ctx, true));
+  CK(cudaEventRecord(ev[4], S0));
+  CK(cudaStreamWaitEvent(Sc, ev[4], 0));
+  NK(N.AllReduce(&c->n_invalid, &c->n_invalid_global, 1, ncclUint64, ncclSum, ctx->comm, Sc));      // the gate of the move, same on all ranks
+  CK(cudaEventRecord(ev[5], Sc));
+  if (ncomp) TRY(do_project(ctx, ncomp));                       // needs neither the global maximum nor the gate
+  CK(cudaStreamWaitEvent(S0, ev[3], 0));
+  TRY(do_mark(ctx));
+  if (ctx->dim == 2 && ctx->ns)
+    LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
+           (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
+  CK(cudaStreamWaitEvent(S0, ev[5], 0));
+  TRY(do_move(ctx, true));
+  if (ctx->dim == 2) TRY(do_legality(ctx));
+  LAUNCH("reduce_vector", k_reduce_vector, 1, 32, ctx->counters.p, ctx->reduce_vec.p);
+  CK(cudaEventRecord(ev[6], S0));
+  CK(cudaStreamWaitEvent(Sc, ev[6], 0));
+  NK(N.AllReduce(ctx->reduce_vec.p, ctx->reduce_vec.p, 16, ncclDouble, ncclSum, ctx->comm, Sc));
+  CK(cudaEventRecord(ev[7], Sc));
+  CK(cudaStreamWaitEvent(S0, ev[7], 0));
+  CK(cudaGetLastError());
+  return MMB_OK;
+}
+int mmb_adapt_step_sharded(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_step_result* res) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok && ctx->comm, MMB_ERR_STATE, "mmb_adapt_step_sharded needs an uploaded shard and mmb_comm_init");
+  REQUIRE(ncomp == 0 || ((ncomp == 1 || ncomp == 3) && ctx->dim == 2), MMB_ERR_INVALID_ARG, "ncomp must be 0, 1 (P0) or 3 (DG-P1); projection is 2-D");
+  REQUIRE((int64_t)ctx->halo_send_counts.size() == ctx->world && (int64_t)ctx->halo_recv_counts.size() == ctx->world, MMB_ERR_STATE,
+          "mmb_adapt_step_sharded before mmb_halo_setup / mmb_halo_counts");
+  TRY(stage_shifts(ctx, shifts_host));
+  if (ncomp) TRY(stage_dofs(ctx, ncomp, 0, nullptr));
+  if (ncomp && ctx->nnew) REQUIRE(ctx->max_old_idx < ctx->n_old, MMB_ERR_INVALID_ARG, "projection: a pair references an old cell beyond the DOF array");
+  static const bool use_graph = []() { const char* e = getenv("MMB_GRAPH"); return !(e && atoi(e) == 0); }();
+  // The first step runs eagerly: NCCL sets up its point-to-point channels on first use, which must not happen inside a
+  // capture.  From the second step on the launch sequence (it depends only on the snapshot, the pairs, ncomp and the
+  // parameters) is captured once and replayed.
+  if (use_graph && !ctx->timing && ctx->sharded_steps > 0) {
+    if (!ctx->graph_valid || ctx->graph_ncomp != ncomp || memcmp(&ctx->graph_prm, &ctx->prm, sizeof(mmb_params)) != 0) {
+      if (ctx->step_graph) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      const int64_t l0 = ctx->launches;
+      CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+      const int rc = sharded_enqueue(ctx, ncomp);
+      const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+      ctx->graph_launches = ctx->launches - l0; ctx->launches = l0;
+      if (rc != MMB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return MMB_ERR_CUDA; }
+      CK(cudaGraphInstantiate(&ctx->step_graph, g, 0));
+      cudaGraphDestroy(g);
+      ctx->graph_valid = true; ctx->graph_ncomp = ncomp; ctx->graph_prm = ctx->prm;
+    }
+    CK(cudaGraphLaunch(ctx->step_graph, ctx->stream));
+    ctx->launches += ctx->graph_launches;
+    ctx->dist_valid = true;
+  } else {
+    TRY(sharded_enqueue(ctx, ncomp));
+  }
+  ctx->sharded_steps++;
+  if (res) {
+    double* hv = reinterpret_cast<double*>(ctx->h_counters);     // pinned staging: 16 doubles + the max word fit in Counters
+    static_assert(sizeof(Counters) >= 17 * sizeof(double), "staging");
+    CK(cudaMemcpyAsync(hv, ctx->reduce_vec.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hv + 16, &ctx->counters.p->max_dist_bits, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    res->n_invalid = (int64_t)hv[0]; res->n_orient_nonpos = (int64_t)hv[1]; res->n_illegal = (int64_t)hv[2];
+    res->n_refine = (int64_t)hv[3]; res->n_coarsen = (int64_t)hv[4]; res->n_exact_orient = (int64_t)hv[5];
+    res->n_exact_incircle = (int64_t)hv[6]; res->n_pieces = (int64_t)hv[7]; res->mass_new = hv[8]; res->covered_area = hv[9];
+    res->max_dist = hv[16];
+    const bool withheld = ctx->prm.move_policy == 0 && res->n_invalid > 0;
+    res->moved = withheld ? 0 : 1;
+    if (ctx->dim == 3 && res->n_invalid > 0) {
+      ctx->err = "Vertices could not be moved, because the removal of vertices is not supported in 3D!";
+      return MMB_ERR_INVALID_CELL_3D;
+    }
+    if (withheld) { ctx->err = "moveVertices withheld: the trial move inverts cells (ensureVertexMovement == true); remove the vertices first"; return MMB_MOVE_WITHHELD; }
+  }
+  return MMB_OK;
+}
 
 // ---- timing ---------------------------------------------------------------------------------------------
 int mmb_timing_enable(mmb_context* ctx, int on) { if (!ctx) return MMB_ERR_INVALID_ARG; ctx->timing = on != 0; return MMB_OK; }

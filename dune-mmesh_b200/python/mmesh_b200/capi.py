@@ -20,7 +20,7 @@ EXPORTS = [
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
     "mmb_step_host_begin", "mmb_step_host_marks", "mmb_step_host_finish", "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
-    "mmb_component_numbers", "mmb_host_register", "mmb_host_unregister", "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
+    "mmb_component_numbers", "mmb_host_register", "mmb_host_unregister", "mmb_comm_unique_id", "mmb_comm_init", "mmb_comm_destroy", "mmb_halo_counts", "mmb_adapt_step_sharded", "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
 
@@ -375,6 +375,41 @@ class Context:
         ptr, nbytes = C.c_void_p(), C.c_int64()
         self._ck(lib().mmb_device_buffer(self._h, C.c_int(which), C.byref(ptr), C.byref(nbytes)))
         return ptr.value, nbytes.value
+
+    # ---- collectives inside the library (NCCL) ----
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        rc = lib().mmb_comm_unique_id(buf)
+        if rc != MMB_OK:
+            raise MMeshError(rc, "mmb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, world, rank, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(lib().mmb_comm_init(self._h, C.c_int(world), C.c_int(rank), buf))
+
+    def halo_counts(self, send_counts, recv_counts):
+        sc, rc = np.ascontiguousarray(send_counts, np.int64), np.ascontiguousarray(recv_counts, np.int64)
+        self._ck(lib().mmb_halo_counts(self._h, _p(sc), _p(rc)))
+
+    def adapt_step_sharded(self, shifts=None, ncomp=0, want_result=True):
+        s = _f64(shifts)
+        res = StepResult() if want_result else None
+        self._ck(lib().mmb_adapt_step_sharded(self._h, _p(s), C.c_int(ncomp), C.byref(res) if want_result else None))
+        return res
+
+    def download_fields(self, ncomp=0):
+        """resident per-cell / per-edge fields of the last step (synchronises)"""
+        out = dict(marks=np.empty(self.nc, np.int8), longest=np.empty(self.nc, np.uint8), valid_fp=np.empty(self.nc, np.uint8),
+                   orient_sign=np.empty(self.nc, np.int8), edge_flags=np.empty(self.ne, np.uint8),
+                   dofs_new=np.empty(self.nc * ncomp, np.float64) if ncomp else None)
+        self._ck(lib().mmb_download_fields(self._h, C.c_int(ncomp), _p(out["dofs_new"]), _p(out["marks"]), _p(out["longest"]), _p(out["valid_fp"]),
+                                           _p(out["orient_sign"]), _p(out["edge_flags"]) if self.ne else None))
+        self._ck(lib().mmb_synchronize(self._h))
+        if ncomp > 1:
+            out["dofs_new"] = out["dofs_new"].reshape(self.nc, ncomp)
+        return out
 
     def step_phase_distance(self):
         self._ck(lib().mmb_step_phase_distance(self._h))

@@ -169,10 +169,11 @@ def trace_curve(curve_xy, hx, hy, nx, ny, closed):
 
 
 def lattice2d(nx, ny, Lx=1.0, Ly=1.0, jitter=0.2, seed=1, curves=(), hilbert=True, perturb=0.0,
-              rotate_tds=True, flat_patch=0):
+              rotate_tds=True, flat_patch=0, flat_patch_perturb=0.0):
     """(nx x ny) quads, 2 triangles each.  `curves` = list of (points[M,2], closed) interface polylines.
     flat_patch = P > 0: the P x P lattice vertices in the lower-left corner keep their exact lattice positions (all quads
-    there are cocircular, all rows collinear: the exact-predicate fallback has work to do, like config 4)."""
+    there are cocircular, all rows collinear: the exact-predicate fallback has work to do, like config 4); with
+    flat_patch_perturb = e > 0 every coordinate of the patch is moved by U(-e, e), so that signs are decided at the last bit."""
     m = Mesh2D()
     hx, hy = Lx / nx, Ly / ny
     m.h = min(hx, hy)
@@ -207,6 +208,10 @@ def lattice2d(nx, ny, Lx=1.0, Ly=1.0, jitter=0.2, seed=1, curves=(), hilbert=Tru
             free &= ~((I < flat_patch) & (J < flat_patch))
         x = x + np.where(free, (2.0 * uniform01(seed, lid, 0) - 1.0) * (jitter * hx), 0.0)
         y = y + np.where(free, (2.0 * uniform01(seed, lid, 1) - 1.0) * (jitter * hy), 0.0)
+    if flat_patch > 0 and flat_patch_perturb > 0:
+        inp = (I < flat_patch) & (J < flat_patch) & ~boundary
+        x = x + np.where(inp, (2.0 * uniform01(seed, lid, 4) - 1.0) * flat_patch_perturb, 0.0)
+        y = y + np.where(inp, (2.0 * uniform01(seed, lid, 5) - 1.0) * flat_patch_perturb, 0.0)
     if perturb > 0:                                          # config 4: every coordinate +- perturb
         x = x + (2.0 * uniform01(seed, lid, 2) - 1.0) * perturb
         y = y + (2.0 * uniform01(seed, lid, 3) - 1.0) * perturb
@@ -279,11 +284,11 @@ def config2(n=708, seed=2):
     return lattice2d(n, n, 1.0, 1.0, jitter=0.2, seed=seed, curves=[(circ, True)])
 
 
-def config3(nx=4096, ny=2048, seed=3, flat_patch=0):
+def config3(nx=4096, ny=2048, seed=3, flat_patch=0, flat_patch_perturb=0.0):
     """16.8M triangles on [0,2]x[0,1], Hilbert-sorted, 4 sinusoidal interface polylines."""
     xs = np.linspace(0.0, 2.0, 16 * nx + 1)
     curves = [(np.stack([xs, 0.2 * k + 0.05 * np.sin(2 * np.pi * xs)], 1), False) for k in (1, 2, 3, 4)]
-    return lattice2d(nx, ny, 2.0, 1.0, jitter=0.2, seed=seed, curves=curves, flat_patch=flat_patch)
+    return lattice2d(nx, ny, 2.0, 1.0, jitter=0.2, seed=seed, curves=curves, flat_patch=flat_patch, flat_patch_perturb=flat_patch_perturb)
 
 
 def config4(n=1024, perturb=1e-15, seed=4):

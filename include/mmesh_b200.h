@@ -242,6 +242,29 @@ int mmb_step_phase_rest(mmb_context* ctx, int ncomp);     /* mark -> validate ->
    distance: run it while the MAX all-reduce is in flight), 2 marks, 3 move + legality + reduce vector, 0 = all */
 int mmb_step_phase(mmb_context* ctx, int which, int ncomp);
 
+/* ---- the sharded step with its collectives INSIDE the library (NCCL over NVLink / NVSwitch) ----------------------------------
+   Replaces the reference's raw MPI point-to-point layer for this path (dune/mmesh/misc/communication.hh:83-127,
+   partitionhelper.hh:175-236).  One context per rank / GPU.  libnccl.so.2 is loaded at run time (the library does not link
+   against it): failures of the load or of any NCCL call return MMB_ERR_NCCL with the NCCL message in mmb_last_error.
+     mmb_comm_unique_id   ncclGetUniqueId on one rank; the caller distributes the 128 bytes (MPI, a file, torch.distributed)
+     mmb_comm_init        ncclCommInitRank on the context's device; from then on the context is one shard of `world`
+     mmb_halo_counts      per-peer sizes of the halo lists given to mmb_halo_setup (send_counts[p] vertices go to rank p,
+                          recv_counts[p] arrive from it, in the order of send_idx / recv_idx)
+     mmb_adapt_step_sharded  the whole adapt step of mmb_adapt_step on this shard, in the reference's order, with
+         halo exchange of the shifts (grouped ncclSend/ncclRecv) overlapped with Distance::update,
+         all-reduce MAX of Distance::maximum() overlapped with trial validity + projection,
+         all-reduce SUM of n_invalid (the device-side gate of moveVertices, identical on every rank),
+         one all-reduce SUM of the step's additive scalars (counts < 2^53 and the mass as doubles);
+       res (may be NULL) receives the GLOBAL scalars on every rank.  shifts_host = this shard's local vertices (owned entries
+       are used, halo entries are overwritten by the exchange) or NULL for the resident shifts.  The kernels and collectives
+       of a step are captured once into a CUDA graph and replayed (MMB_GRAPH=0 disables that); no host synchronisation
+       happens when res == NULL. */
+int mmb_comm_unique_id(uint8_t id_out[128]);
+int mmb_comm_init(mmb_context* ctx, int world, int rank, const uint8_t id[128]);
+int mmb_comm_destroy(mmb_context* ctx);
+int mmb_halo_counts(mmb_context* ctx, const int64_t* send_counts, const int64_t* recv_counts);
+int mmb_adapt_step_sharded(mmb_context* ctx, const double* shifts_host, int ncomp, mmb_step_result* res);
+
 /* ---- 3-D extras -------------------------------------------------------------------------------------- */
 /* P0 interface-coupled transfer (dune/python/mmesh/pyskeletontrace.hh:42-64,133-160):
    trace_in[f] = u[inside(f)], trace_out[f] = u[outside(f)], skeleton[f] = u_gamma[f]. */

@@ -22,7 +22,9 @@ minH, maxH, factor = multigpu.global_indicator_params(m)
 sh = partition.make_shard(m, world, rank, new_off, new_cell, old_xy, old_idx)
 ctx = capi.Context(2, lr, stream.cuda_stream)
 sm = multigpu.ShardedMesh(torch, dist, ctx, sh)
-prm = ctx.get_params(); prm.minH, prm.maxH, prm.factor = minH, maxH, factor; prm.drop_area = 1e-12; ctx.set_params(prm)
+prm = ctx.get_params(); prm.minH, prm.maxH, prm.factor = minH, maxH, factor; prm.drop_area = 1e-12
+prm.move_policy = 1          # the torch-driven phases below have no all-reduce of the move gate: always move
+ctx.set_params(prm)
 ctx.upload_pairs(sh.new_off, sh.new_cell, sh.old_xy, sh.old_idx)
 ctx.project(3, dofs[sh.lcells], download=False)
 sl = s[sh.lverts].copy(); sl[~sh.owned_vertex] = 0.0
@@ -77,7 +79,7 @@ if rank == 0:
     ref.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
     p2 = ref.indicator_init()
     assert (p2.minH, p2.maxH, p2.factor) == (minH, maxH, factor), ((p2.minH, p2.maxH, p2.factor), (minH, maxH, factor))
-    p2.drop_area = 1e-12; ref.set_params(p2)
+    p2.drop_area = 1e-12; p2.move_policy = 1; ref.set_params(p2)
     ref.upload_pairs(new_off, new_cell, old_xy, old_idx)
     ref.project(3, dofs, download=False)
     r = ref.adapt_step(s, 3).asdict()
@@ -89,7 +91,59 @@ if rank == 0:
             ok = False; print("MISMATCH", k, got[k], r[k])
     if hflag.item() != 1:
         ok = False; print("host-buffer sharded step differs from the resident one")
+# ---- the step with its collectives INSIDE the library (mmb_adapt_step_sharded, NCCL C API, CUDA graph from step 2 on) ----
+sm.init_library_comm()
+lib_ok = True
+for policy in (0, 1):
+    prm.move_policy = policy; ctx.set_params(prm)
+    fields, scal = [], []
+    for rep in range(3):                                     # rep 0 eager, rep 1 captures the graph, rep 2 replays it
+        ctx.upload_coords(sh.xy)
+        ctx.project(3, dofs[sh.lcells], download=False)
+        ctx.upload_shifts(sl)
+        scal.append(sm.step_library(3, want_result=True).asdict())
+        f = ctx.download_fields(3)
+        f["xy"] = ctx.download_coords()
+        fields.append(f)
+    for rep in (1, 2):                                       # eager, captured and replayed steps agree bit for bit
+        for k in fields[0]:
+            if not np.array_equal(fields[rep][k], fields[0][k]):
+                lib_ok = False; print("rank", rank, "policy", policy, "GRAPH/EAGER MISMATCH", k)
+        if scal[rep] != scal[0]:
+            lib_ok = False; print("rank", rank, "policy", policy, "GRAPH/EAGER SCALARS", scal[rep], scal[0])
+    np.savez("/tmp/mmb_check_%d_%d.npz" % (policy, rank), **{k: (v[own] if k in ("marks", "longest", "valid_fp", "orient_sign", "dofs_new") else v) for k, v in fields[2].items()},
+             lverts=sh.lverts, owned=sh.owned_vertex)
+    dist.barrier()
+    if rank == 0:
+        p2.move_policy = policy; ref.set_params(p2)
+        ref.upload_coords(m.xy); ref.project(3, dofs, download=False)
+        r = ref.adapt_step(s, 3).asdict()
+        rf = ref.download_fields(3); rxy = ref.download_coords()
+        parts = [np.load("/tmp/mmb_check_%d_%d.npz" % (policy, q)) for q in range(world)]
+        for k in ("marks", "longest", "valid_fp", "orient_sign", "dofs_new", "edge_flags"):
+            g = np.concatenate([q[k] for q in parts])
+            if not np.array_equal(g, rf[k]):
+                lib_ok = False; print("policy", policy, "LIBRARY STEP FIELD MISMATCH", k)
+        for q in parts:                                      # coordinates of every local vertex (owned and halo) equal the global ones
+            if not np.array_equal(q["xy"], rxy[q["lverts"]]):
+                lib_ok = False; print("policy", policy, "LIBRARY STEP COORDINATES MISMATCH")
+        for k in ("n_invalid", "n_orient_nonpos", "n_illegal", "n_refine", "n_coarsen", "n_pieces", "max_dist", "moved"):
+            if scal[2][k] != r[k]:
+                lib_ok = False; print("policy", policy, "LIBRARY STEP SCALAR MISMATCH", k, scal[2][k], r[k])
+        for k in ("mass_new", "covered_area"):
+            if abs(scal[2][k] - r[k]) > 1e-13 * abs(r[k]):
+                lib_ok = False; print("policy", policy, "LIBRARY STEP SCALAR MISMATCH", k, scal[2][k], r[k])
+        if policy == 0 and not (r["n_invalid"] > 0 and r["moved"] == 0):
+            lib_ok = False; print("policy 0 case does not exercise the withheld move", r)
+        print("library step policy", policy, "moved", scal[2]["moved"], "OK" if lib_ok else "FAILED")
+    dist.barrier()
+lflag = torch.tensor([1 if lib_ok else 0], device="cuda")
+dist.all_reduce(lflag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    if lflag.item() != 1:
+        ok = False
     print("mgpu_check world", world, "cells", m.nc, "OK" if ok else "FAILED", got)
+    ref.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 ctx.close()
