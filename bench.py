@@ -117,7 +117,7 @@ def make_workload(args):
     from mmesh_b200 import synth
     t0 = time.time()
     if args.config == 3:
-        m = synth.config3(nx=args.nx, ny=args.ny, flat_patch=FLAT_PATCH, flat_patch_perturb=1e-15)
+        m = synth.config3(nx=args.nx, ny=args.ny, flat_patch=FLAT_PATCH, flat_patch_perturb=2e-17)
         name = "config3: 2-D %dx%d lattice, %d triangles, Hilbert-sorted, 4 sinusoidal interface polylines" % (args.nx, args.ny, 2 * args.nx * args.ny)
     elif args.config == 2:
         m = synth.config2(n=args.nx)
@@ -444,7 +444,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": w["name"], "cells": nc, "vertices": nv, "edges": ne, "interface_segments": ns,
                        "projection": "DG-P1, self+face-neighbour pairs (phi=1, %d pairs), scale-aware clip (clip_translate=1, drop_area=0)" % npairs,
-                       "indicator": "RatioIndicator::init, maxH *= 0.5", "exact_patch": "%dx%d unshifted lattice vertices, exact positions +- 1e-15 (cocircular quads decided at the last bit)" % (FLAT_PATCH, FLAT_PATCH),
+                       "indicator": "RatioIndicator::init, maxH *= 0.5", "exact_patch": "%dx%d unshifted lattice vertices, exact positions +- 2e-17, a few ulps (cocircular quads decided at the last bit)" % (FLAT_PATCH, FLAT_PATCH),
                        "move_policy": "1 (always move; stress: check.n_invalid cells invert under the 0.3 h shifts)",
                        "l2_policy": "inputs larger than L2 (%.2f GB touched per step)" % (sum(k["algorithmic_bytes"] or 0 for k in kern if k["share"]) / 1e9),
                        "step": "distance+mark -> trial validate -> project -> move -> legality (+ shifts *= -1)"},

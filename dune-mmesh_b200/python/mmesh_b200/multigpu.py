@@ -195,11 +195,10 @@ def bench_main(args, world, rank, local_rank, METRIC, UNIT, algorithmic_bytes, C
         step()
     torch.cuda.synchronize()
     res_check = sm.step_library(ncomp, want_result=True).asdict()      # GLOBAL scalars; same phase as the single-GPU `check`
-    ctx.scale_shifts(-1.0)
-    step()
     # ---- field-level parity with a single-GPU run of the same step (outside the timed region) ----
     own = slice(shard.own_lo, shard.own_hi)
     f = ctx.download_fields(ncomp)                           # fields of the step just run (shifts = +s at the original positions)
+    ctx.scale_shifts(-1.0)
     tmp = os.environ.get("MMB_TMP", "/tmp")
     np.savez(os.path.join(tmp, "mmb_fields_%d.npz" % rank), marks=f["marks"][own], longest=f["longest"][own], valid_fp=f["valid_fp"][own],
              orient_sign=f["orient_sign"][own], edge_flags=f["edge_flags"], dofs_new=f["dofs_new"][own])

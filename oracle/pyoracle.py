@@ -178,6 +178,16 @@ def distance_3d(xyz, tris):
     return d
 
 
+def distance_3d_subset(xyz, vidx, tris):
+    """brute-force 3-D estimate (distance.hh:157-173) for the listed vertices only"""
+    xyz, tris = _f64(xyz), _i32(tris)
+    vidx = np.asarray(vidx, np.int64)
+    sub = np.ascontiguousarray(np.concatenate([xyz[vidx], xyz]))      # the queried points first, facet indices shifted behind them
+    d = np.empty(vidx.shape[0], np.float64)
+    lib().orc_distance_3d(_p(sub), C.c_int64(vidx.shape[0]), _p(_i32(tris + vidx.shape[0])), C.c_int64(tris.shape[0]), _p(d))
+    return d
+
+
 def distance_max(dist):
     dist = _f64(dist)
     return lib().orc_distance_max(_p(dist), C.c_int64(dist.size))
