@@ -24,7 +24,7 @@ struct Counters {
   unsigned long long max_dist_bits;               // non-negative double compared as integer
   unsigned long long minmax_bits[4];              // indicator init: iface min, iface max, bulk min, bulk max
   double mass_new, covered_area;
-  unsigned long long pad_[2];
+  unsigned long long pad_[2];                     // pad_[0]: total of the last compaction scan; pad_[1]: predicates outside the exact stage's exponent range
   unsigned long long dbg[8];                      // development counters (MMB_DEV_VARIANTS builds only)
   unsigned long long n_invalid_global;            // what gates the fused step's move: n_invalid of ALL ranks (a sharded caller
 };                                                // all-reduces it; single GPU: a copy of n_invalid)
@@ -207,6 +207,7 @@ k_exact_orient2d(const double2* __restrict__ xy, const double2* __restrict__ sh,
     }
     int s = orient2d_interval(P.x, P.y, Q.x, Q.y, R.x, R.y);
     if (s == SIGN_UNKNOWN) { s = orient2d_exact(P.x, P.y, Q.x, Q.y, R.x, R.y); nexact++; }
+    if (s == SIGN_DOMAIN) { s = 0; atomicAdd(&cnt->pad_[1], 1ull); }
     orient[c] = (int8_t)s;
     nnonpos += (s <= 0 && c >= own_lo && c < own_hi);
   }
@@ -285,6 +286,7 @@ k_exact_incircle(const double2* __restrict__ xy, const double2* __restrict__ sh,
     }
     int s = incircle_interval(A.x, A.y, B.x, B.y, C.x, C.y, D.x, D.y);
     if (s == SIGN_UNKNOWN) { s = incircle_exact(A.x, A.y, B.x, B.y, C.x, C.y, D.x, D.y); nexact++; }
+    if (s == SIGN_DOMAIN) { s = 0; atomicAdd(&cnt->pad_[1], 1ull); }
     flag[e] = (uint8_t)(s > 0 ? 0 : 1);
     nill += (s > 0);
   }
@@ -329,6 +331,7 @@ k_pred_exact(int which, const double* __restrict__ pts, const int32_t* __restric
       s = orient3d_interval(p, p + 3, p + 6, p + 9);
       if (s == SIGN_UNKNOWN) { s = orient3d_exact(p, p + 3, p + 6, p + 9); nexact++; }
     }
+    if (s == SIGN_DOMAIN) { s = 0; atomicAdd(&cnt->pad_[1], 1ull); }
     sign[i] = (int8_t)s;
   }
   block_count_add<128>(nexact, 0u, &cnt->n_exact_orient, &cnt->n_exact_orient);
@@ -1162,6 +1165,7 @@ k_exact_orient3d(const double* __restrict__ x, const double* __restrict__ sh, co
     load3(x, sh, cv2[c], SHIFT, p[2]); load3(x, sh, cv3[c], SHIFT, p[3]);
     int s = orient3d_interval(p[0], p[1], p[2], p[3]);
     if (s == SIGN_UNKNOWN) { s = orient3d_exact(p[0], p[1], p[2], p[3]); nexact++; }
+    if (s == SIGN_DOMAIN) { s = 0; atomicAdd(&cnt->pad_[1], 1ull); }
     orient[c] = (int8_t)s;
     nnonpos += (s <= 0);
   }

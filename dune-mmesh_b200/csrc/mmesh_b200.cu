@@ -139,6 +139,17 @@ static int fetch_counters(mmb_context* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
   return MMB_OK;
 }
+// predicates whose inputs exceed the exponent range of the exact stage (predicates.cuh: pred_rescale) were counted on the
+// device; their signs were set to 0 and must not be trusted
+static int check_predicate_domain(mmb_context* ctx) {
+  if (ctx->h_counters->pad_[1] != 0) {
+    ctx->err = "exact predicate: " + std::to_string((unsigned long long)ctx->h_counters->pad_[1]) +
+               " input(s) outside the exponent range of the exact stage (largest / smallest nonzero magnitude > 2^480 / 2^300 / 2^212 "
+               "for orient2d / orient3d / in-circle, or non-finite coordinates); CGAL's rational fallback has no such limit";
+    return MMB_ERR_CAPACITY;
+  }
+  return MMB_OK;
+}
 #define TRY(expr) do { int rc_ = (expr); if (rc_ != MMB_OK) return rc_; } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -490,6 +501,7 @@ int mmb_trial_move_validate(mmb_context* ctx, const double* shifts_host, uint8_t
   CK(cudaMemsetAsync(&ctx->counters.p->n_invalid, 0, 2 * sizeof(unsigned long long), ctx->stream));
   CK(cudaMemsetAsync(&ctx->counters.p->wl_orient, 0, sizeof(unsigned long long), ctx->stream));
   CK(cudaMemsetAsync(&ctx->counters.p->n_exact_orient, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->pad_[1], 0, sizeof(unsigned long long), ctx->stream));
   TRY(do_validate(ctx, true));
   if (valid_fp_host) CK(cudaMemcpyAsync(valid_fp_host, ctx->valid_fp.p, (size_t)ctx->nc, cudaMemcpyDeviceToHost, ctx->stream));
   if (orient_sign_host) CK(cudaMemcpyAsync(orient_sign_host, ctx->orient.p, (size_t)ctx->nc, cudaMemcpyDeviceToHost, ctx->stream));
@@ -497,6 +509,7 @@ int mmb_trial_move_validate(mmb_context* ctx, const double* shifts_host, uint8_t
   if (n_invalid || valid_fp_host || orient_sign_host || ctx->dim == 3) {
     TRY(fetch_counters(ctx));
     if (n_invalid) *n_invalid = (int64_t)ctx->h_counters->n_invalid;
+    TRY(check_predicate_domain(ctx));
     if (ctx->dim == 3 && ctx->h_counters->n_invalid > 0) {
       ctx->err = "Vertices could not be moved, because the removal of vertices is not supported in 3D!";
       return MMB_ERR_INVALID_CELL_3D;
@@ -560,10 +573,11 @@ int mmb_legality(mmb_context* ctx, uint8_t* flags_host, int64_t* n_illegal) {
   CK(cudaMemsetAsync(&ctx->counters.p->n_illegal, 0, sizeof(unsigned long long), ctx->stream));
   CK(cudaMemsetAsync(&ctx->counters.p->wl_incircle, 0, sizeof(unsigned long long), ctx->stream));
   CK(cudaMemsetAsync(&ctx->counters.p->n_exact_incircle, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->pad_[1], 0, sizeof(unsigned long long), ctx->stream));
   TRY(do_legality(ctx));
   if (flags_host && ctx->ne) CK(cudaMemcpyAsync(flags_host, ctx->edge_flag.p, (size_t)ctx->ne, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaGetLastError());
-  if (flags_host || n_illegal) { TRY(fetch_counters(ctx)); if (n_illegal) *n_illegal = (int64_t)ctx->h_counters->n_illegal; }
+  if (flags_host || n_illegal) { TRY(fetch_counters(ctx)); if (n_illegal) *n_illegal = (int64_t)ctx->h_counters->n_illegal; TRY(check_predicate_domain(ctx)); }
   return MMB_OK;
 }
 
@@ -1130,6 +1144,7 @@ static int step_result(mmb_context* ctx, mmb_step_result* res) {
     res->mass_new = c.mass_new; res->covered_area = c.covered_area;
     const bool withheld = ctx->prm.move_policy == 0 && c.n_invalid_global > 0;
     res->moved = withheld ? 0 : 1;
+    TRY(check_predicate_domain(ctx));
     if (ctx->dim == 3 && c.n_invalid > 0) {
       ctx->err = "Vertices could not be moved, because the removal of vertices is not supported in 3D!";
       return MMB_ERR_INVALID_CELL_3D;
@@ -1333,13 +1348,14 @@ int mmb_predicate_batch(mmb_context* ctx, int which, int64_t n, const double* pt
   CK(cudaMemcpyAsync(ctx->pred_pts.p, pts_host, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(&ctx->counters.p->wl_orient, 0, sizeof(unsigned long long), ctx->stream));
   CK(cudaMemsetAsync(&ctx->counters.p->n_exact_orient, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->counters.p->pad_[1], 0, sizeof(unsigned long long), ctx->stream));
   LAUNCH("pred_filter", k_pred_filter, grid_for(n, 256), 256, which, ctx->pred_pts.p, n, ctx->pred_sign.p, ctx->wl.p, ctx->counters.p);
   LAUNCH("pred_exact", k_pred_exact, ctx->num_sms * 4, 128, which, ctx->pred_pts.p, ctx->wl.p, ctx->pred_sign.p, ctx->counters.p);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(sign_host, ctx->pred_sign.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   TRY(fetch_counters(ctx));
   if (n_exact) *n_exact = (int64_t)ctx->h_counters->n_exact_orient;
-  return MMB_OK;
+  return check_predicate_domain(ctx);
 }
 
 // asynchronous field transfers on the context's stream (host buffers should be pinned); mmb_synchronize completes them

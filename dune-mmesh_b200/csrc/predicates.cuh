@@ -36,6 +36,7 @@ MMB_HD double det3(double a00, double a01, double a02, double a10, double a11, d
 }
 
 constexpr int SIGN_UNKNOWN = 2;
+constexpr int SIGN_DOMAIN = 3;     // exact stage: the input's exponent range exceeds what double expansions can hold (see pred_rescale)
 
 // CGAL/internal/Static_filters/Orientation_2.h:54-91.  Also returns the inexact determinant (== 2*area of
 // CGAL/Cartesian/function_objects.h:918-926, same operations) so validity and the filter share the arithmetic.
@@ -240,8 +241,37 @@ MMB_HD int ex_sign(int n, const double* e) {
   return (top > 0.0) - (top < 0.0);
 }
 
+// Exponent range of the exact stage.  CGAL's exact fallback computes with rationals and has no range limit; expansions of
+// doubles are exact only while no product over- or underflows.  The predicates are homogeneous polynomials of degree `deg`
+// in the coordinates, so multiplying every coordinate by one power of two (exact) leaves the sign alone: the inputs are
+// rescaled so that the largest magnitude lies in [1/2, 1) -- no overflow for any absolute scale.  Every intermediate
+// value is then an integer multiple of beta^k, beta = (smallest nonzero |coordinate|) * 2^-52 (its last bit), k <= deg;
+// all of them, and the error terms of two_prod, are representable iff beta^deg >= 2^-1074.  That bounds the admissible
+// RATIO largest / smallest nonzero magnitude inside one predicate: 2^480 (orient2d), 2^300 (orient3d), 2^212 (in-circle).
+// Inputs beyond it, or non-finite ones, yield SIGN_DOMAIN: the caller counts them and the C-ABI reports
+// MMB_ERR_CAPACITY instead of returning a sign that might be wrong.
+MMB_HD bool pred_rescale(double* c, int n, int max_ratio_log2) {
+  double M = 0.0, m = INFINITY;
+  for (int i = 0; i < n; ++i) {
+    const double a = fabs(c[i]);
+    if (!(a <= 1.79769313486231570e308)) return false;      // inf / NaN
+    if (a > 0.0) { M = a > M ? a : M; m = a < m ? a : m; }
+  }
+  if (M == 0.0) return true;
+  int eM, em;
+  frexp(M, &eM); frexp(m, &em);
+  if (eM - em > max_ratio_log2) return false;
+  for (int i = 0; i < n; ++i) c[i] = ldexp(c[i], -eM);      // exact: the smallest magnitude stays far above the denormals
+  return true;
+}
+
 // exact orientationC2 (CGAL/predicates/kernel_ftC2.h:401-406)
 MMB_HDN int orient2d_exact(double px, double py, double qx, double qy, double rx, double ry) {
+  {
+    double c[6] = { px, py, qx, qy, rx, ry };
+    if (!pred_rescale(c, 6, 480)) return SIGN_DOMAIN;
+    px = c[0]; py = c[1]; qx = c[2]; qy = c[3]; rx = c[4]; ry = c[5];
+  }
   double a[2], b[2], c[2], d[2], tmp[4], acc[16];
   const int na = ex_diff(qx, px, a), nb = ex_diff(qy, py, b), nc = ex_diff(rx, px, c), nd = ex_diff(ry, py, d);
   int n = 1; acc[0] = 0.0;
@@ -252,6 +282,11 @@ MMB_HDN int orient2d_exact(double px, double py, double qx, double qy, double rx
 
 // exact side_of_oriented_circleC2 (CGAL/predicates/kernel_ftC2.h:477-499, 2x2 reduced form)
 MMB_HDN int incircle_exact(double px, double py, double qx, double qy, double rx, double ry, double tx, double ty) {
+  {
+    double c[8] = { px, py, qx, qy, rx, ry, tx, ty };
+    if (!pred_rescale(c, 8, 212)) return SIGN_DOMAIN;
+    px = c[0]; py = c[1]; qx = c[2]; qy = c[3]; rx = c[4]; ry = c[5]; tx = c[6]; ty = c[7];
+  }
   double qpx[2], qpy[2], rpx[2], rpy[2], tpx[2], tpy[2], tqx[2], tqy[2], rqx[2], rqy[2];
   const int nqpx = ex_diff(qx, px, qpx), nqpy = ex_diff(qy, py, qpy), nrpx = ex_diff(rx, px, rpx),
             nrpy = ex_diff(ry, py, rpy), ntpx = ex_diff(tx, px, tpx), ntpy = ex_diff(ty, py, tpy),
@@ -276,7 +311,11 @@ MMB_HDN int incircle_exact(double px, double py, double qx, double qy, double rx
 }
 
 // exact orientationC3 (CGAL/predicates/kernel_ftC3.h:114-122; determinant.h:37-52)
-MMB_HDN int orient3d_exact(const double* p, const double* q, const double* r, const double* s) {
+MMB_HDN int orient3d_exact(const double* p_in, const double* q_in, const double* r_in, const double* s_in) {
+  double c12[12];
+  for (int j = 0; j < 3; ++j) { c12[j] = p_in[j]; c12[3 + j] = q_in[j]; c12[6 + j] = r_in[j]; c12[9 + j] = s_in[j]; }
+  if (!pred_rescale(c12, 12, 300)) return SIGN_DOMAIN;
+  const double *p = c12, *q = c12 + 3, *r = c12 + 6, *s = c12 + 9;
   double a[3][3][2]; int na[3][3];
   for (int j = 0; j < 3; ++j) {
     na[0][j] = ex_diff(q[j], p[j], a[0][j]);

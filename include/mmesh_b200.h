@@ -34,7 +34,10 @@ typedef enum mmb_status {
   MMB_ERR_CUDA = 2,
   MMB_ERR_NCCL = 3,
   MMB_ERR_INVALID_CELL_3D = 4, /* the DUNE_THROW(GridError) of mmesh.hh:1104-1107 */
-  MMB_ERR_CAPACITY = 5,
+  MMB_ERR_CAPACITY = 5,        /* an index space exceeded, or an exact predicate whose input lies outside the exponent range the
+                                  expansion arithmetic can hold (ratio largest / smallest nonzero magnitude > 2^212 for in-circle,
+                                  2^300 orient3d, 2^480 orient2d, or non-finite coordinates): the outputs are filled, the affected
+                                  signs are 0 and must not be trusted.  Any absolute scale is fine (inputs are rescaled exactly). */
   MMB_ERR_STATE = 6,           /* e.g. mark before distance update, project before upload */
   MMB_MOVE_WITHHELD = 7        /* not an error: the step ran, but ensureVertexMovement found cells that would invert
                                   (n_invalid > 0), so moveVertices was NOT applied -- the caller removes the vertices

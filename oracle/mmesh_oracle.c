@@ -97,7 +97,28 @@ static void ex_det2(const expn* a, const expn* b, const expn* c, const expn* d, 
 
 /* CGAL/predicates/kernel_ftC2.h:401-406 orientationC2 = sign_of_determinant(qx-px, qy-py, rx-px, ry-py),
    evaluated over the reals (Filtered_predicate.h:86-106 falls back to an exact number type). */
-int orc_orient2d(const double* p, const double* q, const double* r) {
+/* Exponent range of the expansion arithmetic (the product's predicates.cuh states the same rule): the predicates are
+   homogeneous, so all coordinates are multiplied by one power of two (exact) until the largest magnitude is in [1/2, 1);
+   beyond a ratio largest / smallest nonzero magnitude of 2^max_ratio_log2, or for non-finite input, the result is 3
+   ("outside the exact stage's range") instead of a sign.  CGAL's rational arithmetic has no such limit. */
+static int orc_rescale(double* c, int n, int max_ratio_log2) {
+  double M = 0.0, m = INFINITY;
+  for (int i = 0; i < n; ++i) {
+    double a = fabs(c[i]);
+    if (!(a <= 1.79769313486231570e308)) return 0;
+    if (a > 0.0) { if (a > M) M = a; if (a < m) m = a; }
+  }
+  if (M == 0.0) return 1;
+  int eM, em;
+  frexp(M, &eM); frexp(m, &em);
+  if (eM - em > max_ratio_log2) return 0;
+  for (int i = 0; i < n; ++i) c[i] = ldexp(c[i], -eM);
+  return 1;
+}
+int orc_orient2d(const double* p_, const double* q_, const double* r_) {
+  double cc[6] = { p_[0], p_[1], q_[0], q_[1], r_[0], r_[1] };
+  if (!orc_rescale(cc, 6, 480)) return 3;
+  const double *p = cc, *q = cc + 2, *r = cc + 4;
   expn *a = malloc(sizeof(expn)), *b = malloc(sizeof(expn)), *c = malloc(sizeof(expn)),
        *d = malloc(sizeof(expn)), *h = malloc(sizeof(expn));
   ex_set2(a, q[0], p[0]); ex_set2(b, q[1], p[1]);
@@ -110,7 +131,11 @@ int orc_orient2d(const double* p, const double* q, const double* r) {
 
 /* CGAL/predicates/kernel_ftC3.h:114-122 orientationC3 (transposed layout, same determinant),
    CGAL/determinant.h:37-52 3x3 formula. */
-int orc_orient3d(const double* p, const double* q, const double* r, const double* s) {
+int orc_orient3d(const double* p_, const double* q_, const double* r_, const double* s_) {
+  double cc[12];
+  for (int j = 0; j < 3; ++j) { cc[j] = p_[j]; cc[3 + j] = q_[j]; cc[6 + j] = r_[j]; cc[9 + j] = s_[j]; }
+  if (!orc_rescale(cc, 12, 300)) return 3;
+  const double *p = cc, *q = cc + 3, *r = cc + 6, *s = cc + 9;
   expn* A[3][3]; expn *m01 = malloc(sizeof(expn)), *m02 = malloc(sizeof(expn)), *m12 = malloc(sizeof(expn));
   expn *t = malloc(sizeof(expn)), *u = malloc(sizeof(expn)), *acc = malloc(sizeof(expn));
   const double* rows[3] = { q, r, s };
@@ -130,7 +155,10 @@ int orc_orient3d(const double* p, const double* q, const double* r, const double
 }
 
 /* CGAL/predicates/kernel_ftC2.h:477-499 side_of_oriented_circleC2 (2x2 reduced form). */
-int orc_incircle(const double* p, const double* q, const double* r, const double* t) {
+int orc_incircle(const double* p_, const double* q_, const double* r_, const double* t_) {
+  double cc[8] = { p_[0], p_[1], q_[0], q_[1], r_[0], r_[1], t_[0], t_[1] };
+  if (!orc_rescale(cc, 8, 212)) return 3;
+  const double *p = cc, *q = cc + 2, *r = cc + 4, *t = cc + 6;
   expn* v[10]; for (int i = 0; i < 10; ++i) v[i] = malloc(sizeof(expn));
   expn *a00 = malloc(sizeof(expn)), *a01 = malloc(sizeof(expn)), *a10 = malloc(sizeof(expn)),
        *a11 = malloc(sizeof(expn)), *x = malloc(sizeof(expn)), *y = malloc(sizeof(expn)), *h = malloc(sizeof(expn));

@@ -580,3 +580,27 @@ def test_component_numbers_like_adapt(gpu_ctx_factory, oracle):
     zn, cn, cc = ctx.component_numbers(off, cells, 1)
     rz, rc, rcc = oracle.component_numbers(off, cells, m.nc, 1)
     assert np.array_equal(zn, rz) and np.array_equal(cn, rc) and cc == rcc and len(set(rz.tolist())) < len(rz)
+
+
+def test_predicate_exponent_range(gpu_ctx_factory, oracle):
+    """The exact stage rescales by a power of two: any absolute scale is decided exactly; an exponent RATIO beyond what
+    expansions can hold is reported (MMB_ERR_CAPACITY), never answered with a guessed sign."""
+    from mmesh_b200 import capi
+    ctx = gpu_ctx_factory(2)
+    rng = np.random.default_rng(8)
+    base = rng.integers(0, 8, size=(4000, 4, 2)) / 8.0
+    base[1000:] += rng.uniform(-1e-15, 1e-15, size=(3000, 4, 2))
+    for scale in (1e-290, 1e-150, 1.0, 1e150, 1e290):
+        q = (base * scale).reshape(-1, 8)
+        if scale < 1e-200:
+            q[np.abs(q) < 1e-307] = 0.0                       # keep the inputs normal doubles
+        si, _ = ctx.predicate_batch(1, q)
+        assert np.array_equal(si, oracle.incircle_batch(q))
+        so, _ = ctx.predicate_batch(0, q[:, :6])
+        assert np.array_equal(so, oracle.orient2d_batch(q[:, :6]))
+    bad = np.array([[0.0, 0.0, 1.0, 2.0 ** -230, 2.0, 2.0 ** -229, 1.0, 1.0]])
+    with pytest.raises(capi.MMeshError) as ei:
+        ctx.predicate_batch(1, bad)
+    assert ei.value.status == capi.MMB_ERR_CAPACITY
+    sg, _ = ctx.predicate_batch(0, bad[:, :6])                # the same collinear triple is inside orient2d's range
+    assert sg[0] == 0 == oracle.orient2d_batch(bad[:, :6])[0]
