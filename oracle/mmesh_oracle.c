@@ -1174,3 +1174,99 @@ int64_t orc_component_numbers(int64_t nz, const int64_t* zone_off, const int32_t
   }
   return component_count;
 }
+
+/* mmesh.hh:920-1088 ensureInterfaceMovement (dim == 2), restated on index arrays; see the header for the conventions */
+int orc_ensure_interface_movement_2d(const double* x, int64_t nv, const int32_t* cells, const uint8_t* perm, int64_t nc,
+                                     const uint8_t* vflags, const int32_t* facets, int64_t ns, const int32_t* iverts, int64_t niv,
+                                     const double* ishifts, const int32_t* level, uint8_t* removed_mask, int32_t* removed,
+                                     int64_t* n_removed, int32_t* ins_edge, double* ins_point, int32_t* ins_v0, int64_t* ins_level,
+                                     int32_t* ins_crossing, uint8_t* ins_comp_is_edge, int64_t* n_inserted) {
+  int change = 0;
+  *n_removed = 0; *n_inserted = 0;
+  double* xt = (double*)malloc((size_t)nv * 2 * sizeof(double));
+  double* sh = (double*)malloc((size_t)(niv ? niv : 1) * 2 * sizeof(double));
+  int32_t* ivof = (int32_t*)malloc((size_t)nv * sizeof(int32_t));      /* interface leaf index of a bulk vertex */
+  int32_t* nincident = (int32_t*)calloc((size_t)nv, sizeof(int32_t));
+  memcpy(xt, x, (size_t)nv * 2 * sizeof(double));
+  memcpy(sh, ishifts, (size_t)niv * 2 * sizeof(double));
+  for (int64_t v = 0; v < nv; ++v) ivof[v] = -1;
+  for (int64_t i = 0; i < niv; ++i) ivof[iverts[i]] = (int32_t)i;
+  for (int64_t f = 0; f < 2 * ns; ++f) nincident[facets[f]]++;
+  int rc = 0;
+#define SIGNED_AREA(c) (((xt[2 * cells[3 * (c) + 1]] - xt[2 * cells[3 * (c)]]) * (xt[2 * cells[3 * (c) + 2] + 1] - xt[2 * cells[3 * (c)] + 1]) - \
+                         (xt[2 * cells[3 * (c) + 2]] - xt[2 * cells[3 * (c)]]) * (xt[2 * cells[3 * (c) + 1] + 1] - xt[2 * cells[3 * (c)] + 1])) / 2)
+  for (int64_t c = 0; c < nc && rc == 0; ++c)                           /* :926-930 check if grid is still valid */
+    if (SIGNED_AREA(c) <= 0.0) rc = -1;
+  if (rc == 0) {
+    for (int64_t i = 0; i < niv; ++i) {                                  /* :933 moveInterface(shifts) */
+      xt[2 * iverts[i]] = x[2 * iverts[i]] + sh[2 * i]; xt[2 * iverts[i] + 1] = x[2 * iverts[i] + 1] + sh[2 * i + 1];
+    }
+    static const int EV[3][2] = { { 0, 1 }, { 0, 2 }, { 1, 2 } };         /* DUNE edge numbering of the id-sorted corners */
+    for (int64_t c = 0; c < nc && rc == 0; ++c) {                        /* :935 */
+      if (!(SIGNED_AREA(c) <= 0.0)) continue;
+      int32_t k[3];
+      for (int j = 0; j < 3; ++j) k[j] = cells[3 * c + ((perm[c] >> (2 * j)) & 3)];    /* subEntity<dim>(j): id order */
+      int allInterface = 1;
+      for (int j = 0; j < 3; ++j) {                                      /* :945-962 */
+        const int32_t v = k[j];
+        if (!(vflags[v] & 1)) {
+          if (vflags[v] & 2) continue;                                   /* boundaryFlag(v) == 1 */
+          if (!removed_mask[v]) { removed_mask[v] = 1; removed[(*n_removed)++] = v; change = 1; }
+          allInterface = 0;
+        }
+      }
+      if (!allInterface) continue;
+      int ie = -1;
+      for (int j = 0; j < 3 && rc == 0; ++j) {                           /* :966-980 isInterface(edge) */
+        const int32_t a = k[EV[j][0]], b = k[EV[j][1]];
+        int isif = 0;
+        if ((vflags[a] & 1) && (vflags[b] & 1))
+          for (int64_t f = 0; f < ns && !isif; ++f)
+            isif = (facets[2 * f] == a && facets[2 * f + 1] == b) || (facets[2 * f] == b && facets[2 * f + 1] == a);
+        if (isif) { if (ie >= 0) rc = -2; else ie = j; }
+      }
+      if (rc) break;
+      if (ie < 0) {                                                      /* :983-1006 */
+        int allNonRemovable = 1;
+        for (int j = 0; j < 3; ++j)
+          if (nincident[k[j]] == 2) {                                    /* isRemoveable, longestedgerefinement.hh:160-168 */
+            allNonRemovable = 0;
+            if (!removed_mask[k[j]]) { removed_mask[k[j]] = 1; removed[(*n_removed)++] = k[j]; change = 1; }
+          }
+        if (allNonRemovable) rc = -3;
+        continue;
+      }
+      const int32_t ea = k[EV[ie][0]], eb = k[EV[ie][1]], third = k[3 - EV[ie][0] - EV[ie][1]];
+      int32_t crossing = -1;
+      for (int64_t f = 0; f < ns && rc == 0; ++f)                        /* :1021-1036 incidentInterfaceElements(iThirdVertex) */
+        if (facets[2 * f] == third || facets[2 * f + 1] == third) { if (crossing >= 0) rc = -4; else crossing = (int32_t)f; }
+      if (rc) break;
+      /* :1039-1046: corners through AffineGeometry::corner (c1 = c0 + 1.0 * (v1 - c0)) */
+      const double c0[2] = { xt[2 * ea], xt[2 * ea + 1] };
+      const double c1[2] = { c0[0] + 1.0 * (xt[2 * eb] - c0[0]), c0[1] + 1.0 * (xt[2 * eb + 1] - c0[1]) };
+      const int32_t fa = facets[2 * crossing], fb = facets[2 * crossing + 1];
+      const double e0[2] = { xt[2 * fa], xt[2 * fa + 1] };
+      const double e1[2] = { e0[0] + 1.0 * (xt[2 * fb] - e0[0]), e0[1] + 1.0 * (xt[2 * fb + 1] - e0[1]) };
+      double xi[2];
+      line_isect(c0, c1, e0, e1, xi);                                    /* polygoncutting.hh:100-114 */
+      double dot = 0.0; dot += (c0[0] - xi[0]) * (c1[0] - xi[0]); dot += (c0[1] - xi[1]) * (c1[1] - xi[1]);
+      if (dot > 0.) continue;                                            /* :1049 */
+      const int64_t n = (*n_inserted)++;
+      ins_edge[2 * n] = ea; ins_edge[2 * n + 1] = eb; ins_point[2 * n] = xi[0]; ins_point[2 * n + 1] = xi[1];
+      ins_v0[n] = third; ins_level[n] = (level ? (int64_t)level[third] : 0) + 1; ins_crossing[n] = crossing;
+      {
+        double la = 0.0, lb = 0.0, t;
+        t = c1[0] - c0[0]; la += t * t; t = c1[1] - c0[1]; la += t * t;
+        t = e1[0] - e0[0]; lb += t * t; t = e1[1] - e0[1]; lb += t * t;
+        ins_comp_is_edge[n] = sqrt(la) > sqrt(lb);                       /* :1060-1063 the edge with the larger volume */
+      }
+      change = 1;
+      const int32_t idx = ivof[third];                                   /* :1072-1076 move third vertex back */
+      xt[2 * third] = xt[2 * third] - sh[2 * idx]; xt[2 * third + 1] = xt[2 * third + 1] - sh[2 * idx + 1];
+      sh[2 * idx] = 0.0; sh[2 * idx + 1] = 0.0;
+    }
+  }
+#undef SIGNED_AREA
+  free(xt); free(sh); free(ivof); free(nincident);
+  return rc ? rc : change;
+}

@@ -156,6 +156,20 @@ int orc_num_threads(void);
 void orc_distance_2d_culled_subset(const double* xy, int64_t nv_all, const int32_t* vidx, int64_t nsub, const int32_t* segs,
                                    int64_t ns, double* dist_sub);
 
+/* ---- MMesh::ensureInterfaceMovement, 2-D (dune/mmesh/grid/mmesh.hh:920-1088) ------------------------ */
+/* Statement-by-statement restatement on index arrays.  x = current vertex coordinates, cells TDS order + perm (sub-entity
+   order = id order), vflags bit0 isInterface / bit1 boundaryFlag == 1, facets = interface elements (vertex indices, facet
+   order), iverts[i] = bulk vertex of interface vertex i, ishifts[niv][2], level = insertionLevel or NULL, removed_mask[nv] =
+   removed_ on entry (updated).  Outputs: removed[<= nv] (appended to remove_, in order), ins_* per insertion point
+   (edge vertices, point, v0, insertionLevel, crossing facet, connectedcomponent == interface edge).
+   Returns 0 / 1 = `change`, or the GridError: -1 "A cell has a negative volume" (:926-930), -2 "more than one interface
+   edge" (:970-974), -3 "without any interface edge" (:1001-1005), -4 "two interfaces cross" (:1023-1026). */
+int orc_ensure_interface_movement_2d(const double* x, int64_t nv, const int32_t* cells, const uint8_t* perm, int64_t nc,
+                                     const uint8_t* vflags, const int32_t* facets, int64_t ns, const int32_t* iverts, int64_t niv,
+                                     const double* ishifts, const int32_t* level, uint8_t* removed_mask, int32_t* removed,
+                                     int64_t* n_removed, int32_t* ins_edge, double* ins_point, int32_t* ins_v0, int64_t* ins_level,
+                                     int32_t* ins_crossing, uint8_t* ins_comp_is_edge, int64_t* n_inserted);
+
 /* ---- component numbers of adapt_() ------------------------------------------------------------- */
 /* dune/mmesh/grid/mmesh.hh:1194-1218 (the `while (markAgain)` loop over insert_ then remove_) with getComponentNumber_
    (:1919-1941) and the marking of the zone's elements (:1862-1872, :1889-1903).  zones = CSR over cell indices in the order the

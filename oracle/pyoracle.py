@@ -369,3 +369,24 @@ def component_numbers(zone_off, zone_cells, nc, component_count=1, cell_number=N
     lib().orc_component_numbers.restype = C.c_int64
     cc = lib().orc_component_numbers(C.c_int64(nz), _p(zone_off), _p(zone_cells), C.c_int64(component_count), _p(zn), _p(cn))
     return zn[:nz], cn, int(cc)
+
+
+def ensure_interface_movement_2d(x, cells, perm, vflags, facets, iverts, ishifts, level=None, removed=()):
+    """mmesh.hh:920-1088 restated in C (oracle/mmesh_oracle.c).  Returns ("ok", change, removed, inserted) with inserted rows
+    (edge a, edge b, x, y, v0, insertionLevel, crossing facet, component-is-interface-edge), or ("error", code)."""
+    x, cells, facets, iverts, ishifts = _f64(x), _i32(cells), _i32(facets).reshape(-1, 2), _i32(iverts), _f64(ishifts).reshape(-1, 2)
+    perm = np.ascontiguousarray(perm, np.uint8); vflags = np.ascontiguousarray(vflags, np.uint8)
+    nv, nc, ns, niv = x.shape[0], cells.shape[0], facets.shape[0], iverts.shape[0]
+    mask = np.zeros(nv, np.uint8); mask[list(removed)] = 1
+    rem = np.zeros(nv + 1, np.int32); nrem = C.c_int64(); nins = C.c_int64()
+    ie = np.zeros((nc + 1, 2), np.int32); ip = np.zeros((nc + 1, 2)); iv0 = np.zeros(nc + 1, np.int32); il = np.zeros(nc + 1, np.int64)
+    ic = np.zeros(nc + 1, np.int32); icomp = np.zeros(nc + 1, np.uint8)
+    lev = None if level is None else _i32(level)
+    rc = lib().orc_ensure_interface_movement_2d(_p(x), C.c_int64(nv), _p(cells), _p(perm), C.c_int64(nc), _p(vflags), _p(facets), C.c_int64(ns),
+                                                _p(iverts), C.c_int64(niv), _p(ishifts), None if lev is None else _p(lev), _p(mask), _p(rem),
+                                                C.byref(nrem), _p(ie), _p(ip), _p(iv0), _p(il), _p(ic), _p(icomp), C.byref(nins))
+    if rc < 0:
+        return ("error", rc)
+    n = nins.value
+    ins = [(int(ie[i, 0]), int(ie[i, 1]), float(ip[i, 0]), float(ip[i, 1]), int(iv0[i]), int(il[i]), int(ic[i]), int(icomp[i])) for i in range(n)]
+    return ("ok", bool(rc), rem[:nrem.value].tolist(), ins)

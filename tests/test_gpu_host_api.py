@@ -168,3 +168,70 @@ def test_adapt_handle_drop_in(oracle, tmp_path, ncomp):
     # accumulation order differs (component order vs ascending index), pieces below the 1e-8 cut-off differ by touching pairs: 1e-12
     assert np.abs(got[created] - ref[created]).max() <= 1e-12 * np.abs(ref[created]).max()
     assert int(lines["after"][1]) == 0
+
+
+IFMOVE_EXE = os.path.join(ROOT, "tests", "native", "_build", "interface_move_gpu_test")
+
+
+@pytest.mark.gpu
+def test_ensure_interface_movement_on_device(oracle, tmp_path):
+    """MMesh::ensureInterfaceMovement (mmesh.hh:920-1088) through the GPU path on a mesh that was moved since its snapshot:
+    pre-check + inverted cells on the device, the element loop on the CURRENT coordinates.  Expected: the oracle's C
+    restatement of the reference loop, run on the moved coordinates (moveVertices is one IEEE add per component)."""
+    os.makedirs(os.path.dirname(IFMOVE_EXE), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "dune-mmesh_b200", "host"),
+                           os.path.join(ROOT, "tests", "native", "interface_move_gpu_test.cc"), "-o", IFMOVE_EXE,
+                           "-L", os.path.join(ROOT, "dune-mmesh_b200", "lib"), "-lmmesh_b200", "-Wl,-rpath," + os.path.join(ROOT, "dune-mmesh_b200", "lib")])
+    rng = np.random.default_rng(14)
+    n = 24
+    bottom = [(float(i), 0.0) for i in range(n + 1)]; top = [(float(i), 1.0) for i in range(n + 1)]; tips = [(i + 0.5, 0.3) for i in range(n)]
+    x = np.array(bottom + top + tips)
+    B = lambda i: i; Tp = lambda i: n + 1 + i; Ti = lambda i: 2 * (n + 1) + i
+    cells, facets = [], []
+    for i in range(n):
+        cells += [(B(i), B(i + 1), Ti(i)), (B(i + 1), Tp(i + 1), Ti(i)), (Tp(i + 1), Tp(i), Ti(i)), (Tp(i), B(i), Ti(i))]
+        facets.append((B(i), B(i + 1)))
+        facets.append((Ti(i), Tp(i)) if i % 2 == 0 else (Tp(i + 1), Ti(i)))
+    cells = np.array(cells, np.int32); facets = np.array(facets, np.int32)
+    perm = np.array([int(o[0]) | (int(o[1]) << 2) | (int(o[2]) << 4) for o in np.argsort(cells, axis=1, kind="stable")], np.uint8)
+    vflags = np.zeros(len(x), np.uint8)
+    vflags[facets.ravel()] |= 1
+    iverts = np.nonzero(vflags & 1)[0].astype(np.int32)
+    levels = rng.integers(0, 3, len(x)).astype(np.int32)
+    seen_insert = seen_error = 0
+    for trial in range(12):
+        vsh = rng.uniform(-0.05, 0.05, x.shape)                       # the mesh moves first: the snapshot coordinates go stale
+        vsh[: 2 * (n + 1), 1] = 0.0
+        ish = np.zeros((len(iverts), 2))
+        for i in range(n):
+            if rng.uniform() < 0.4:
+                ish[list(iverts).index(Ti(i))] = (rng.uniform(-0.2, 0.2), -rng.uniform(0.25, 0.7))
+        f = tmp_path / ("ifm_%d.txt" % trial)
+        with open(f, "w") as out:
+            out.write("%d %d %d %d\n" % (len(x), len(cells), len(facets), len(iverts)))
+            for arr, fmt in ((x, "%.17g"), (cells, "%d")):
+                np.savetxt(out, arr, fmt=fmt)
+            out.write(" ".join(str(int(p)) for p in perm) + "\n")
+            np.savetxt(out, facets, fmt="%d")
+            for arr in (vflags, levels, iverts):
+                out.write(" ".join(str(int(v)) for v in arr) + "\n")
+            np.savetxt(out, ish, fmt="%.17g"); np.savetxt(out, vsh, fmt="%.17g")
+        res = subprocess.run([IFMOVE_EXE, str(f)], capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr
+        lines = res.stdout.strip().splitlines()
+        want = oracle.ensure_interface_movement_2d(oracle.move(x, vsh), cells, perm, vflags, facets, iverts, ish, levels)
+        if want[0] == "error":
+            msg = {-1: "negative volume", -2: "more than one interface edge", -3: "without any interface edge", -4: "two interfaces cross"}[want[1]]
+            assert lines[0].startswith("GridError") and msg in lines[0]
+            seen_error += 1
+            continue
+        assert lines[0] == "change %d" % int(want[1])
+        assert [int(v) for v in lines[1].split()[1:]] == want[2]
+        assert lines[2] == "inserted %d" % len(want[3])
+        for ln, w in zip(lines[3:], want[3]):
+            t = ln.split()
+            assert [int(t[1]), int(t[2])] == [w[0], w[1]] and (float(t[3]), float(t[4])) == (w[2], w[3])
+            assert [int(t[5]), int(t[6]), int(t[7]), int(t[8])] == [w[4], w[5], w[6], w[7]]
+        assert lines[3 + len(want[3])] == "coords_kept 1"
+        seen_insert += len(want[3])
+    assert seen_insert > 3

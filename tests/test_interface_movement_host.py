@@ -1,7 +1,9 @@
 """Host-side branch of ensureInterfaceMovement for cells that invert under the interface movement (mmesh.hh:935-1078;
-dune-mmesh_b200/host/mmesh_b200.hh::resolveInterfaceMovement2d) against a direct Python restatement of the reference loop
-(all elements in order, validity re-evaluated after every move-back).  CPU only: the inverted-cell list the device would
-report is computed here with the same inexact area formula."""
+dune-mmesh_b200/host/mmesh_b200.hh::resolveInterfaceMovement2d) against the ORACLE's C restatement of the reference loop
+(oracle/mmesh_oracle.c: orc_ensure_interface_movement_2d -- all elements in order, validity re-evaluated after every
+move-back); a second, independent Python restatement in this file must agree with the oracle too.  CPU only: the
+inverted-cell list the device would report is computed here with the same inexact area formula (the GPU run of the
+whole member is tests/test_gpu_host_api.py::test_ensure_interface_movement_on_device)."""
 import os
 import subprocess
 
@@ -117,7 +119,13 @@ def _run(exe, tmp_path, x, cells, facets, vflags, levels, iverts, ishifts):
         out.write(" ".join(str(c) for c in invalid) + "\n")
     res = subprocess.run([exe, str(f)], capture_output=True, text=True, timeout=60)
     assert res.returncode == 0, res.stderr
-    want = _reference_loop(x, cells, [tuple(r) for r in facets.tolist()], list(vflags), list(levels), list(iverts), np.asarray(ishifts, float))
+    twin = _reference_loop(x, cells, [tuple(r) for r in facets.tolist()], list(vflags), list(levels), list(iverts), np.asarray(ishifts, float))
+    from oracle import pyoracle as O
+    O.build()
+    want = O.ensure_interface_movement_2d(x, cells, [_perm(c) for c in cells], vflags, facets, iverts, ishifts, levels)
+    if want[0] == "error":
+        want = ("error", {-2: "more than one interface edge", -3: "without any interface edge", -4: "two interfaces cross"}[want[1]])
+    assert want == twin, (want, twin)
     return res.stdout.strip().splitlines(), want, invalid
 
 
