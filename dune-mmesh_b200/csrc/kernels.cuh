@@ -1054,6 +1054,107 @@ k_project_tile(const ProjArgs a, double* __restrict__ part_mass, double* __restr
     if (N) atomicAdd(&cnt->n_pieces, (unsigned long long)N);
   }
 }
+// DG-P1 projection as two passes without phase barriers (development variant):
+//   k_project_pairs  one thread per (old, new) pair: clip in the thread's own shared-memory column, fan + quadrature, the
+//                    pair's partial sums (r1, r2, u, covered area) and piece count go to global memory;
+//   k_project_cells  one thread per new cell: the partial sums of its pairs added in CSR order, the local solve.
+// The only barrier is the one after the per-cell set-up (clip-edge constants, inverse affine map) that the NT/4 cell
+// threads of a CTA share with its NT pair threads.
+template <int NT, int MINB, bool FMA>
+__global__ void __launch_bounds__(NT, MINB)
+k_project_pairs(const ProjArgs a, double4* __restrict__ partial, uint8_t* __restrict__ pieces) {
+  extern __shared__ __align__(16) unsigned char proj_smem[];
+  ProjTile<NT>& T = *reinterpret_cast<ProjTile<NT>*>(proj_smem);
+  constexpr int NCELL = NT / 4;
+  const int t = threadIdx.x;
+  const int64_t i0 = a.i_begin + (int64_t)blockIdx.x * NCELL;
+  const int ncell = (int)((a.nnew - i0) < NCELL ? (a.nnew - i0) : NCELL);
+  const long long p_lo = a.new_off[i0];
+  const int np_tile = (int)(a.new_off[i0 + ncell] - p_lo);
+  bool four = true;
+  if (t < ncell) four = proj_cell_setup<NT>(T, a, t, i0 + t, p_lo) == 4;
+  const bool uniform = __syncthreads_and(four) != 0;
+  for (int cl = 0; cl < np_tile; cl += NT) {
+    const int np = (np_tile - cl) < NT ? (np_tile - cl) : NT;
+    if (!uniform) { __syncthreads(); if (t < ncell) proj_paint<NT>(T, t, cl); __syncthreads(); }
+    int j = t; bool live = t < np;
+    if (uniform) { const int q = t / NCELL, c = t - q * NCELL; j = 4 * c + q; live = c < ncell; }
+    if (!live) continue;
+    const long long p = p_lo + cl + j;
+    const int c = uniform ? (j >> 2) : T.owner[j];
+    const int col = t;                                               // the thread's own column: no other thread touches it
+    double cx[3], cy[3];
+    proj_old_corners(a.old_xy, p, T.org[c], cx, cy);
+    {
+      const double od = (cy[1] - cy[0]) * (cx[2] - cx[1]) - (cx[1] - cx[0]) * (cy[2] - cy[1]);
+      const int o = (fabs(od) < 2147483648.0) ? (int)od : 0;
+      const bool sw = o > 0;
+      T.P[0][col] = make_double2(cx[0], cy[0]);
+      T.P[1][col] = sw ? make_double2(cx[2], cy[2]) : make_double2(cx[1], cy[1]);
+      T.P[2][col] = sw ? make_double2(cx[1], cy[1]) : make_double2(cx[2], cy[2]);
+    }
+    double r1 = 0.0, r2 = 0.0, u = 0.0, cov = 0.0; unsigned npc = 0;
+    if (proj_clip_column<NT>(T, a, col, c)) {
+      const int nC = T.npts[col];
+      if (nC != PROJ_HARD) {
+        const Aff2 gO = aff2_make(cx[0], cy[0], cx[1], cy[1], cx[2], cy[2]);
+        const double* uo = a.dofs_old + 3 * (int64_t)a.old_idx[p];
+        const double u0 = uo[0], u1 = uo[1], u2 = uo[2];
+        const double du1 = u1 - u0, du2 = u2 - u0;
+        const double gx = du1 * gO.i00 + du2 * gO.i01, gy = du1 * gO.i10 + du2 * gO.i11;
+        proj_fan<FMA>([&](int k) { return T.Q[k][col]; }, nC, u0, gx, gy, gO.ox, gO.oy, T.G[0][c], T.G[1][c], T.G[2][c], a.prm.drop_area,
+                      r1, r2, u, cov, npc);
+      } else {
+        const ProjPartial g = proj_pair_generic<FMA>(a, T.K[c], p);
+        r1 = g.r1; r2 = g.r2; u = g.u; cov = g.cov; npc = g.npc;
+      }
+    }
+    partial[p] = make_double4(r1, r2, u, cov);
+    pieces[p] = (uint8_t)npc;
+  }
+}
+__global__ void __launch_bounds__(128)
+k_project_cells(const ProjArgs a, const double4* __restrict__ partial, const uint8_t* __restrict__ pieces, double* __restrict__ part_mass,
+                double* __restrict__ part_cov, Counters* __restrict__ cnt) {
+  const int64_t i = a.i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double mass = 0.0, cov = 0.0; unsigned npc = 0;
+  if (i < a.nnew) {
+    const int K = a.new_cell[i];
+    const int v[3] = { a.cv0[K], a.cv1[K], a.cv2[K] };
+    const unsigned pm = a.perm[K];
+    double ex[3], ey[3], kx[3], ky[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { const double2 q = ldg2(a.xy + v[t]); ex[t] = q.x; ey[t] = q.y; }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { const int s = (pm >> (2 * t)) & 3; kx[t] = s == 0 ? ex[0] : (s == 1 ? ex[1] : ex[2]); ky[t] = s == 0 ? ey[0] : (s == 1 ? ey[1] : ey[2]); }
+    const double volK = aff2_make(kx[0], ky[0], kx[1], ky[1], kx[2], ky[2]).vol;
+    double R1 = 0.0, R2 = 0.0, U = 0.0;
+    for (long long p = a.new_off[i]; p < a.new_off[i + 1]; ++p) {     // pairs are added in CSR order
+      const double4 r = partial[p];
+      R1 += r.x; R2 += r.y; U += r.z; cov += r.w; npc += pieces[p];
+    }
+    const double R0 = U - R1 - R2;
+    const double f = 3.0 / volK;
+    const double r0 = f * (4.0 * R0 - U), r1 = f * (4.0 * R1 - U), r2 = f * (4.0 * R2 - U);
+    double* o = a.dofs_new + 3 * (int64_t)K;
+    o[0] = r0; o[1] = r1; o[2] = r2;
+    mass = volK * ((r0 + r1 + r2) / 3.0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mass += __shfl_xor_sync(0xffffffffu, mass, o); cov += __shfl_xor_sync(0xffffffffu, cov, o); }
+  npc = warp_sum(npc);
+  __shared__ double sm[4], sc[4]; __shared__ unsigned sn[4];
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) { sm[threadIdx.x >> 5] = mass; sc[threadIdx.x >> 5] = cov; sn[threadIdx.x >> 5] = npc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    part_mass[blockIdx.x] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+    part_cov[blockIdx.x] = (sc[0] + sc[1]) + (sc[2] + sc[3]);
+    const unsigned N = sn[0] + sn[1] + sn[2] + sn[3];
+    if (N) atomicAdd(&cnt->n_pieces, (unsigned long long)N);
+  }
+}
+
 // Fixed-shape reduction of the per-block partial sums (deterministic: the shape depends only on n and the grid).  Every
 // block reduces one contiguous slice; the block that finishes last (ticket) adds the slice sums in slice order.
 constexpr int REDUCE_MAX_BLOCKS = 256;
@@ -1205,6 +1306,53 @@ k_mark3d(const double* __restrict__ x, const double* __restrict__ dist, const in
     nref = (m > 0);
   }
   block_count_add<256>(nref, 0u, &cnt->n_refine, &cnt->n_coarsen);
+}
+// RatioIndicator::init in 3-D (ratioindicator.hh:62-91): min / max over the edges of the listed simplices (k = 3: interface
+// triangles, k = 4: tetrahedra); every edge is seen by all its simplices, which min / max do not notice
+__global__ void __launch_bounds__(256)
+k_edge_minmax3d(const double* __restrict__ x, const int32_t* __restrict__ simplices, int k, int64_t n,
+                unsigned long long* __restrict__ mn, unsigned long long* __restrict__ mx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long lo = ~0ull, hi = 0ull;
+  if (i < n) {
+    for (int a = 0; a < k; ++a)
+      for (int b = a + 1; b < k; ++b) {
+        const int va = simplices[k * i + a], vb = simplices[k * i + b];
+        double q = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const double j = __ldg(x + 3 * (int64_t)vb + c) - __ldg(x + 3 * (int64_t)va + c); q += j * j; }
+        const unsigned long long h = (unsigned long long)__double_as_longlong(sqrt(q));
+        lo = h < lo ? h : lo; hi = h > hi ? h : hi;
+      }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0) { if (lo != ~0ull) atomicMin(mn, lo); atomicMax(mx, hi); }
+}
+// interface triangles of a 3-D grid through RatioIndicator::operator() (mmesh.hh:745-748): distance 0 => l = 0; coarsening
+// cannot be returned because dim == 3 (ratioindicator.hh:151-153) => +1 iff an edge is longer than maxH
+__global__ void __launch_bounds__(256)
+k_mark_interface3d(const double* __restrict__ x, const int32_t* __restrict__ tris, int ns, DevParams prm,
+                   const Counters* __restrict__ cin, int8_t* __restrict__ mark) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns) return;
+  const double maxDist = prm.distProportion * __longlong_as_double((long long)cin->max_dist_bits);
+  const double dist = (0.0 < maxDist) ? 0.0 : maxDist;
+  const double l = dist / maxDist;
+  const double maxH = (1. - l) * prm.maxH + l * prm.factor * prm.maxH;
+  int refine = 0;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    const int va = tris[3 * s + e], vb = tris[3 * s + (e + 1) % 3];
+    double q = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const double j = __ldg(x + 3 * (int64_t)vb + c) - __ldg(x + 3 * (int64_t)va + c); q += j * j; }
+    if (sqrt(q) > maxH) refine++;
+  }
+  mark[s] = (int8_t)(refine > 0 ? 1 : 0);
 }
 // 3-D facet leaves: 7 sample points (3 corners, 3 edge midpoints, centre), distance.hh:157-173.  Same tree machinery as
 // in 2-D: fp32 boxes rounded outward (two float4 per node), one-launch refit, hint-seeded leaf->root walk.
@@ -1396,6 +1544,51 @@ k_project_interface_p0(const double* __restrict__ new_len, const long long* __re
     initialize = false;
   }
   dofs_new[i] = acc;
+}
+// MMeshInterfaceGrid::adapt(handle) with DG-P1 data on the segments (2 nodal DOFs on the id-ordered corners),
+// dune/mmesh/interface/grid.hh:388-415 + geometryInFather (interface/entity.hh:491-507).  The longer of (old, new) is the
+// father: old longer => the father's function evaluated at the son's corners (prolongLocal, overwrites); else the local L2
+// projection of the son on the father's P1 space, M_f^-1 int_son u phi_i, set or added (restrictLocal).  The arithmetic is
+// the oracle's definition (dune-fem un-vendored): local(x) = ((x - c0) . d) / (d . d), vertex rule len/6 (2 1; 1 2).
+__device__ __forceinline__ double seg_len4(const double4 c) {
+  const double dx = c.z - c.x, dy = c.w - c.y; double q = 0.0; q += dx * dx; q += dy * dy; return sqrt(q);
+}
+__device__ __forceinline__ double seg_local4(const double4 c, double px, double py) {
+  const double dx = c.z - c.x, dy = c.w - c.y;
+  double s = 0.0; s += (px - c.x) * dx; s += (py - c.y) * dy;
+  double n2 = 0.0; n2 += dx * dx; n2 += dy * dy;
+  return s / n2;
+}
+__global__ void __launch_bounds__(256)
+k_project_interface_p1(const double4* __restrict__ new_xy, const long long* __restrict__ new_off, int64_t nnew,
+                       const double4* __restrict__ old_xy, const int32_t* __restrict__ old_idx, const double2* __restrict__ dofs_old,
+                       double2* __restrict__ dofs_new) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnew) return;
+  const double4 nw = ldg4(new_xy + i);
+  const double ln = seg_len4(nw);
+  double a0 = 0.0, a1 = 0.0; bool initialize = true;
+  for (long long p = new_off[i]; p < new_off[i + 1]; ++p) {
+    const double4 od = ldg4(old_xy + p);
+    const double2 u = ldg2(dofs_old + old_idx[p]);
+    const double lo = seg_len4(od);
+    if (lo > ln) {
+      const double t0 = seg_local4(od, nw.x, nw.y), t1 = seg_local4(od, nw.z, nw.w);
+      a0 = (1.0 - t0) * u.x + t0 * u.y;
+      a1 = (1.0 - t1) * u.x + t1 * u.y;
+    } else {
+      const double ta = seg_local4(nw, od.x, od.y), tb = seg_local4(nw, od.z, od.w);
+      const double pa0 = 1.0 - ta, pb0 = 1.0 - tb, pa1 = ta, pb1 = tb;
+      const double w = lo * (1.0 / 6.0);
+      const double r0 = w * (((2.0 * u.x) * pa0 + u.x * pb0) + (u.y * pa0 + (2.0 * u.y) * pb0));
+      const double r1 = w * (((2.0 * u.x) * pa1 + u.x * pb1) + (u.y * pa1 + (2.0 * u.y) * pb1));
+      const double f = 2.0 / ln;
+      const double c0 = f * (2.0 * r0 - r1), c1 = f * (2.0 * r1 - r0);
+      if (initialize) { a0 = c0; a1 = c1; } else { a0 += c0; a1 += c1; }
+    }
+    initialize = false;
+  }
+  dofs_new[i] = make_double2(a0, a1);
 }
 // LongestEdgeRefinement::refinement (longestedgerefinement.hh:41-57): centre of the longest edge of the listed cells,
 // edge.geometry().center() = origin + 0.5 * (second - first) on the id-ordered corners (DUNE edge numbering)

@@ -57,7 +57,7 @@ struct mmb_context {
   bool sharded = false;             // one of several ranks: the gate of the fused step's move comes from an all-reduce
   int64_t own_lo = 0, own_hi = 0;   // owned cell range (counts); halo cells outside it are evaluated but not counted
   DBuf<int32_t> halo_send_idx, halo_recv_idx; DBuf<double2> halo_send, halo_recv; int64_t n_halo_send = 0, n_halo_recv = 0;
-  DBuf<double> reduce_vec, red_slices; DBuf<unsigned> red_ticket;
+  DBuf<double> reduce_vec, red_slices, pair_partial; DBuf<unsigned> red_ticket; DBuf<uint8_t> pair_pieces;
   mmb_params prm{};
   // mesh
   DBuf<double> x, shift, dist;
@@ -198,7 +198,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->dofs_old.release(); ctx->dofs_new.release(); ctx->part_a.release(); ctx->part_b.release(); ctx->pair_vol.release();
   ctx->tr_in.release(); ctx->tr_out.release(); ctx->tr_u.release(); ctx->tr_ug.release();
   ctx->tr_a.release(); ctx->tr_b.release(); ctx->tr_c.release(); ctx->pred_pts.release(); ctx->pred_sign.release();
-  ctx->halo_send_idx.release(); ctx->halo_recv_idx.release(); ctx->halo_send.release(); ctx->halo_recv.release(); ctx->reduce_vec.release(); ctx->red_slices.release(); ctx->red_ticket.release();
+  ctx->halo_send_idx.release(); ctx->halo_recv_idx.release(); ctx->halo_send.release(); ctx->halo_recv.release(); ctx->reduce_vec.release(); ctx->red_slices.release(); ctx->red_ticket.release(); ctx->pair_partial.release(); ctx->pair_pieces.release();
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->h_remote_stage) cudaFreeHost(ctx->h_remote_stage);
   ctx->d_remote_idx.release(); ctx->d_remote_stage.release();
@@ -640,23 +640,30 @@ int mmb_distance_set(mmb_context* ctx, const double* dist_host) {
 // ---- indicator ------------------------------------------------------------------------------------------
 int mmb_indicator_init(mmb_context* ctx) {
   if (!ctx) return MMB_ERR_INVALID_ARG;
-  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "indicator_init needs an uploaded 2-D mesh");
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "indicator_init needs an uploaded mesh");
   Counters* c = ctx->counters.p;
   const unsigned long long init[4] = { ~0ull, 0ull, ~0ull, 0ull };
   CK(cudaMemcpyAsync(c->minmax_bits, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
-  if (ctx->ns)
-    LAUNCH("edge_minmax", k_edge_minmax, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, ctx->facets.p, 2, ctx->ns,
-           &c->minmax_bits[0], &c->minmax_bits[1]);
-  if (ctx->ne)
-    LAUNCH("edge_minmax", k_edge_minmax, grid_for(ctx->ne, 256), 256, (const double2*)ctx->x.p, (const int32_t*)ctx->edges.p, 4,
-           ctx->ne, &c->minmax_bits[2], &c->minmax_bits[3]);
+  if (ctx->dim == 2) {
+    if (ctx->ns)
+      LAUNCH("edge_minmax", k_edge_minmax, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, ctx->facets.p, 2, ctx->ns,
+             &c->minmax_bits[0], &c->minmax_bits[1]);
+    if (ctx->ne)
+      LAUNCH("edge_minmax", k_edge_minmax, grid_for(ctx->ne, 256), 256, (const double2*)ctx->x.p, (const int32_t*)ctx->edges.p, 4,
+             ctx->ne, &c->minmax_bits[2], &c->minmax_bits[3]);
+  } else {                                                  // ratioindicator.hh:62-91 is dimension generic
+    if (ctx->ns)
+      LAUNCH("edge_minmax3d", k_edge_minmax3d, grid_for(ctx->ns, 256), 256, ctx->x.p, ctx->facets.p, 3, ctx->ns, &c->minmax_bits[0], &c->minmax_bits[1]);
+    if (ctx->nc)
+      LAUNCH("edge_minmax3d", k_edge_minmax3d, grid_for(ctx->nc, 256), 256, ctx->x.p, ctx->cells_aos.p, 4, ctx->nc, &c->minmax_bits[2], &c->minmax_bits[3]);
+  }
   CK(cudaGetLastError());
   TRY(fetch_counters(ctx));
   auto as_d = [](unsigned long long b) { double d; memcpy(&d, &b, 8); return d; };
   const double K = 2.0, k = K / (2.0 * 4.0);
   double maxH = 0.0, minH = 1e100, maxh = 0.0, minh = 1e100;
   if (ctx->ns) { minH = std::min(minH, as_d(ctx->h_counters->minmax_bits[0])); maxH = std::max(maxH, as_d(ctx->h_counters->minmax_bits[1])); }
-  if (ctx->ne) { minh = std::min(minh, as_d(ctx->h_counters->minmax_bits[2])); maxh = std::max(maxh, as_d(ctx->h_counters->minmax_bits[3])); }
+  if (ctx->dim == 2 ? ctx->ne > 0 : ctx->nc > 0) { minh = std::min(minh, as_d(ctx->h_counters->minmax_bits[2])); maxh = std::max(maxh, as_d(ctx->h_counters->minmax_bits[3])); }
   maxH = K * maxH; minH = k * minH;
   if (ctx->ns == 0) { maxH = K * maxh; minH = k * minh; }
   ctx->prm.maxH = maxH; ctx->prm.minH = minH; ctx->prm.factor = maxh / minh;
@@ -690,11 +697,15 @@ int mmb_mark_elements(mmb_context* ctx, int run_distance, int8_t* marks_host, ui
 }
 int mmb_mark_interface(mmb_context* ctx, int8_t* marks_host) {
   if (!ctx) return MMB_ERR_INVALID_ARG;
-  REQUIRE(ctx->mesh_ok && ctx->dim == 2, MMB_ERR_STATE, "mark_interface needs an uploaded 2-D mesh");
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "mark_interface needs an uploaded mesh");
   REQUIRE(ctx->dist_valid, MMB_ERR_STATE, "mark_interface before Distance::update");
   if (ctx->ns == 0) return MMB_OK;
-  LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
-         (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
+  if (ctx->dim == 2)
+    LAUNCH("mark_interface2d", k_mark_interface2d, grid_for(ctx->ns, 256), 256, (const double2*)ctx->x.p, (const int2*)ctx->facets.p,
+           (int)ctx->ns, dev_params(ctx->prm), ctx->counters.p, ctx->imark.p);
+  else
+    LAUNCH("mark_interface3d", k_mark_interface3d, grid_for(ctx->ns, 256), 256, ctx->x.p, ctx->facets.p, (int)ctx->ns, dev_params(ctx->prm),
+           ctx->counters.p, ctx->imark.p);
   CK(cudaGetLastError());
   if (marks_host) {
     CK(cudaMemcpyAsync(marks_host, ctx->imark.p, (size_t)ctx->ns, cudaMemcpyDeviceToHost, ctx->stream));
@@ -792,6 +803,24 @@ static int launch_project_tile(mmb_context* ctx, const ProjArgs& pa, int pb0, un
   *nb_out = nb;
   return MMB_OK;
 }
+template <int NT, int MINB, bool FMA>
+static int launch_project_pairs(mmb_context* ctx, const ProjArgs& pa, int pb0, unsigned* nb_out) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_project_pairs<NT, MINB, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProjTile<NT>)));
+    attr_set = true;
+  }
+  CK(ctx->pair_partial.ensure(4 * (size_t)ctx->npairs + 4)); CK(ctx->pair_pieces.ensure((size_t)ctx->npairs + 4));
+  const unsigned nbp = grid_for(pa.nnew - pa.i_begin, NT / 4);
+  {
+    LaunchScope ls_(ctx, "project_p1");
+    k_project_pairs<NT, MINB, FMA><<<nbp, NT, sizeof(ProjTile<NT>), ctx->stream>>>(pa, (double4*)ctx->pair_partial.p, ctx->pair_pieces.p);
+  }
+  const unsigned nb = grid_for(pa.nnew - pa.i_begin, 128);
+  LAUNCH("project_p1_cells", k_project_cells, nb, 128, pa, (const double4*)ctx->pair_partial.p, ctx->pair_pieces.p, ctx->part_a.p + pb0, ctx->part_b.p + pb0, ctx->counters.p);
+  *nb_out = nb;
+  return MMB_OK;
+}
 }  // extern "C++"
 #endif
 // projection of the new cells [i0, i1) of the pair CSR; per-block partial sums go to part_[pb0 ...); returns #blocks
@@ -815,6 +844,12 @@ static int project_range(mmb_context* ctx, int ncomp, int64_t i0, int64_t i1, in
       case 11: TRY((launch_project_tile<128, 7, true>(ctx, pa, pb0, &nb))); break;
       case 12: TRY((launch_project_tile<256, 3, false>(ctx, pa, pb0, &nb))); break;
       case 13: TRY((launch_project_tile<256, 3, true>(ctx, pa, pb0, &nb))); break;
+      case 30: TRY((launch_project_pairs<128, 7, false>(ctx, pa, pb0, &nb))); break;
+      case 31: TRY((launch_project_pairs<128, 7, true>(ctx, pa, pb0, &nb))); break;
+      case 32: TRY((launch_project_pairs<128, 6, false>(ctx, pa, pb0, &nb))); break;
+      case 33: TRY((launch_project_pairs<128, 5, false>(ctx, pa, pb0, &nb))); break;
+      case 34: TRY((launch_project_pairs<256, 3, false>(ctx, pa, pb0, &nb))); break;
+      case 35: TRY((launch_project_pairs<64, 14, false>(ctx, pa, pb0, &nb))); break;
       case 21: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 2>), nb, PROJ_THREADS, PROJ_ARGS); break;
       case 22: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 3>), nb, PROJ_THREADS, PROJ_ARGS); break;
       default: nb = grid_for(i1 - i0, PROJ_THREADS); LAUNCH("project_p1", (k_project<3, 1, 5, 1>), nb, PROJ_THREADS, PROJ_ARGS); break;
@@ -907,6 +942,33 @@ int mmb_project_interface_p0(mmb_context* ctx, int64_t nnew, const double* new_l
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(e);
   nl.release(); ol.release(); dO.release(); dN.release(); off.release(); oi.release();
+  return MMB_OK;
+}
+int mmb_project_interface_p1(mmb_context* ctx, int64_t nnew, const double* new_xy_host, const int64_t* new_off_host,
+                             int64_t npairs, const double* old_xy_host, const int32_t* old_idx_host, int64_t n_old,
+                             const double* dofs_old_host, double* dofs_new_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(nnew > 0 && npairs >= 0 && n_old > 0 && new_xy_host && new_off_host && dofs_old_host && dofs_new_host &&
+          (npairs == 0 || (old_xy_host && old_idx_host)), MMB_ERR_INVALID_ARG, "mmb_project_interface_p1: bad arguments");
+  REQUIRE(new_off_host[0] == 0 && new_off_host[nnew] == npairs, MMB_ERR_INVALID_ARG, "mmb_project_interface_p1: malformed CSR");
+  for (int64_t i = 0; i < nnew; ++i) REQUIRE(new_off_host[i + 1] >= new_off_host[i], MMB_ERR_INVALID_ARG, "mmb_project_interface_p1: malformed CSR");
+  for (int64_t p = 0; p < npairs; ++p) REQUIRE(old_idx_host[p] >= 0 && old_idx_host[p] < n_old, MMB_ERR_INVALID_ARG, "mmb_project_interface_p1: old index out of range");
+  DBuf<double> nx, ox, dO, dN; DBuf<long long> off; DBuf<int32_t> oi;
+  auto release = [&]() { nx.release(); ox.release(); dO.release(); dN.release(); off.release(); oi.release(); };
+  auto fail = [&](cudaError_t e) { ctx->err = cudaGetErrorString(e); release(); return (int)MMB_ERR_CUDA; };
+  cudaError_t e;
+  if ((e = nx.ensure(4 * nnew)) || (e = ox.ensure(4 * npairs + 4)) || (e = dO.ensure(2 * n_old)) || (e = dN.ensure(2 * nnew)) || (e = off.ensure(nnew + 1)) || (e = oi.ensure(npairs + 1))) return fail(e);
+  cudaMemcpyAsync(nx.p, new_xy_host, (size_t)nnew * 32, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(off.p, new_off_host, (size_t)(nnew + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (npairs) { cudaMemcpyAsync(ox.p, old_xy_host, (size_t)npairs * 32, cudaMemcpyHostToDevice, ctx->stream); cudaMemcpyAsync(oi.p, old_idx_host, (size_t)npairs * 4, cudaMemcpyHostToDevice, ctx->stream); }
+  cudaMemcpyAsync(dO.p, dofs_old_host, (size_t)n_old * 16, cudaMemcpyHostToDevice, ctx->stream);
+  LAUNCH("project_interface_p1", k_project_interface_p1, grid_for(nnew, 256), 256, (const double4*)nx.p, off.p, nnew, (const double4*)ox.p, oi.p,
+         (const double2*)dO.p, (double2*)dN.p);
+  cudaMemcpyAsync(dofs_new_host, dN.p, (size_t)nnew * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(e);
+  release();
   return MMB_OK;
 }
 int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host, double* points_host, int32_t* edge_vertices_host) {

@@ -19,7 +19,7 @@ EXPORTS = [
     "mmb_indicator_init", "mmb_move_vertices", "mmb_trial_move_validate", "mmb_invalid_cells", "mmb_legality",
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
-    "mmb_step_host_begin", "mmb_step_host_marks", "mmb_step_host_finish", "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
+    "mmb_step_host_begin", "mmb_step_host_marks", "mmb_step_host_finish", "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_project_interface_p1", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
     "mmb_component_numbers", "mmb_host_register", "mmb_host_unregister", "mmb_comm_unique_id", "mmb_comm_init", "mmb_comm_destroy", "mmb_halo_counts", "mmb_adapt_step_sharded", "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
 ]
 
@@ -294,6 +294,15 @@ class Context:
         self._ck(lib().mmb_component_numbers(self._h, C.c_int64(nz), _p(zone_off), _p(zone_cells), C.c_int64(component_count), _p(zn), _p(cn),
                                              C.byref(cc)))
         return zn[:nz], cn, cc.value
+
+    def project_interface_p1(self, new_xy, new_off, old_xy, old_idx, dofs_old):
+        new_xy, old_xy, dofs_old = _f64(new_xy).reshape(-1, 4), _f64(old_xy).reshape(-1, 4), _f64(dofs_old).reshape(-1, 2)
+        new_off = np.ascontiguousarray(new_off, np.int64)
+        old_idx = _i32(old_idx)
+        out = np.empty((new_xy.shape[0], 2))
+        self._ck(lib().mmb_project_interface_p1(self._h, C.c_int64(new_xy.shape[0]), _p(new_xy), _p(new_off), C.c_int64(old_idx.shape[0]),
+                                                _p(old_xy), _p(old_idx), C.c_int64(dofs_old.shape[0]), _p(dofs_old), _p(out)))
+        return out
 
     def upload_neighbours(self, nb):
         nb = _i32(nb)

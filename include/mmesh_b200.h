@@ -153,6 +153,13 @@ int mmb_intersection_volumes(mmb_context* ctx, double* vol_host);
 int mmb_project_interface_p0(mmb_context* ctx, int64_t nnew, const double* new_len_host, const int64_t* new_off_host,
                              int64_t npairs, const double* old_len_host, const int32_t* old_idx_host, int64_t n_old,
                              const double* dofs_old_host, double* dofs_new_host);
+/* The same for DG-P1 interface data (two nodal DOFs per element on its id-ordered corners): new_xy / old_xy hold the two
+   corners (x0, y0, x1, y1) of every new element / old child; old longer => the father's function evaluated at the son's
+   corners through geometryInFather (interface/entity.hh:491-507), else the local L2 projection of the son onto the
+   father's P1 space.  dofs_old [n_old][2], dofs_new [nnew][2]. */
+int mmb_project_interface_p1(mmb_context* ctx, int64_t nnew, const double* new_xy_host, const int64_t* new_off_host,
+                             int64_t npairs, const double* old_xy_host, const int32_t* old_idx_host, int64_t n_old,
+                             const double* dofs_old_host, double* dofs_new_host);
 /* LongestEdgeRefinement::refinement (longestedgerefinement.hh:41-57) for the listed cells (after mmb_mark_elements):
    centre of the longest edge ([n][dim]) and, optionally, its two vertex indices (id order).  2-D and 3-D. */
 int mmb_refinement_points(mmb_context* ctx, int64_t n, const int32_t* cells_host, double* points_host, int32_t* edge_vertices_host);

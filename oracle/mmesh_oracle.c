@@ -1270,3 +1270,79 @@ int orc_ensure_interface_movement_2d(const double* x, int64_t nv, const int32_t*
   free(xt); free(sh); free(ivof); free(nincident);
   return rc ? rc : change;
 }
+
+/* interface/grid.hh:388-415 with DG-P1 data; see the header for the definitions */
+static inline double seg_len(const double* c) {                /* AffineGeometry<1,2>::volume(): sqrt(J J^T) */
+  double dx = c[2] - c[0], dy = c[3] - c[1], q = 0.0; q += dx * dx; q += dy * dy; return sqrt(q);
+}
+static inline double seg_local(const double* c, double px, double py) {     /* father.geometry().local(p) */
+  double dx = c[2] - c[0], dy = c[3] - c[1];
+  double s = 0.0; s += (px - c[0]) * dx; s += (py - c[1]) * dy;
+  double n2 = 0.0; n2 += dx * dx; n2 += dy * dy;
+  return s / n2;
+}
+void orc_project_interface_p1(const double* new_xy, const int64_t* new_off, int64_t nnew, const double* old_xy, const int32_t* old_idx,
+                              const double* dofs_old, double* dofs_new) {
+  for (int64_t i = 0; i < nnew; ++i) {
+    const double* nw = new_xy + 4 * i;
+    const double ln = seg_len(nw);
+    double a0 = 0.0, a1 = 0.0; int initialize = 1;
+    for (int64_t p = new_off[i]; p < new_off[i + 1]; ++p) {
+      const double* od = old_xy + 4 * p;
+      const double u0 = dofs_old[2 * (int64_t)old_idx[p]], u1 = dofs_old[2 * (int64_t)old_idx[p] + 1];
+      const double lo = seg_len(od);
+      if (lo > ln) {                                             /* prolongLocal(father = old, son = new, true) */
+        const double t0 = seg_local(od, nw[0], nw[1]), t1 = seg_local(od, nw[2], nw[3]);
+        a0 = (1.0 - t0) * u0 + t0 * u1;
+        a1 = (1.0 - t1) * u0 + t1 * u1;
+      } else {                                                   /* restrictLocal(father = new, son = old, initialize) */
+        const double ta = seg_local(nw, od[0], od[1]), tb = seg_local(nw, od[2], od[3]);
+        /* int_son u phi_i with the exact vertex rule len/6 (2 ua pa + ua pb + ub pa + 2 ub pb), phi_0 = 1 - t, phi_1 = t */
+        const double pa0 = 1.0 - ta, pb0 = 1.0 - tb, pa1 = ta, pb1 = tb;
+        const double w = lo * (1.0 / 6.0);
+        const double r0 = w * (((2.0 * u0) * pa0 + u0 * pb0) + (u1 * pa0 + (2.0 * u1) * pb0));
+        const double r1 = w * (((2.0 * u0) * pa1 + u0 * pb1) + (u1 * pa1 + (2.0 * u1) * pb1));
+        /* M_f^-1 = (2 / len_f) [2 -1; -1 2] */
+        const double f = 2.0 / ln;
+        const double c0 = f * (2.0 * r0 - r1), c1 = f * (2.0 * r1 - r0);
+        if (initialize) { a0 = c0; a1 = c1; } else { a0 += c0; a1 += c1; }
+      }
+      initialize = 0;
+    }
+    dofs_new[2 * i] = a0; dofs_new[2 * i + 1] = a1;
+  }
+}
+
+/* ratioindicator.hh:62-91 in 3-D */
+void orc_indicator_init_3d(const double* xyz, const int32_t* cells, int64_t nc, const int32_t* tris, int64_t ns, orc_params* prm) {
+  const double K = 2.0, k = K / (2.0 * 4.0);
+  double maxH = 0.0, minH = 1e100;
+  for (int64_t s = 0; s < ns; ++s)
+    for (int e = 0; e < 3; ++e) {
+      double h = edge_len3d(xyz + 3 * (int64_t)tris[3 * s + e], xyz + 3 * (int64_t)tris[3 * s + (e + 1) % 3]);
+      maxH = (maxH < h) ? h : maxH; minH = (h < minH) ? h : minH;
+    }
+  maxH = K * maxH; minH = k * minH;
+  double maxh = 0.0, minh = 1e100;
+  for (int64_t c = 0; c < nc; ++c)
+    for (int a = 0; a < 4; ++a) for (int b = a + 1; b < 4; ++b) {
+      double h = edge_len3d(xyz + 3 * (int64_t)cells[4 * c + a], xyz + 3 * (int64_t)cells[4 * c + b]);
+      maxh = (maxh < h) ? h : maxh; minh = (h < minh) ? h : minh;
+    }
+  if (ns == 0) { maxH = K * maxh; minH = k * minh; }
+  prm->maxH = maxH; prm->minH = minH; prm->factor = maxh / minh;
+}
+/* mmesh.hh:745-748 + ratioindicator.hh:106-160 for the triangles of a 3-D interface */
+void orc_mark_interface_3d(const double* xyz, const int32_t* tris, int64_t ns, const orc_params* prm, double maxDist, int8_t* mark) {
+  for (int64_t s = 0; s < ns; ++s) {
+    double dist = (0.0 < maxDist) ? 0.0 : maxDist;                 /* std::min(maxDist_, distance_(ielement) == 0) */
+    const double l = dist / maxDist;
+    const double maxH = (1. - l) * prm->maxH + l * prm->factor * prm->maxH;
+    int refine = 0;
+    for (int e = 0; e < 3; ++e) {
+      double len = edge_len3d(xyz + 3 * (int64_t)tris[3 * s + e], xyz + 3 * (int64_t)tris[3 * s + (e + 1) % 3]);
+      if (len > maxH) refine++;
+    }
+    mark[s] = (int8_t)(refine > 0 ? 1 : 0);                        /* coarse > 0 returns -1 only if dim != 3 */
+  }
+}

@@ -156,6 +156,25 @@ int orc_num_threads(void);
 void orc_distance_2d_culled_subset(const double* xy, int64_t nv_all, const int32_t* vidx, int64_t nsub, const int32_t* segs,
                                    int64_t ns, double* dist_sub);
 
+/* RatioIndicator::init in 3-D (ratioindicator.hh:62-91 is dimension generic): interface edges = the three edges of every
+   interface triangle, bulk edges = the six edges of every tetrahedron (min / max do not depend on multiplicity or order) */
+void orc_indicator_init_3d(const double* xyz, const int32_t* cells, int64_t nc, const int32_t* tris, int64_t ns, orc_params* prm);
+/* interface elements of a 3-D grid through RatioIndicator::operator() (mmesh.hh:745-748): distance 0 => l = 0; the coarsening
+   criteria cannot fire because dim == dimensionworld == 3 (ratioindicator.hh:151-153) => +1 iff an edge is longer than maxH */
+void orc_mark_interface_3d(const double* xyz, const int32_t* tris, int64_t ns, const orc_params* prm, double maxDist, int8_t* mark);
+
+/* MMeshInterfaceGrid::adapt(handle) (interface/grid.hh:388-415) with DG-P1 data on the interface segments (2 nodal DOFs per
+   element on its id-ordered corners).  new_xy / old_xy: the two corners (x0, y0, x1, y1) of every new element / old child.
+   father = the longer one (volume() = two_norm of c1 - c0):
+     old longer  -> prolongLocal(father = old, son = new, true): the father's function evaluated at the son's corners through
+                    geometryInFather (interface/entity.hh:491-507: father.geometry().local(corner)), overwriting;
+     else        -> restrictLocal(father = new, son = old, initialize): local L2 projection of the son's function on the
+                    father's P1 space over the son, M_f^-1 int_son u_son phi_i, set (initialize) or added.
+   dune-fem / dune-geometry are un-vendored: AffineGeometry<1,2>::local(x) is taken as ((x - c0) . d) / (d . d), d = c1 - c0,
+   and the transfer arithmetic is this definition (parity unpinned; pins: linears reproduced, mass conserved). */
+void orc_project_interface_p1(const double* new_xy, const int64_t* new_off, int64_t nnew, const double* old_xy, const int32_t* old_idx,
+                              const double* dofs_old, double* dofs_new);
+
 /* ---- MMesh::ensureInterfaceMovement, 2-D (dune/mmesh/grid/mmesh.hh:920-1088) ------------------------ */
 /* Statement-by-statement restatement on index arrays.  x = current vertex coordinates, cells TDS order + perm (sub-entity
    order = id order), vflags bit0 isInterface / bit1 boundaryFlag == 1, facets = interface elements (vertex indices, facet

@@ -390,3 +390,25 @@ def ensure_interface_movement_2d(x, cells, perm, vflags, facets, iverts, ishifts
     n = nins.value
     ins = [(int(ie[i, 0]), int(ie[i, 1]), float(ip[i, 0]), float(ip[i, 1]), int(iv0[i]), int(il[i]), int(ic[i]), int(icomp[i])) for i in range(n)]
     return ("ok", bool(rc), rem[:nrem.value].tolist(), ins)
+
+
+def project_interface_p1(new_xy, new_off, old_xy, old_idx, dofs_old):
+    """interface/grid.hh:388-415 with DG-P1 data (2 nodal DOFs per segment)."""
+    new_xy, old_xy, dofs_old = _f64(new_xy).reshape(-1, 4), _f64(old_xy).reshape(-1, 4), _f64(dofs_old).reshape(-1, 2)
+    new_off = np.ascontiguousarray(new_off, np.int64); old_idx = _i32(old_idx)
+    out = np.zeros((new_xy.shape[0], 2))
+    lib().orc_project_interface_p1(_p(new_xy), _p(new_off), C.c_int64(new_xy.shape[0]), _p(old_xy), _p(old_idx), _p(dofs_old), _p(out))
+    return out
+
+
+def indicator_init_3d(xyz, cells, tris, prm):
+    xyz, cells, tris = _f64(xyz), _i32(cells), _i32(tris).reshape(-1, 3)
+    lib().orc_indicator_init_3d(_p(xyz), _p(cells), C.c_int64(cells.shape[0]), _p(tris), C.c_int64(tris.shape[0]), C.byref(prm))
+    return prm
+
+
+def mark_interface_3d(xyz, tris, prm, maxDist):
+    xyz, tris = _f64(xyz), _i32(tris).reshape(-1, 3)
+    m = np.empty(tris.shape[0], np.int8)
+    lib().orc_mark_interface_3d(_p(xyz), _p(tris), C.c_int64(tris.shape[0]), C.byref(prm), C.c_double(maxDist), _p(m))
+    return m

@@ -270,7 +270,16 @@ def test_config5_3d_8m_tets(gpu_ctx_factory, oracle):
         assert m.nc == 110 ** 3 * 6
         ctx = gpu_ctx_factory(3)
         ctx.upload_mesh(m.xyz, m.cells, m.perm, None, m.tris)
-        s = synth.shifts_uniform(m, 0.2 * m.h, 50)
+        from mmesh_b200 import capi
+        # shifts U(-0.2h, 0.2h) on the 0.15h-jittered lattice invert a few hundred tetrahedra: that is the
+        # GridError of mmesh.hh:1104-1107 (no vertex removal in 3-D); the error carries the full flag arrays
+        big = synth.shifts_uniform(m, 0.2 * m.h, 50)
+        rv, rs, rn = oracle.trial_validate(m.xyz, big, m.cells, dim=3)
+        assert rn > 0
+        with pytest.raises(capi.GridError) as ei:
+            ctx.trial_move_validate(big)
+        assert np.array_equal(ei.value.valid_fp, rv) and np.array_equal(ei.value.orient_sign, rs) and ei.value.n_invalid == rn
+        s = synth.shifts_uniform(m, 0.1 * m.h, 50)                 # a movement the reference accepts
         valid, sign, ninv = ctx.trial_move_validate(s)
         rv, rs, rn = oracle.trial_validate(m.xyz, s, m.cells, dim=3)
         assert np.array_equal(valid, rv) and np.array_equal(sign, rs) and ninv == rn == 0

@@ -604,3 +604,54 @@ def test_predicate_exponent_range(gpu_ctx_factory, oracle):
     assert ei.value.status == capi.MMB_ERR_CAPACITY
     sg, _ = ctx.predicate_batch(0, bad[:, :6])                # the same collinear triple is inside orient2d's range
     assert sg[0] == 0 == oracle.orient2d_batch(bad[:, :6])[0]
+
+
+def test_interface_projection_p1(gpu_ctx_factory, oracle):
+    """interface/grid.hh:388-415 with DG-P1 data on the segments: device == oracle bit for bit (mixed prolong / restrict
+    rows, ragged child lists, degenerate lengths)"""
+    ctx = gpu_ctx_factory(2)
+    m = _mesh1(20)
+    _upload(ctx, m)
+    rng = np.random.default_rng(6)
+    nnew, n_old = 5000, 3000
+    cnt = rng.integers(0, 5, nnew)
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    P = int(off[-1])
+    new_xy = rng.uniform(0, 1, (nnew, 4))
+    old_xy = rng.uniform(0, 1, (P, 4))
+    row = np.repeat(np.arange(nnew), cnt)
+    sub = rng.random(P) < 0.5                                            # half of the children lie inside their new element
+    ta, tb = np.sort(rng.uniform(0, 1, (2, P)), axis=0)
+    d = new_xy[row, 2:] - new_xy[row, :2]
+    old_xy[sub, :2] = (new_xy[row, :2] + ta[:, None] * d)[sub]
+    old_xy[sub, 2:] = (new_xy[row, :2] + tb[:, None] * d)[sub]
+    old_xy[::97, 2:] = old_xy[::97, :2]                                  # zero-length children
+    old_idx = rng.integers(0, n_old, P).astype(np.int32)
+    dofs = rng.uniform(-1, 1, (n_old, 2))
+    got = ctx.project_interface_p1(new_xy, off, old_xy, old_idx, dofs)
+    ref = oracle.project_interface_p1(new_xy, off, old_xy, old_idx, dofs)
+    assert np.array_equal(got, ref, equal_nan=True)
+
+
+def test_3d_indicator_init_and_interface_marks(gpu_ctx_factory, oracle):
+    """RatioIndicator::init (ratioindicator.hh:62-91) and the interface marks of markElements (mmesh.hh:745-748) in 3-D"""
+    from mmesh_b200 import synth
+    m = synth.lattice3d(14)
+    ctx = gpu_ctx_factory(3)
+    ctx.upload_mesh(m.xyz, m.cells, m.perm, None, m.tris)
+    prm = ctx.indicator_init()
+    oprm = oracle.indicator_init_3d(m.xyz, m.cells, m.tris, oracle.Params.default())
+    assert (prm.minH, prm.maxH, prm.factor) == (oprm.minH, oprm.maxH, oprm.factor) and prm.maxH > prm.minH > 0
+    d, mx = ctx.distance_update()
+    for scale in (1.0, 0.4, 0.3):
+        p = ctx.get_params(); p.maxH = prm.maxH * scale; ctx.set_params(p)
+        got = ctx.mark_interface()
+        ref = oracle.mark_interface_3d(m.xyz, m.tris, oracle.Params.from_buffer_copy(bytes(p)), p.distProportion * mx)
+        assert np.array_equal(got, ref)
+    assert 0 < (ref == 1).sum() and set(np.unique(ref)).issubset({0, 1})
+    # no interface: the bulk edges define the parameters (:84-88)
+    ctx2 = gpu_ctx_factory(3)
+    ctx2.upload_mesh(m.xyz, m.cells, m.perm, None, None)
+    p2 = ctx2.indicator_init()
+    o2 = oracle.indicator_init_3d(m.xyz, m.cells, np.zeros((0, 3), np.int32), oracle.Params.default())
+    assert (p2.minH, p2.maxH, p2.factor) == (o2.minH, o2.maxH, o2.factor)

@@ -168,3 +168,28 @@ def test_indicator_canonical_params(oracle):
     im = oracle.mark_interface_2d(m.xy, m.segs, prm, 1.0)
     ln = np.hypot(*(m.xy[m.segs[:, 1]] - m.xy[m.segs[:, 0]]).T)
     assert np.array_equal(im, np.where(ln < 0.02, -1, np.where(ln > 0.03, 1, 0)))
+
+
+def test_interface_p1_transfer_pins(oracle):
+    """MMeshInterfaceGrid::adapt(handle) with DG-P1 data (interface/grid.hh:388-415): the oracle's definition must reproduce
+    linear functions along the interface under refinement (prolong) and coarsening (restrict), conserve the mass of
+    discontinuous data, and use the reference's father choice (the longer element)."""
+    rng = np.random.default_rng(3)
+    f = lambda p: 1.5 + 2.0 * p[..., 0] - 0.7 * p[..., 1]                 # linear in the plane => linear along every segment
+    for trial in range(50):
+        a, b = rng.uniform(-1, 1, 2), rng.uniform(-1, 1, 2)
+        k = int(rng.integers(2, 6))
+        t = np.sort(np.concatenate([[0.0, 1.0], rng.uniform(0.05, 0.95, k - 1)]))
+        pts = a + t[:, None] * (b - a)
+        fine = np.concatenate([pts[:-1], pts[1:]], axis=1)                 # k segments tiling (a, b)
+        coarse = np.array([[a[0], a[1], b[0], b[1]]])
+        # refine: every new (fine) element has the coarse one as its single, longer child -> prolong
+        got = oracle.project_interface_p1(fine, np.arange(k + 1), np.repeat(coarse, k, 0), np.zeros(k, np.int32), f(coarse.reshape(1, 2, 2)))
+        assert np.max(np.abs(got - f(fine.reshape(k, 2, 2)))) <= 1e-13
+        # coarsen: the new (coarse) element has the k shorter fine ones as children -> restrict
+        got = oracle.project_interface_p1(coarse, [0, k], fine, np.arange(k, dtype=np.int32), f(fine.reshape(k, 2, 2)))
+        assert np.max(np.abs(got - f(coarse.reshape(1, 2, 2)))) <= 1e-12
+        u = rng.uniform(-1, 1, (k, 2))                                     # discontinuous data: the mass is conserved
+        got = oracle.project_interface_p1(coarse, [0, k], fine, np.arange(k, dtype=np.int32), u)
+        lens = np.linalg.norm(fine[:, 2:] - fine[:, :2], axis=1)
+        assert abs(np.linalg.norm(b - a) * got.mean() - (lens * u.mean(axis=1)).sum()) <= 1e-13
