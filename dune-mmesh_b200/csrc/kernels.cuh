@@ -1897,6 +1897,32 @@ __global__ void k_reduce_vector(const Counters* __restrict__ c, double* __restri
 }
 
 
+// mmb_patch_mesh: scatter of the changed vertices / cells / edges into the resident tables
+__global__ void __launch_bounds__(256)
+k_patch_vertices(double* __restrict__ x, int32_t* __restrict__ hint, int dim, const int32_t* __restrict__ idx, const double* __restrict__ val, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t v = idx[i];
+  for (int c = 0; c < dim; ++c) x[v * dim + c] = val[i * dim + c];
+  hint[v] = -1;                                              // the vertex moved or is new: no usable hint
+}
+__global__ void __launch_bounds__(256)
+k_patch_cells(int32_t* __restrict__ aos, int32_t* p0, int32_t* p1, int32_t* p2, int32_t* p3, uint8_t* __restrict__ perm, int k,
+              const int32_t* __restrict__ idx, const int32_t* __restrict__ val, const uint8_t* __restrict__ pval, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t c = idx[i];
+  for (int j = 0; j < k; ++j) aos[k * c + j] = val[k * i + j];
+  p0[c] = val[k * i]; p1[c] = val[k * i + 1]; p2[c] = val[k * i + 2];
+  if (k == 4) p3[c] = val[k * i + 3];
+  perm[c] = pval[i];
+}
+__global__ void __launch_bounds__(256)
+k_patch_edges(int4* __restrict__ edges, const int32_t* __restrict__ idx, const int4* __restrict__ val, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) edges[idx[i]] = val[i];
+}
+
 // AoS -> SoA transposition of the uploaded cell table
 __global__ void __launch_bounds__(256)
 k_cells_to_planes(const int32_t* __restrict__ aos, int k, int64_t nc, int64_t nc_pad, int32_t* p0, int32_t* p1,

@@ -32,6 +32,19 @@ struct DBuf {
     if (e == cudaSuccess) cap = n;
     return e;
   }
+  // grow to >= n elements keeping the first `keep` ones (device-to-device copy on `stream`)
+  cudaError_t grow(size_t n, size_t keep, cudaStream_t stream) {
+    if (n <= cap) return cudaSuccess;
+    T* q = nullptr;
+    const size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void**)&q, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) e = cudaMemcpyAsync(q, p, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (p) cudaFree(p);
+    p = q; cap = want;
+    return e;
+  }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
@@ -272,6 +285,72 @@ static uint64_t morton3(const double* c, const double* lo, const double* inv) {
   return spread(q((c[0] - lo[0]) * inv[0])) | (spread(q((c[1] - lo[1]) * inv[1])) << 1) | (spread(q((c[2] - lo[2]) * inv[2])) << 2);
 }
 
+// Everything that depends on the interface facets: original order (marks) + Morton order (BVH leaves), interface-vertex
+// flags, sorted interface-edge keys, BVH storage, and the distance hints (reset: they index the Morton order).
+static int setup_facets(mmb_context* ctx, int64_t ns, const int32_t* facets_host, const double* x_host) {
+  const int dim = ctx->dim;
+  const int64_t nv = ctx->nv;
+  ctx->ns = ns;
+  // interface facets: original order (marks) + Morton order (BVH leaves)
+  CK(ctx->facets.ensure((size_t)ns * dim + 2)); CK(ctx->facets_sorted.ensure((size_t)ns * dim + 2)); CK(ctx->imark.ensure(ns + 4));
+  int L = 1; while (L < ns) L <<= 1;
+  ctx->L = L;
+  if (ns) {
+    CK(cudaMemcpyAsync(ctx->facets.p, facets_host, (size_t)ns * dim * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, inv[3];
+    std::vector<double> mid((size_t)ns * dim);
+    for (int64_t s = 0; s < ns; ++s)
+      for (int j = 0; j < dim; ++j) {
+        double m = 0;
+        for (int c = 0; c < dim; ++c) m += x_host[(size_t)facets_host[s * dim + c] * dim + j];
+        m /= dim; mid[s * dim + j] = m; lo[j] = std::min(lo[j], m); hi[j] = std::max(hi[j], m);
+      }
+    for (int j = 0; j < dim; ++j) inv[j] = hi[j] > lo[j] ? 1.0 / (hi[j] - lo[j]) : 0.0;
+    std::vector<std::pair<uint64_t, int32_t>> keyed(ns);
+    for (int64_t s = 0; s < ns; ++s)
+      keyed[s] = { dim == 2 ? morton2(mid[2 * s], mid[2 * s + 1], lo, inv) : morton3(&mid[3 * s], lo, inv), (int32_t)s };
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<int32_t> sorted((size_t)ns * dim);
+    for (int64_t s = 0; s < ns; ++s)
+      for (int c = 0; c < dim; ++c) sorted[s * dim + c] = facets_host[(size_t)keyed[s].second * dim + c];
+    CK(cudaMemcpyAsync(ctx->facets_sorted.p, sorted.data(), sorted.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // `sorted` is a stack-owned staging buffer
+  }
+  ctx->cand_ready = false;
+  {
+    // per-vertex interface flag + sorted (min,max) keys of the interface edges: MMesh::isInterface(edge) on the device
+    // (2-D: the facets themselves, mmesh.hh:607-621; 3-D: the three edges of every interface triangle, :624-645)
+    const int64_t nk = dim == 2 ? ns : 3 * ns;
+    CK(ctx->v_if.ensure(nv + 1)); CK(ctx->cand_flag.ensure((size_t)std::max(ctx->nc_pad, ns) + 4)); CK(ctx->facet_keys.ensure(nk + 1));
+    CK(cudaMemsetAsync(ctx->v_if.p, 0, (size_t)nv, ctx->stream));
+    ctx->n_facet_keys = nk;
+    if (ns) {
+      LAUNCH("flag_interface_vertices", k_flag_interface_vertices, grid_for(dim * ns, 256), 256, ctx->facets.p, dim * ns, ctx->v_if.p);
+      std::vector<unsigned long long> keys; keys.reserve((size_t)nk);
+      auto key = [](int32_t a, int32_t b) { const unsigned x = (unsigned)std::min(a, b), y = (unsigned)std::max(a, b); return ((unsigned long long)x << 32) | y; };
+      for (int64_t s2 = 0; s2 < ns; ++s2) {
+        const int32_t* f = facets_host + (size_t)s2 * dim;
+        if (dim == 2) keys.push_back(key(f[0], f[1]));
+        else { keys.push_back(key(f[0], f[1])); keys.push_back(key(f[0], f[2])); keys.push_back(key(f[1], f[2])); }
+      }
+      std::sort(keys.begin(), keys.end());
+      CK(cudaMemcpy(ctx->facet_keys.p, keys.data(), (size_t)nk * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+  }
+  if (dim == 2) {
+    CK(ctx->seg_leaf.ensure(L)); CK(ctx->box2.ensure(2 * (size_t)L)); CK(ctx->seg_hint.ensure(nv)); CK(ctx->ticket.ensure(1));
+    CK(cudaMemsetAsync(ctx->seg_hint.p, 0xFF, (size_t)nv * sizeof(int32_t), ctx->stream));    // -1: no hint yet
+    ctx->hints_cold = true;
+    CK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
+  }
+  else {
+    CK(ctx->tri_leaf.ensure(L)); CK(ctx->box3.ensure(2 * (size_t)L)); CK(ctx->seg_hint.ensure(nv)); CK(ctx->ticket.ensure(1));
+    CK(cudaMemsetAsync(ctx->seg_hint.p, 0xFF, (size_t)nv * sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
+  }
+  return MMB_OK;
+}
+
 int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t nc, const int32_t* cells_host,
                     const uint8_t* perm_host, int64_t ne, const int32_t* edges_host, int64_t ns,
                     const int32_t* facets_host) {
@@ -332,63 +411,8 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
     if (nc) LAUNCH("tile_windows", k_tile_windows, (unsigned)ntc, 256, ctx->cv[0].p, 1, nc, nv, ctx->tile_lo_cells.p);
     if (ne) LAUNCH("tile_windows", k_tile_windows, (unsigned)nte, 256, (const int32_t*)ctx->edges.p, 4, ne, nv, ctx->tile_lo_edges.p);
   }
-  // interface facets: original order (marks) + Morton order (BVH leaves)
-  CK(ctx->facets.ensure((size_t)ns * dim + 2)); CK(ctx->facets_sorted.ensure((size_t)ns * dim + 2)); CK(ctx->imark.ensure(ns + 4));
-  int L = 1; while (L < ns) L <<= 1;
-  ctx->L = L;
-  if (ns) {
-    CK(cudaMemcpyAsync(ctx->facets.p, facets_host, (size_t)ns * dim * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, inv[3];
-    std::vector<double> mid((size_t)ns * dim);
-    for (int64_t s = 0; s < ns; ++s)
-      for (int j = 0; j < dim; ++j) {
-        double m = 0;
-        for (int c = 0; c < dim; ++c) m += x_host[(size_t)facets_host[s * dim + c] * dim + j];
-        m /= dim; mid[s * dim + j] = m; lo[j] = std::min(lo[j], m); hi[j] = std::max(hi[j], m);
-      }
-    for (int j = 0; j < dim; ++j) inv[j] = hi[j] > lo[j] ? 1.0 / (hi[j] - lo[j]) : 0.0;
-    std::vector<std::pair<uint64_t, int32_t>> keyed(ns);
-    for (int64_t s = 0; s < ns; ++s)
-      keyed[s] = { dim == 2 ? morton2(mid[2 * s], mid[2 * s + 1], lo, inv) : morton3(&mid[3 * s], lo, inv), (int32_t)s };
-    std::sort(keyed.begin(), keyed.end());
-    std::vector<int32_t> sorted((size_t)ns * dim);
-    for (int64_t s = 0; s < ns; ++s)
-      for (int c = 0; c < dim; ++c) sorted[s * dim + c] = facets_host[(size_t)keyed[s].second * dim + c];
-    CK(cudaMemcpyAsync(ctx->facets_sorted.p, sorted.data(), sorted.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));   // `sorted` is a stack-owned staging buffer
-  }
-  ctx->have_nb = false; ctx->cand_ready = false; ctx->have_levels = false;
-  {
-    // per-vertex interface flag + sorted (min,max) keys of the interface edges: MMesh::isInterface(edge) on the device
-    // (2-D: the facets themselves, mmesh.hh:607-621; 3-D: the three edges of every interface triangle, :624-645)
-    const int64_t nk = dim == 2 ? ns : 3 * ns;
-    CK(ctx->v_if.ensure(nv + 1)); CK(ctx->cand_flag.ensure((size_t)std::max(ctx->nc_pad, ns) + 4)); CK(ctx->facet_keys.ensure(nk + 1));
-    CK(cudaMemsetAsync(ctx->v_if.p, 0, (size_t)nv, ctx->stream));
-    ctx->n_facet_keys = nk;
-    if (ns) {
-      LAUNCH("flag_interface_vertices", k_flag_interface_vertices, grid_for(dim * ns, 256), 256, ctx->facets.p, dim * ns, ctx->v_if.p);
-      std::vector<unsigned long long> keys; keys.reserve((size_t)nk);
-      auto key = [](int32_t a, int32_t b) { const unsigned x = (unsigned)std::min(a, b), y = (unsigned)std::max(a, b); return ((unsigned long long)x << 32) | y; };
-      for (int64_t s2 = 0; s2 < ns; ++s2) {
-        const int32_t* f = facets_host + (size_t)s2 * dim;
-        if (dim == 2) keys.push_back(key(f[0], f[1]));
-        else { keys.push_back(key(f[0], f[1])); keys.push_back(key(f[0], f[2])); keys.push_back(key(f[1], f[2])); }
-      }
-      std::sort(keys.begin(), keys.end());
-      CK(cudaMemcpy(ctx->facet_keys.p, keys.data(), (size_t)nk * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-    }
-  }
-  if (dim == 2) {
-    CK(ctx->seg_leaf.ensure(L)); CK(ctx->box2.ensure(2 * (size_t)L)); CK(ctx->seg_hint.ensure(nv)); CK(ctx->ticket.ensure(1));
-    CK(cudaMemsetAsync(ctx->seg_hint.p, 0xFF, (size_t)nv * sizeof(int32_t), ctx->stream));    // -1: no hint yet
-    ctx->hints_cold = true;
-    CK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
-  }
-  else {
-    CK(ctx->tri_leaf.ensure(L)); CK(ctx->box3.ensure(2 * (size_t)L)); CK(ctx->seg_hint.ensure(nv)); CK(ctx->ticket.ensure(1));
-    CK(cudaMemsetAsync(ctx->seg_hint.p, 0xFF, (size_t)nv * sizeof(int32_t), ctx->stream));
-    CK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
-  }
+  ctx->have_nb = false; ctx->have_levels = false;
+  TRY(setup_facets(ctx, ns, facets_host, x_host));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   ctx->has_shift = false; ctx->dist_valid = false; ctx->mesh_ok = true;
@@ -409,6 +433,122 @@ int mmb_download_coords(mmb_context* ctx, double* x_host) {
   REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
   CK(cudaMemcpyAsync(x_host, ctx->x.p, (size_t)ctx->nv * ctx->dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return MMB_OK;
+}
+// Incremental snapshot update after a small TDS edit (what adapt_() changes, mmesh.hh:1338-1355): only the listed vertices,
+// cells and edges are transferred; the resident arrays grow in place; per-vertex distance hints of untouched vertices survive
+// when the interface is unchanged, so the next Distance::update starts warm.
+int mmb_patch_mesh(mmb_context* ctx, int64_t nv_new, int64_t n_vert, const int32_t* vert_idx_host, const double* vert_x_host,
+                   int64_t nc_new, int64_t n_cell, const int32_t* cell_idx_host, const int32_t* cell_v_host, const uint8_t* cell_perm_host,
+                   int64_t ne_new, int64_t n_edge, const int32_t* edge_idx_host, const int32_t* edge_q_host,
+                   int64_t ns_new, const int32_t* facets_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "mmb_patch_mesh needs an uploaded mesh");
+  const int dim = ctx->dim, k = dim + 1;
+  REQUIRE(nv_new > 0 && nc_new >= 0 && ne_new >= 0 && n_vert >= 0 && n_cell >= 0 && n_edge >= 0 && (n_vert == 0 || (vert_idx_host && vert_x_host)) &&
+          (n_cell == 0 || (cell_idx_host && cell_v_host && cell_perm_host)) && (n_edge == 0 || (dim == 2 && edge_idx_host && edge_q_host)),
+          MMB_ERR_INVALID_ARG, "mmb_patch_mesh: bad sizes or null arrays");
+  REQUIRE(nv_new < (1ll << 31) && nc_new < (1ll << 31) && ne_new < (1ll << 31), MMB_ERR_CAPACITY, "mmb_patch_mesh: int32 index space exceeded");
+  REQUIRE(dim == 2 || ne_new == 0, MMB_ERR_INVALID_ARG, "mmb_patch_mesh: edges are a 2-D concept");
+  const int64_t nv0 = ctx->nv, nc0 = ctx->nc, ne0 = ctx->ne;
+  {  // the kernels trust the snapshot: validate the patch here; every index beyond the old sizes must be supplied
+    int64_t bad = 0;
+    std::vector<uint8_t> seen_v((size_t)std::max<int64_t>(nv_new - nv0, 0), 0), seen_c((size_t)std::max<int64_t>(nc_new - nc0, 0), 0),
+        seen_e((size_t)std::max<int64_t>(ne_new - ne0, 0), 0);
+    for (int64_t i = 0; i < n_vert; ++i) { const int64_t v = vert_idx_host[i]; if (v < 0 || v >= nv_new) ++bad; else if (v >= nv0) seen_v[(size_t)(v - nv0)] = 1; }
+    for (int64_t i = 0; i < n_cell; ++i) {
+      const int64_t c = cell_idx_host[i];
+      if (c < 0 || c >= nc_new) ++bad; else if (c >= nc0) seen_c[(size_t)(c - nc0)] = 1;
+      unsigned seen = 0;
+      for (int j = 0; j < k; ++j) { bad += (cell_v_host[k * i + j] < 0 || cell_v_host[k * i + j] >= nv_new); seen |= 1u << ((cell_perm_host[i] >> (2 * j)) & 3u); }
+      bad += (seen != (1u << k) - 1u);
+    }
+    for (int64_t i = 0; i < n_edge; ++i) {
+      const int64_t e = edge_idx_host[i];
+      if (e < 0 || e >= ne_new) ++bad; else if (e >= ne0) seen_e[(size_t)(e - ne0)] = 1;
+      const int32_t* q = edge_q_host + 4 * i;
+      bad += (q[0] < 0 || q[0] >= nv_new || q[1] < 0 || q[1] >= nv_new || q[2] < 0 || q[2] >= nv_new || q[3] < -1 || q[3] >= nv_new);
+    }
+    for (uint8_t f : seen_v) bad += !f;
+    for (uint8_t f : seen_c) bad += !f;
+    for (uint8_t f : seen_e) bad += !f;
+    if (facets_host) for (int64_t i = 0; i < ns_new * dim; ++i) bad += (facets_host[i] < 0 || facets_host[i] >= nv_new);
+    REQUIRE(bad == 0, MMB_ERR_INVALID_ARG, "mmb_patch_mesh: index out of range, invalid corner permutation, or a new index without data");
+    REQUIRE(facets_host || ctx->ns == 0 || nv_new >= nv0, MMB_ERR_INVALID_ARG, "mmb_patch_mesh: shrinking the vertex set needs the facet list (its indices may be stale)");
+  }
+  cudaStream_t S = ctx->stream;
+  const int64_t nc_pad_new = (nc_new + 3) / 4 * 4;
+  // resident data that must survive: grow in place
+  CK(ctx->x.grow((size_t)nv_new * dim + 2, (size_t)nv0 * dim, S)); CK(ctx->seg_hint.grow((size_t)nv_new, (size_t)nv0, S));
+  CK(ctx->v_if.grow((size_t)nv_new + 1, (size_t)nv0, S));
+  for (int j = 0; j < k; ++j) CK(ctx->cv[j].grow((size_t)nc_pad_new + 4, (size_t)nc0, S));
+  CK(ctx->cells_aos.grow((size_t)nc_new * k + 4, (size_t)nc0 * k, S)); CK(ctx->perm.grow((size_t)nc_pad_new + 4, (size_t)nc0, S));
+  if (dim == 2) CK(ctx->edges.grow((size_t)ne_new + 1, (size_t)ne0, S));
+  // outputs / scratch: contents need not survive
+  CK(ctx->shift.ensure((size_t)nv_new * dim + 2)); CK(ctx->dist.ensure((size_t)nv_new));
+  CK(ctx->valid_fp.ensure(nc_pad_new + 4)); CK(ctx->orient.ensure(nc_pad_new + 4)); CK(ctx->mark.ensure(nc_pad_new + 4)); CK(ctx->longest.ensure(nc_pad_new + 4));
+  CK(ctx->wl.ensure(std::max(nc_pad_new, ne_new) + 4)); CK(ctx->list_out.ensure(std::max(nc_pad_new, ne_new) + 4));
+  CK(ctx->block_count.ensure((std::max(nc_pad_new, ne_new) + COMPACT_TILE - 1) / COMPACT_TILE + 1));
+  CK(ctx->cand_flag.ensure((size_t)std::max(nc_pad_new, std::max(ns_new, ctx->ns)) + 4));
+  if (dim == 2) CK(ctx->edge_flag.ensure(ne_new + 4));
+  if (nv_new > nv0) {
+    CK(cudaMemsetAsync(ctx->seg_hint.p + nv0, 0xFF, (size_t)(nv_new - nv0) * sizeof(int32_t), S));
+    CK(cudaMemsetAsync(ctx->v_if.p + nv0, 0, (size_t)(nv_new - nv0), S));
+  }
+  // scatter the patch (staged through temporary device buffers)
+  DBuf<int32_t> d_idx, d_val; DBuf<double> d_x; DBuf<uint8_t> d_perm;
+  auto release = [&]() { d_idx.release(); d_val.release(); d_x.release(); d_perm.release(); };
+  auto fail = [&](cudaError_t e) { ctx->err = cudaGetErrorString(e); release(); return (int)MMB_ERR_CUDA; };
+  cudaError_t e;
+  if (n_vert) {
+    if ((e = d_idx.ensure(n_vert)) || (e = d_x.ensure((size_t)n_vert * dim))) return fail(e);
+    cudaMemcpyAsync(d_idx.p, vert_idx_host, (size_t)n_vert * 4, cudaMemcpyHostToDevice, S);
+    cudaMemcpyAsync(d_x.p, vert_x_host, (size_t)n_vert * dim * 8, cudaMemcpyHostToDevice, S);
+    LAUNCH("patch_vertices", k_patch_vertices, grid_for(n_vert, 256), 256, ctx->x.p, ctx->seg_hint.p, dim, d_idx.p, d_x.p, n_vert);
+    if ((e = cudaStreamSynchronize(S)) != cudaSuccess) return fail(e);
+  }
+  if (n_cell) {
+    if ((e = d_idx.ensure(n_cell)) || (e = d_val.ensure((size_t)n_cell * k)) || (e = d_perm.ensure(n_cell))) return fail(e);
+    cudaMemcpyAsync(d_idx.p, cell_idx_host, (size_t)n_cell * 4, cudaMemcpyHostToDevice, S);
+    cudaMemcpyAsync(d_val.p, cell_v_host, (size_t)n_cell * k * 4, cudaMemcpyHostToDevice, S);
+    cudaMemcpyAsync(d_perm.p, cell_perm_host, (size_t)n_cell, cudaMemcpyHostToDevice, S);
+    LAUNCH("patch_cells", k_patch_cells, grid_for(n_cell, 256), 256, ctx->cells_aos.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, k == 4 ? ctx->cv[3].p : nullptr,
+           ctx->perm.p, k, d_idx.p, d_val.p, d_perm.p, n_cell);
+    if ((e = cudaStreamSynchronize(S)) != cudaSuccess) return fail(e);
+  }
+  for (int j = 0; j < k; ++j)                                // padding cells reference vertex 0 (4 cells per thread in k_validate2d)
+    CK(cudaMemsetAsync(ctx->cv[j].p + nc_new, 0, (size_t)(nc_pad_new + 4 - nc_new) * sizeof(int32_t), S));
+  if (n_edge) {
+    if ((e = d_idx.ensure(n_edge)) || (e = d_val.ensure((size_t)n_edge * 4))) return fail(e);
+    cudaMemcpyAsync(d_idx.p, edge_idx_host, (size_t)n_edge * 4, cudaMemcpyHostToDevice, S);
+    cudaMemcpyAsync(d_val.p, edge_q_host, (size_t)n_edge * 16, cudaMemcpyHostToDevice, S);
+    LAUNCH("patch_edges", k_patch_edges, grid_for(n_edge, 256), 256, ctx->edges.p, d_idx.p, (const int4*)d_val.p, n_edge);
+    if ((e = cudaStreamSynchronize(S)) != cudaSuccess) return fail(e);
+  }
+  release();
+  ctx->nv = nv_new; ctx->nc = nc_new; ctx->ne = ne_new; ctx->nc_pad = nc_pad_new;
+  ctx->own_lo = 0; ctx->own_hi = nc_new;
+  if (dim == 2) {                                              // Hilbert tile windows of the new tables
+    const int64_t ntc = (nc_pad_new + TILE - 1) / TILE, nte = (ne_new + TILE - 1) / TILE;
+    CK(ctx->tile_lo_cells.ensure(ntc + 1)); CK(ctx->tile_lo_edges.ensure(nte + 1));
+    CK(cudaMemsetAsync(ctx->tile_lo_cells.p, 0, (ntc + 1) * sizeof(int32_t), S));
+    CK(cudaMemsetAsync(ctx->tile_lo_edges.p, 0, (nte + 1) * sizeof(int32_t), S));
+    if (nc_new) LAUNCH("tile_windows", k_tile_windows, (unsigned)ntc, 256, ctx->cv[0].p, 1, nc_new, nv_new, ctx->tile_lo_cells.p);
+    if (ne_new) LAUNCH("tile_windows", k_tile_windows, (unsigned)nte, 256, (const int32_t*)ctx->edges.p, 4, ne_new, nv_new, ctx->tile_lo_edges.p);
+  }
+  if (facets_host || (ns_new == 0 && ctx->ns != 0)) {          // the interface changed: rebuild what hangs on it (hints start cold)
+    std::vector<double> xh((size_t)nv_new * dim);
+    CK(cudaMemcpyAsync(xh.data(), ctx->x.p, xh.size() * sizeof(double), cudaMemcpyDeviceToHost, S));
+    CK(cudaStreamSynchronize(S));
+    TRY(setup_facets(ctx, ns_new, facets_host, xh.data()));
+  } else {
+    REQUIRE(ns_new == ctx->ns, MMB_ERR_INVALID_ARG, "mmb_patch_mesh: ns changed but no facet list given");
+    if (n_vert) ctx->hints_cold = true;                        // patched vertices lost their hints: they take a seed-grid facet
+  }
+  CK(cudaStreamSynchronize(S));
+  CK(cudaGetLastError());
+  ctx->has_shift = false; ctx->dist_valid = false; ctx->have_nb = false; ctx->have_levels = false; ctx->cand_ready = false;
+  ctx->nnew = ctx->npairs = 0; ctx->graph_valid = false; ctx->sharded_steps = 0; ctx->n_halo_send = ctx->n_halo_recv = 0;
   return MMB_OK;
 }
 int mmb_upload_shifts(mmb_context* ctx, const double* shifts_host) {

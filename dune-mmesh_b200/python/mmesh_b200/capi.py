@@ -14,7 +14,7 @@ MMB_OK, MMB_ERR_INVALID_ARG, MMB_ERR_CUDA, MMB_ERR_NCCL, MMB_ERR_INVALID_CELL_3D
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "NCCL error", 4: "invalid 3-D cell", 5: "capacity", 6: "state"}
 
 EXPORTS = [
-    "mmb_create", "mmb_destroy", "mmb_last_error", "mmb_stream", "mmb_synchronize", "mmb_upload_mesh",
+    "mmb_create", "mmb_destroy", "mmb_last_error", "mmb_stream", "mmb_synchronize", "mmb_upload_mesh", "mmb_patch_mesh",
     "mmb_upload_coords", "mmb_download_coords", "mmb_upload_shifts", "mmb_scale_shifts", "mmb_set_params", "mmb_get_params",
     "mmb_indicator_init", "mmb_move_vertices", "mmb_trial_move_validate", "mmb_invalid_cells", "mmb_legality",
     "mmb_distance_update", "mmb_distance_set", "mmb_mark_elements", "mmb_mark_interface", "mmb_marked_cells",
@@ -130,6 +130,21 @@ class Context:
         self.ns = 0 if facets is None else facets.shape[0]
         self._ck(lib().mmb_upload_mesh(self._h, C.c_int64(self.nv), _p(x), C.c_int64(self.nc), _p(cells), _p(perm),
                                        C.c_int64(self.ne), _p(edges), C.c_int64(self.ns), _p(facets)))
+
+    def patch_mesh(self, nv, vert_idx, vert_x, nc, cell_idx, cell_v, cell_perm, ne=0, edge_idx=None, edge_q=None, facets=None, ns=None):
+        """incremental snapshot update (mmb_patch_mesh): only the listed vertices / cells / edges are transferred"""
+        vi, vx = _i32(vert_idx), _f64(vert_x)
+        ci, cv = _i32(cell_idx), _i32(cell_v)
+        cp = np.ascontiguousarray(cell_perm, np.uint8)
+        ei = _i32(edge_idx) if edge_idx is not None else None
+        eq = _i32(edge_q) if edge_q is not None else None
+        fc = _i32(facets) if facets is not None else None
+        ns_new = self.ns if ns is None and fc is None else (fc.shape[0] if fc is not None else ns)
+        self._ck(lib().mmb_patch_mesh(self._h, C.c_int64(nv), C.c_int64(vi.shape[0]), _p(vi) if vi.size else None, _p(vx) if vi.size else None,
+                                      C.c_int64(nc), C.c_int64(ci.shape[0]), _p(ci) if ci.size else None, _p(cv) if ci.size else None, _p(cp) if ci.size else None,
+                                      C.c_int64(ne), C.c_int64(0 if ei is None else ei.shape[0]), None if ei is None or not ei.size else _p(ei),
+                                      None if eq is None or not eq.size else _p(eq), C.c_int64(ns_new), None if fc is None else _p(fc)))
+        self.nv, self.nc, self.ne, self.ns = nv, nc, ne, ns_new
 
     def upload_coords(self, x):
         x = _f64(x)

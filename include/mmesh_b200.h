@@ -92,6 +92,17 @@ int mmb_host_unregister(mmb_context* ctx, void* ptr);
 int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t nc, const int32_t* cells_host,
                     const uint8_t* perm_host, int64_t ne, const int32_t* edges_host, int64_t ns,
                     const int32_t* facets_host);
+/* Incremental snapshot update after a small TDS edit -- what adapt_() changes (mmesh.hh:1338-1355: a few inserted / removed
+   vertices, the cells of their conflict zones, the index sets): only the listed entries cross the host link, the resident tables
+   grow in place, and the per-vertex distance hints of untouched vertices survive when the interface is unchanged (the next
+   Distance::update starts warm).  New sizes nv/nc/ne/ns; vert_idx / vert_x: changed or new vertices; cell_idx / cell_v [n][dim+1]
+   / cell_perm: changed or new cells; edge_idx / edge_q [n][4]: changed or new edge quads (2-D); every index >= the old size must
+   be listed.  facets = the full new interface list, or NULL when the interface is unchanged (ns_new must then equal the old ns).
+   Afterwards: shifts, neighbours, vertex levels, pairs and halo lists must be supplied again, like after mmb_upload_mesh. */
+int mmb_patch_mesh(mmb_context* ctx, int64_t nv_new, int64_t n_vert, const int32_t* vert_idx_host, const double* vert_x_host,
+                   int64_t nc_new, int64_t n_cell, const int32_t* cell_idx_host, const int32_t* cell_v_host, const uint8_t* cell_perm_host,
+                   int64_t ne_new, int64_t n_edge, const int32_t* edge_idx_host, const int32_t* edge_q_host,
+                   int64_t ns_new, const int32_t* facets_host);
 int mmb_upload_coords(mmb_context* ctx, const double* x_host);      /* vh->point() = ... for every vertex */
 int mmb_download_coords(mmb_context* ctx, double* x_host);
 int mmb_upload_shifts(mmb_context* ctx, const double* shifts_host); /* make `shifts` resident */

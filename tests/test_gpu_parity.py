@@ -598,13 +598,16 @@ def test_predicate_exponent_range(gpu_ctx_factory, oracle):
         assert np.array_equal(si, oracle.incircle_batch(q))
         so, _ = ctx.predicate_batch(0, q[:, :6])
         assert np.array_equal(so, oracle.orient2d_batch(q[:, :6]))
-    bad = np.array([[0.0, 0.0, 1.0, 2.0 ** -230, 2.0, 2.0 ** -229, 1.0, 1.0]])
+    # a rectangle (cocircular corners) whose sides differ by 2^230: filter and interval abstain, the exact stage cannot hold it
+    a, b = 1.0 / 3.0, (1.0 / 3.0) * 2.0 ** -230
+    bad = np.array([[0.0, 0.0, a, 0.0, a, b, 0.0, b]])
     with pytest.raises(capi.MMeshError) as ei:
         ctx.predicate_batch(1, bad)
     assert ei.value.status == capi.MMB_ERR_CAPACITY
-    sg, _ = ctx.predicate_batch(0, bad[:, :6])                # the same collinear triple is inside orient2d's range
-    assert sg[0] == 0 == oracle.orient2d_batch(bad[:, :6])[0]
-
+    b2 = a * 2.0 ** -200                                      # the same rectangle inside the range: decided exactly (0)
+    ok = np.array([[0.0, 0.0, a, 0.0, a, b2, 0.0, b2]])
+    sg, nex = ctx.predicate_batch(1, ok)
+    assert sg[0] == 0 == oracle.incircle_batch(ok)[0] and nex == 1
 
 def test_interface_projection_p1(gpu_ctx_factory, oracle):
     """interface/grid.hh:388-415 with DG-P1 data on the segments: device == oracle bit for bit (mixed prolong / restrict
@@ -655,3 +658,77 @@ def test_3d_indicator_init_and_interface_marks(gpu_ctx_factory, oracle):
     p2 = ctx2.indicator_init()
     o2 = oracle.indicator_init_3d(m.xyz, m.cells, np.zeros((0, 3), np.int32), oracle.Params.default())
     assert (p2.minH, p2.maxH, p2.factor) == (o2.minH, o2.maxH, o2.factor)
+
+
+def test_patch_mesh_equals_full_upload(gpu_ctx_factory, oracle):
+    """mmb_patch_mesh (incremental snapshot update after a small TDS edit): edge-midpoint insertions patched into the resident
+    snapshot give the same fields as a context that uploads the edited mesh from scratch -- with the interface unchanged
+    (hints of untouched vertices survive) and with a changed interface (hints rebuilt)."""
+    from mmesh_b200 import synth
+    m = synth.config1(n=40)
+    rng = np.random.default_rng(17)
+    nv0, nc0 = m.nv, m.nc
+    cells = m.cells.astype(np.int64).copy()
+    ids = m.vid.astype(np.int64)
+    key = {tuple(sorted(t)): i for i, t in enumerate(cells.tolist())}
+    inner = np.nonzero(m.edges[:, 3] >= 0)[0]
+    rng.shuffle(inner)
+    touched = np.zeros(nc0, bool)
+    new_pts, new_ids, app = [], [], []
+    segset = {tuple(sorted(s)) for s in m.segs.tolist()}
+    for e in inner:
+        if len(new_pts) == 60:
+            break
+        a, b, c, d = (int(t) for t in m.edges[e])
+        if tuple(sorted((a, b))) in segset:
+            continue                                              # bulk insertions only: the interface stays as it is
+        L, R = key[tuple(sorted((a, b, c)))], key[tuple(sorted((a, b, d)))]
+        if touched[L] or touched[R]:
+            continue
+        touched[[L, R]] = True
+        mid = nv0 + len(new_pts)
+        new_pts.append(m.xy[a] + 0.5 * (m.xy[b] - m.xy[a])); new_ids.append(int(ids.max()) + 1 + len(new_ids))
+        cells[L] = (a, mid, c); cells[R] = (b, mid, d)            # two of the four new cells replace the old ones in place ...
+        app += [(mid, b, c), (mid, a, d)]                         # ... two are appended
+    xy1 = np.concatenate([m.xy, np.array(new_pts)])
+    id1 = np.concatenate([ids, np.array(new_ids, np.int64)])
+    cells1 = np.concatenate([cells, np.array(app, np.int64)]).astype(np.int32)
+    perm1 = synth.pack_perm(id1[cells1])
+    edges1, _, _ = synth.build_edges(cells1, xy1.shape[0])
+    ne0, ne1 = m.edges.shape[0], edges1.shape[0]
+    common = min(ne0, ne1)
+    ech = np.concatenate([np.nonzero((edges1[:common] != m.edges[:common]).any(axis=1))[0], np.arange(common, ne1)]).astype(np.int32)
+    cch = np.concatenate([np.nonzero(touched)[0], np.arange(nc0, cells1.shape[0])]).astype(np.int32)
+    vch = np.arange(nv0, xy1.shape[0], dtype=np.int32)
+    assert ne1 >= ne0 and len(new_pts) == 60
+
+    def fields(ctx):
+        prm = ctx.indicator_init()
+        d, mx = ctx.distance_update()
+        marks, le, counts = ctx.mark_elements(run_distance=False)
+        valid, sign, ninv = ctx.trial_move_validate(np.zeros_like(xy1))
+        flags, nill = ctx.legality()
+        return dict(prm=bytes(prm), d=d, mx=mx, marks=marks, le=le, valid=valid, sign=sign, flags=flags, nill=nill, imarks=ctx.mark_interface())
+
+    fresh = gpu_ctx_factory(2)
+    fresh.upload_mesh(xy1, cells1, perm1, edges1, m.segs)
+    want = fields(fresh)
+    ctx = gpu_ctx_factory(2)
+    _upload(ctx, m)
+    ctx.distance_update()                                          # hints of the old mesh
+    ctx.patch_mesh(xy1.shape[0], vch, xy1[vch], cells1.shape[0], cch, cells1[cch], perm1[cch], ne1, ech, edges1[ech])
+    got = fields(ctx)
+    for k in want:
+        assert np.array_equal(got[k], want[k]) if isinstance(want[k], np.ndarray) else got[k] == want[k], k
+    assert np.array_equal(got["d"], oracle.distance_2d(xy1, m.segs))
+    # a patch that also changes the interface (one facet dropped) and moves a vertex
+    segs2 = m.segs[:-1]
+    xy2 = xy1.copy(); xy2[5] += 1e-3 * m.h
+    fresh2 = gpu_ctx_factory(2)
+    fresh2.upload_mesh(xy2, cells1, perm1, edges1, segs2)
+    want2 = fields(fresh2)
+    ctx.patch_mesh(xy2.shape[0], np.array([5], np.int32), xy2[[5]], cells1.shape[0], np.zeros(0, np.int32), np.zeros((0, 3), np.int32), np.zeros(0, np.uint8),
+                   ne1, None, None, facets=segs2)
+    got2 = fields(ctx)
+    for k in want2:
+        assert np.array_equal(got2[k], want2[k]) if isinstance(want2[k], np.ndarray) else got2[k] == want2[k], k
