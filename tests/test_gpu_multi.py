@@ -61,7 +61,8 @@ def test_cpp_two_rank_driver(tmp_path):
         procs = [subprocess.Popen([SHARD_EXE, str(f), str(r), "2", idf], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
         outs = [p.communicate(timeout=300) for p in procs]
         assert all(p.returncode == 0 for p in procs), [o[1][-2000:] for o in outs]
-        rows = [dict(zip(o[0].split()[2::2], o[0].split()[3::2])) for o in outs]
+        lines = [[ln for ln in o[0].splitlines() if ln.startswith("rank ")][-1] for o in outs]     # (NCCL may print its version first)
+        rows = [dict(zip(ln.split()[2::2], ln.split()[3::2])) for ln in lines]
         ref = capi.Context(2, 0)
         ref.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
         p2 = ref.get_params(); p2.minH, p2.maxH, p2.factor, p2.drop_area, p2.move_policy = minH, maxH, factor, 1e-12, policy; ref.set_params(p2)
