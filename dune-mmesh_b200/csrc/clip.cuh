@@ -66,18 +66,8 @@ MMB_HD int clip_stage_core(Load load, int n, double dQx, double dQy, double q2xq
   const unsigned c1 = Pm & Nj, c2 = Nm & Pj & ~c1, c3 = Gm & Pj & ~(c1 | c2);
   const int e1 = mmb_ffs(c1) - 1, e2 = mmb_ffs(c2) - 1;      // a convex polygon has at most one edge of each kind
   double2 X1 = make_double2(0.0, 0.0), X2 = X1;
-  if ((e1 | e2) >= 0) {
-    // the usual case when the clip line cuts the polygon: it enters and leaves, one crossing of each kind.  Both points
-    // are computed in one block so that their four independent divisions overlap (same operations, same bits).
-    double ax, ay, bx, by, cx, cy, dx, dy;
-    load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by);
-    load(e2, cx, cy); load(e2 + 1 == n ? 0 : e2 + 1, dx, dy);
-    X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq);
-    X2 = line_isect(cx, cy, dx, dy, iQx, iQy, fq);
-  } else {
-    if (e1 >= 0) { double ax, ay, bx, by; load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by); X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
-    if (e2 >= 0) { double ax, ay, bx, by; load(e2, ax, ay); load(e2 + 1 == n ? 0 : e2 + 1, bx, by); X2 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
-  }
+  if (e1 >= 0) { double ax, ay, bx, by; load(e1, ax, ay); load(e1 + 1 == n ? 0 : e1 + 1, bx, by); X1 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
+  if (e2 >= 0) { double ax, ay, bx, by; load(e2, ax, ay); load(e2 + 1 == n ? 0 : e2 + 1, bx, by); X2 = line_isect(ax, ay, bx, by, iQx, iQy, fq); }
   // pass 3: emission in edge order (pure data movement): c1 -> X, second; c2 -> X; c3 -> nothing; otherwise -> second.
   const unsigned keep = ~(c2 | c3);
   if (CAP < NMAX + NMAX / 2) {

@@ -779,10 +779,10 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
           const int32_t* __restrict__ old_idx, const double* __restrict__ dofs_old, double* __restrict__ dofs_new,
           DevParams prm, double* __restrict__ part_mass, double* __restrict__ part_cov, Counters* __restrict__ cnt) {
   __shared__ double2 sP[6][PROJ_THREADS];      // subject triangle, then output of clip edge 1 (<= 6)
-  __shared__ double2 sQ[UNR >= 2 ? 6 : 9][PROJ_THREADS];      // outputs of clip edges 0 (<= 4) and 2 (<= 9; UNR >= 2: <= 6, else generic path)
+  __shared__ double2 sQ[(UNR == 2 || UNR == 3) ? 6 : 9][PROJ_THREADS];      // outputs of clip edges 0 (<= 4) and 2 (<= 9; UNR >= 2: <= 6, else generic path)
   // UNR < 2: the new cell's TDS-order corners e0, e1, e2, e0 (clip edge st = (sE[st], sE[st+1]));
   // UNR >= 2: per clip edge st the constants dQx, dQy, q2xq1 (rows 3 st ..), hoisted out of the pair loop
-  __shared__ double sCell[UNR >= 2 ? 9 : 8][PROJ_THREADS];
+  __shared__ double sCell[(UNR == 2 || UNR == 3) ? 9 : 8][PROJ_THREADS];
   double2 (*sE)[PROJ_THREADS] = reinterpret_cast<double2 (*)[PROJ_THREADS]>(&sCell[0][0]);
   double (*sEC)[PROJ_THREADS] = sCell;
   __shared__ double2 sG[3][PROJ_THREADS];      // the new cell's inverse affine map (origin, J^-T rows), used by the fan only
@@ -815,7 +815,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
       sG[0][tid] = make_double2(gK.ox, gK.oy); sG[1][tid] = make_double2(gK.i00, gK.i01); sG[2][tid] = make_double2(gK.i10, gK.i11);
     }
   }
-  if (UNR >= 2) {
+  if (UNR == 2 || UNR == 3) {
 #pragma unroll
     for (int st = 0; st < 3; ++st) {
       const int sn = st == 2 ? 0 : st + 1;
@@ -858,7 +858,7 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
       sP[0][tid] = make_double2(cx[0], cy[0]);
       sP[1][tid] = sw ? make_double2(cx[2], cy[2]) : make_double2(cx[1], cy[1]);
       sP[2][tid] = sw ? make_double2(cx[1], cy[1]) : make_double2(cx[2], cy[2]);
-      if (UNR >= 2) {                                       // clip-edge constants hoisted per new cell (sEC)
+      if (UNR == 2 || UNR == 3) {                                       // clip-edge constants hoisted per new cell (sEC)
         auto ldP = [&](int k, double& x, double& y) { const double2 v = sP[k][tid]; x = v.x; y = v.y; };
         auto ldQ = [&](int k, double& x, double& y) { const double2 v = sQ[k][tid]; x = v.x; y = v.y; };
         auto stP = [&](int k, double x, double y) { sP[k][tid] = make_double2(x, y); };
@@ -908,13 +908,13 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
         uj = 0.0; f1 = 0.0; f2 = 0.0;
         if (NCOMP == 3) {
           const double d0 = P.x - gO.ox, d1 = P.y - gO.oy;
-          uj = u0 + (d0 * gx + d1 * gy);                       // affine old function: u0 + grad . (x - o)
           const double e0 = P.x - gK.ox, e1 = P.y - gK.oy;
+          uj = u0 + (d0 * gx + d1 * gy);                       // affine old function: u0 + grad . (x - o)
           f1 = e0 * gK.i00 + e1 * gK.i10;                      // barycentric coordinates in the new cell
           f2 = e0 * gK.i01 + e1 * gK.i11;
         }
       };
-      if (NCOMP == 3 && UNR >= 2) {
+      if (NCOMP == 3 && (UNR == 2 || UNR == 3)) {
         unsigned np = 0;
         if (nC >= 3)
           proj_fan<UNR == 3>([&](int k) { return sC[k][tid]; }, nC, u0, gx, gy, gO.ox, gO.oy, make_double2(gK.ox, gK.oy),
@@ -949,9 +949,9 @@ k_project(const double2* __restrict__ xy, const int32_t* __restrict__ cv0, const
             } else {
               const double su = fu + pu + uj;
               const double s1 = ff1 + pf1 + f1, s2 = ff2 + pf2 + f2;
+              const double w12 = aT * (1.0 / 12.0);
               const double d1 = fu * ff1 + pu * pf1 + uj * f1;
               const double d2 = fu * ff2 + pu * pf2 + uj * f2;
-              const double w12 = aT * (1.0 / 12.0);
               r1 += w12 * (su * s1 + d1);
               r2 += w12 * (su * s2 + d2);
               u += (aT * (1.0 / 3.0)) * su;
