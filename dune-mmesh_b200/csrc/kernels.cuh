@@ -13,6 +13,7 @@
 #include "clip.cuh"
 #include "geom.cuh"
 #include "project.cuh"
+#include "flip.cuh"
 
 namespace mmb {
 
@@ -1932,6 +1933,88 @@ k_cells_to_planes(const int32_t* __restrict__ aos, int k, int64_t nc, int64_t nc
   const bool live = c < nc;
   p0[c] = live ? aos[k * c] : 0; p1[c] = live ? aos[k * c + 1] : 0; p2[c] = live ? aos[k * c + 2] : 0;
   if (k == 4) p3[c] = live ? aos[k * c + 3] : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// F4  Delaunay restoration by edge flips (flip.cuh: mark / select / apply) and the derived edge list.
+//     CGAL/Delaunay_triangulation_2.h:936-1022 (which edges flip), CGAL/Triangulation_data_structure_2.h:885-915
+//     (the flip).  Off the timed step: runs between steps when the legality pass reports illegal edges.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_flip_mark(const double* __restrict__ xy, const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2,
+            const int32_t* __restrict__ nb, const uint8_t* __restrict__ v_if, const unsigned long long* __restrict__ keys, int nkeys,
+            int64_t nc, unsigned* __restrict__ claim, uint8_t* __restrict__ ill, FlipCounts* __restrict__ fc) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  unsigned cnt[5] = { 0, 0, 0, 0, 0 };
+  ill[c] = (uint8_t)flip_mark_cell(c, xy, cv0, cv1, cv2, nb, v_if, keys, nkeys,
+                                   [&](int64_t cell, unsigned id) { atomicMin(claim + cell, id); }, [&](int which) { cnt[which]++; });
+  if (cnt[0]) atomicAdd(&fc->illegal, (unsigned long long)cnt[0]);
+  if (cnt[1]) atomicAdd(&fc->constrained, (unsigned long long)cnt[1]);
+  if (cnt[2]) atomicAdd(&fc->inverted, (unsigned long long)cnt[2]);
+  if (cnt[3]) atomicAdd(&fc->broken, (unsigned long long)cnt[3]);
+  if (cnt[4]) atomicAdd(&fc->domain, (unsigned long long)cnt[4]);
+}
+__global__ void __launch_bounds__(256)
+k_flip_select(const int32_t* __restrict__ nb, const unsigned* __restrict__ claim, const uint8_t* __restrict__ ill, int64_t nc,
+              uint8_t* __restrict__ sel) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nc) sel[c] = (uint8_t)flip_select_cell(c, ill[c], nb, claim);
+}
+__global__ void __launch_bounds__(256)
+k_flip_apply(int32_t* cv0, int32_t* cv1, int32_t* cv2, int32_t* nb, int32_t* __restrict__ aos, const int64_t* __restrict__ vid,
+             uint8_t* perm, const uint8_t* __restrict__ sel, int64_t nc, FlipCounts* __restrict__ fc) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k1 = c < nc ? sel[c] : 0;
+  if (k1) {
+    const int32_t n = nb[3 * c + (k1 - 1)];
+    flip_apply_cell(c, k1 - 1, cv0, cv1, cv2, nb, vid, perm);
+    aos[3 * c] = cv0[c]; aos[3 * c + 1] = cv1[c]; aos[3 * c + 2] = cv2[c];
+    aos[3 * (int64_t)n] = cv0[n]; aos[3 * (int64_t)n + 1] = cv1[n]; aos[3 * (int64_t)n + 2] = cv2[n];
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, k1 != 0);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fc->flips, (unsigned long long)__popc(m));
+}
+// edge list from cells + neighbours: per-block counts (COMPACT_TILE cells per block), k_compact_scan, emission
+__global__ void __launch_bounds__(256)
+k_edges_count(const int32_t* __restrict__ nb, int64_t nc, uint32_t* __restrict__ block_count) {
+  const int64_t base = (int64_t)blockIdx.x * COMPACT_TILE;
+  unsigned c = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int64_t i = base + r * 256 + threadIdx.x;
+    if (i < nc) c += (unsigned)flip_edge_count(i, nb);
+  }
+  __shared__ unsigned sm[8];
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned t = 0; for (int w = 0; w < 8; ++w) t += sm[w]; block_count[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(256)
+k_edges_emit(const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2, const int32_t* __restrict__ nb,
+             int64_t nc, const uint32_t* __restrict__ block_off, int4* __restrict__ edges, int64_t cap) {
+  const int64_t base = (int64_t)blockIdx.x * COMPACT_TILE;
+  __shared__ unsigned wcount[8];
+  unsigned off = block_off[blockIdx.x];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = 0; r < 8; ++r) {
+    const int64_t i = base + r * 256 + threadIdx.x;
+    int32_t q[12];
+    const unsigned m = i < nc ? (unsigned)flip_edge_emit(i, cv0, cv1, cv2, nb, q) : 0u;
+    unsigned incl = m;                                     // inclusive warp scan of the per-cell counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wcount[w] = incl;
+    __syncthreads();
+    unsigned before = 0, tot = 0;
+    for (int k = 0; k < 8; ++k) { const unsigned t = wcount[k]; if (k < w) before += t; tot += t; }
+    const int64_t pos = (int64_t)off + before + incl - m;
+    for (unsigned e = 0; e < m; ++e)
+      if (pos + e < cap) edges[pos + e] = make_int4(q[4 * e], q[4 * e + 1], q[4 * e + 2], q[4 * e + 3]);
+    off += tot;
+    __syncthreads();
+  }
 }
 
 }  // namespace mmb

@@ -1583,6 +1583,91 @@ int mmb_download_fields(mmb_context* ctx, int ncomp, double* dofs_new_host, int8
   return MMB_OK;
 }
 
+// ---- f4: Delaunay restoration by edge flips on the resident snapshot (flip.cuh) ------------------------------------------
+int mmb_restore_delaunay(mmb_context* ctx, const int64_t* vertex_id_host, int32_t max_rounds, mmb_flip_result* out) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  if (out) std::memset(out, 0, sizeof(*out));
+  REQUIRE(ctx->mesh_ok && ctx->dim == 2 && ctx->have_nb, MMB_ERR_STATE, "mmb_restore_delaunay needs a 2-D mesh with neighbours (mmb_upload_neighbours)");
+  REQUIRE(ctx->own_lo == 0 && ctx->own_hi == ctx->nc, MMB_ERR_STATE, "mmb_restore_delaunay works on an unsharded snapshot");
+  REQUIRE(max_rounds >= 0, MMB_ERR_INVALID_ARG, "mmb_restore_delaunay: max_rounds < 0");
+  const int64_t nc = ctx->nc, nv = ctx->nv;
+  REQUIRE(3 * nc < 0xffffffffll, MMB_ERR_CAPACITY, "mmb_restore_delaunay: edge ids exceed 32 bits");
+  if (nc == 0) { if (out) out->converged = 1; return MMB_OK; }
+  DBuf<unsigned> claim; DBuf<uint8_t> ill, sel; DBuf<FlipCounts> fc; DBuf<int64_t> vid;
+  auto release = [&]() { claim.release(); ill.release(); sel.release(); fc.release(); vid.release(); };
+  auto fail = [&](cudaError_t e) { ctx->err = std::string("mmb_restore_delaunay: ") + cudaGetErrorString(e); release(); return (int)MMB_ERR_CUDA; };
+  cudaError_t e;
+  if ((e = claim.ensure((size_t)nc)) || (e = ill.ensure((size_t)nc)) || (e = sel.ensure((size_t)nc)) || (e = fc.ensure(1)) ||
+      (vertex_id_host && (e = vid.ensure((size_t)nv)))) return fail(e);
+  cudaStream_t S = ctx->stream;
+  if (vertex_id_host && (e = cudaMemcpyAsync(vid.p, vertex_id_host, (size_t)nv * sizeof(int64_t), cudaMemcpyHostToDevice, S))) return fail(e);
+  cudaMemsetAsync(fc.p, 0, sizeof(FlipCounts), S);
+  FlipCounts h; std::memset(&h, 0, sizeof(h));
+  int rounds = 0, converged = 0;
+  for (;;) {
+    // mark: counts of this sweep (flips accumulate)
+    cudaMemsetAsync(fc.p, 0, offsetof(FlipCounts, flips), S);
+    cudaMemsetAsync(claim.p, 0xff, (size_t)nc * sizeof(unsigned), S);
+    LAUNCH("flip_mark", k_flip_mark, grid_for(nc, 128), 128, ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->cell_nb.p, ctx->v_if.p,
+           ctx->facet_keys.p, (int)ctx->n_facet_keys, nc, claim.p, ill.p, fc.p);
+    if ((e = cudaMemcpyAsync(&h, fc.p, sizeof(FlipCounts), cudaMemcpyDeviceToHost, S)) || (e = cudaStreamSynchronize(S))) return fail(e);
+    if (h.broken) { release(); REQUIRE(false, MMB_ERR_INVALID_ARG, "mmb_restore_delaunay: the neighbour table is not symmetric"); }
+    if (h.domain) { release(); REQUIRE(false, MMB_ERR_CAPACITY, "mmb_restore_delaunay: coordinates outside the exact predicates' exponent range"); }
+    if (h.inverted) {
+      release();
+      REQUIRE(false, MMB_ERR_STATE, "mmb_restore_delaunay: " + std::to_string(h.inverted) + " cells are not positively oriented; flips need a valid triangulation (ensureVertexMovement first)");
+    }
+    if (h.illegal == 0) { converged = 1; break; }
+    if (rounds >= max_rounds) break;
+    LAUNCH("flip_select", k_flip_select, grid_for(nc, 256), 256, ctx->cell_nb.p, claim.p, ill.p, nc, sel.p);
+    LAUNCH("flip_apply", k_flip_apply, grid_for(nc, 256), 256, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->cell_nb.p, ctx->cells_aos.p,
+           vertex_id_host ? vid.p : (const int64_t*)nullptr, ctx->perm.p, sel.p, nc, fc.p);
+    ++rounds;
+  }
+  if (out) {
+    out->n_flips = (int64_t)h.flips; out->n_illegal_left = (int64_t)h.illegal; out->n_constrained_illegal = (int64_t)h.constrained;
+    out->rounds = rounds; out->converged = converged;
+  }
+  if (h.flips) {
+    // derived arrays: edge list (count is invariant under flips), tile windows; everything computed from the old topology is stale
+    const int64_t ntc = (ctx->nc_pad + TILE - 1) / TILE, nte = (ctx->ne + TILE - 1) / TILE;
+    LAUNCH("tile_windows", k_tile_windows, (unsigned)ntc, 256, ctx->cv[0].p, 1, nc, nv, ctx->tile_lo_cells.p);
+    ctx->nnew = ctx->npairs = 0; ctx->graph_valid = false; ctx->cand_ready = false;
+  }
+  if (h.flips && ctx->ne) {
+    const int nb_blocks = (int)((nc + COMPACT_TILE - 1) / COMPACT_TILE);
+    LAUNCH("edges_count", k_edges_count, nb_blocks, 256, ctx->cell_nb.p, nc, ctx->block_count.p);
+    LAUNCH("compact_scan", k_compact_scan, 1, 1024, ctx->block_count.p, nb_blocks, &ctx->counters.p->pad_[0]);
+    LAUNCH("edges_emit", k_edges_emit, nb_blocks, 256, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->cell_nb.p, nc, ctx->block_count.p,
+           (int4*)ctx->edges.p, ctx->ne);
+    const int64_t nte = (ctx->ne + TILE - 1) / TILE;
+    LAUNCH("tile_windows", k_tile_windows, (unsigned)nte, 256, (const int32_t*)ctx->edges.p, 4, ctx->ne, nv, ctx->tile_lo_edges.p);
+    if ((e = cudaGetLastError())) return fail(e);
+    if (int rc = fetch_counters(ctx)) { release(); return rc; }
+    if ((int64_t)ctx->h_counters->pad_[0] != ctx->ne) {
+      release();
+      REQUIRE(false, MMB_ERR_STATE, "mmb_restore_delaunay: the rebuilt edge list has " + std::to_string(ctx->h_counters->pad_[0]) + " edges, the snapshot " + std::to_string(ctx->ne));
+    }
+  }
+  if ((e = cudaStreamSynchronize(S))) return fail(e);
+  release();
+  return MMB_OK;
+}
+int mmb_download_topology(mmb_context* ctx, int32_t* cells_host, uint8_t* perm_host, int32_t* cell_nb_host, int32_t* edges_host) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(ctx->mesh_ok, MMB_ERR_STATE, "no mesh uploaded");
+  const size_t nc = (size_t)ctx->nc, k = (size_t)ctx->dim + 1;
+  if (cells_host && nc) CK(cudaMemcpyAsync(cells_host, ctx->cells_aos.p, nc * k * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (perm_host && nc) CK(cudaMemcpyAsync(perm_host, ctx->perm.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cell_nb_host) {
+    REQUIRE(ctx->have_nb, MMB_ERR_STATE, "no neighbours uploaded");
+    if (nc) CK(cudaMemcpyAsync(cell_nb_host, ctx->cell_nb.p, 3 * nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (edges_host && ctx->ne) CK(cudaMemcpyAsync(edges_host, ctx->edges.p, (size_t)ctx->ne * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MMB_OK;
+}
+
 // ---- multi-GPU plumbing: ownership, halo pack/unpack, phased step ------------------------------------------------
 int mmb_set_owned_cells(mmb_context* ctx, int64_t lo, int64_t hi) {
   if (!ctx) return MMB_ERR_INVALID_ARG;

@@ -238,6 +238,25 @@ class MMesh {
     removed_.clear(); removedMask_.assign(s.x.size(), 0);
   }
 
+  //! Delaunay restoration of the resident snapshot by edge flips on the device (the flips CGAL performs one
+  //! by one in restore_Delaunay / propagating_flip, CGAL/Delaunay_triangulation_2.h:936-1022).  `s` must be the snapshot
+  //! handed to setSnapshot (with neighbours); its cells, perm, neighbours and edges are replaced by the flipped topology, so
+  //! the adapter can replay it into its TDS.  Interface edges are constraints.  Throws GridError if a cell is inverted.
+  mmb_flip_result restoreDelaunay(Snapshot<dim>& s, int maxRounds = 1000) {
+    static_assert(dim == 2, "edge flips are the 2-D algorithm");
+    if (&s != snap_) throw InvalidStateException("restoreDelaunay: pass the snapshot given to setSnapshot");
+    if (s.neighbours.size() != s.cells.size()) throw InvalidStateException("restoreDelaunay needs Snapshot::neighbours");
+    mmb_flip_result r{};
+    const int rc = mmb_restore_delaunay(ctx_, s.vertexId.size() == s.x.size() && !s.x.empty() ? s.vertexId.data() : nullptr, maxRounds, &r);
+    if (rc == MMB_ERR_STATE) throw GridError(mmb_last_error(ctx_));
+    check(rc);
+    if (r.n_flips > 0 && !s.cells.empty())
+      check(mmb_download_topology(ctx_, s.cells[0].data(), s.perm.data(), s.neighbours[0].data(), s.edges.empty() ? nullptr : s.edges[0].data()));
+    marks_.assign(s.cells.size(), 0);
+    refineMarked_ = coarsenMarked_ = 0; interfaceMarked_ = false;
+    return r;
+  }
+
   //! mmesh.hh:1421-1430
   void moveVertices(const std::vector<Coordinate>& shifts) {
     requireSize(shifts);

@@ -21,6 +21,7 @@ EXPORTS = [
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
     "mmb_step_host_begin", "mmb_step_host_marks", "mmb_step_host_finish", "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_project_interface_p1", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
     "mmb_component_numbers", "mmb_host_register", "mmb_host_unregister", "mmb_comm_unique_id", "mmb_comm_init", "mmb_comm_destroy", "mmb_halo_counts", "mmb_adapt_step_sharded", "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
+    "mmb_restore_delaunay", "mmb_download_topology",
 ]
 
 
@@ -50,9 +51,14 @@ class StepResult(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class FlipResult(C.Structure):
+    _fields_ = [("n_flips", C.c_int64), ("n_illegal_left", C.c_int64), ("n_constrained_illegal", C.c_int64),
+                ("rounds", C.c_int32), ("converged", C.c_int32)]
+
+
 def build(force=False):
     """Compile the sm_100a library in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_PKG, "csrc", f) for f in ("mmesh_b200.cu", "kernels.cuh", "predicates.cuh", "clip.cuh", "geom.cuh", "project.cuh")]
+    srcs = [os.path.join(_PKG, "csrc", f) for f in ("mmesh_b200.cu", "kernels.cuh", "predicates.cuh", "clip.cuh", "geom.cuh", "project.cuh", "flip.cuh")]
     srcs.append(os.path.join(os.path.dirname(_PKG), "include", "mmesh_b200.h"))
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _PKG, "-s"])
@@ -145,6 +151,23 @@ class Context:
                                       C.c_int64(ne), C.c_int64(0 if ei is None else ei.shape[0]), None if ei is None or not ei.size else _p(ei),
                                       None if eq is None or not eq.size else _p(eq), C.c_int64(ns_new), None if fc is None else _p(fc)))
         self.nv, self.nc, self.ne, self.ns = nv, nc, ne, ns_new
+
+    def restore_delaunay(self, vertex_id=None, max_rounds=1000):
+        """Delaunay restoration by edge flips on the resident snapshot (mmb_restore_delaunay).  Returns a dict with n_flips,
+        n_illegal_left, n_constrained_illegal, rounds, converged."""
+        r = FlipResult()
+        vid = None if vertex_id is None else np.ascontiguousarray(vertex_id, np.int64)
+        self._ck(lib().mmb_restore_delaunay(self._h, _p(vid), C.c_int32(max_rounds), C.byref(r)))
+        return {k: int(getattr(r, k)) for k, _ in FlipResult._fields_}
+
+    def download_topology(self, neighbours=True, edges=True):
+        """resident cells [nc][dim+1], perm [nc], neighbours [nc][3] and edges [ne][4] (2-D)"""
+        k = self.dim + 1
+        cells = np.empty((self.nc, k), np.int32); perm = np.empty(self.nc, np.uint8)
+        nb = np.empty((self.nc, 3), np.int32) if neighbours and self.dim == 2 else None
+        e = np.empty((self.ne, 4), np.int32) if edges and self.dim == 2 and self.ne else None
+        self._ck(lib().mmb_download_topology(self._h, _p(cells), _p(perm), _p(nb), _p(e)))
+        return cells, perm, nb, e
 
     def upload_coords(self, x):
         x = _f64(x)

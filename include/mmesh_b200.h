@@ -74,6 +74,14 @@ typedef struct mmb_step_result {
   int64_t moved;          /* 1 = moveVertices was applied, 0 = withheld (see MMB_MOVE_WITHHELD) */
 } mmb_step_result;
 
+typedef struct mmb_flip_result {
+  int64_t n_flips;               /* edge flips applied */
+  int64_t n_illegal_left;        /* illegal unconstrained edges at the last sweep (0 when converged) */
+  int64_t n_constrained_illegal; /* interface edges failing the in-circle test: constraints, never flipped */
+  int32_t rounds;                /* mark / select / apply rounds executed */
+  int32_t converged;             /* 1 = no illegal unconstrained edge is left */
+} mmb_flip_result;
+
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
 /* dim = 2 or 3.  stream = a cudaStream_t to launch on (as void*), or NULL for an internal stream. */
 int mmb_create(int device, int dim, void* stream, mmb_context** out);
@@ -103,6 +111,20 @@ int mmb_patch_mesh(mmb_context* ctx, int64_t nv_new, int64_t n_vert, const int32
                    int64_t nc_new, int64_t n_cell, const int32_t* cell_idx_host, const int32_t* cell_v_host, const uint8_t* cell_perm_host,
                    int64_t ne_new, int64_t n_edge, const int32_t* edge_idx_host, const int32_t* edge_q_host,
                    int64_t ns_new, const int32_t* facets_host);
+/* Delaunay restoration on the resident 2-D snapshot by edge flips: what CGAL does edge by edge after an
+   insertion -- restore_Delaunay / propagating_flip, CGAL/Delaunay_triangulation_2.h:936-1022, flip =
+   Triangulation_data_structure_2::flip, CGAL/Triangulation_data_structure_2.h:885-915 -- as data-parallel rounds over all cells:
+   an edge flips when the opposite vertex is strictly inside the circumcircle (exact sign; ON_POSITIVE_SIDE, :969); interface edges
+   are constraints (dune/mmesh/cgal/triangulationwrapper.hh:65-125) and stay.  Needs mmb_upload_neighbours; every cell must be
+   positively oriented (MMB_ERR_STATE otherwise: run ensureVertexMovement first).  vertex_id = persistent id per vertex for the
+   corner permutation of the new cells (NULL: id = index).  At most max_rounds rounds (each flips a maximal set of edges that do not
+   touch one another).  Cells, neighbours, corner permutations, the edge list and the tile windows are updated in place
+   (mmb_download_topology reads them back); marks, flags, candidates and projection pairs of the old topology are void.
+   The result is the constrained Delaunay triangulation: unique for points in general position, so it equals CGAL's. */
+int mmb_restore_delaunay(mmb_context* ctx, const int64_t* vertex_id_host, int32_t max_rounds, mmb_flip_result* out);
+/* resident topology -> host: cells [nc][dim+1] (TDS order), perm [nc], neighbours [nc][3] (2-D, if uploaded), edges [ne][4]
+   (2-D); NULL skips an array */
+int mmb_download_topology(mmb_context* ctx, int32_t* cells_host, uint8_t* perm_host, int32_t* cell_nb_host, int32_t* edges_host);
 int mmb_upload_coords(mmb_context* ctx, const double* x_host);      /* vh->point() = ... for every vertex */
 int mmb_download_coords(mmb_context* ctx, double* x_host);
 int mmb_upload_shifts(mmb_context* ctx, const double* shifts_host); /* make `shifts` resident */

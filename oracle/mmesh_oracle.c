@@ -1346,3 +1346,53 @@ void orc_mark_interface_3d(const double* xyz, const int32_t* tris, int64_t ns, c
     mark[s] = (int8_t)(refine > 0 ? 1 : 0);                        /* coarse > 0 returns -1 only if dim != 3 */
   }
 }
+
+/* ---- Delaunay restoration by edge flips (sequential Lawson; see mmesh_oracle.h) -------------------- */
+static int slot_of(const int32_t* nb, int64_t cell, int32_t target) {
+  for (int k = 0; k < 3; ++k) if (nb[3 * cell + k] == target) return k;
+  return -1;
+}
+int64_t orc_restore_delaunay_2d(const double* xy, int32_t* cells, int32_t* nb, int64_t nc, const int32_t* segs, int64_t ns,
+                                int64_t max_flips) {
+  keyset constrained;
+  if (!keyset_init(&constrained, ns)) return -1;
+  for (int64_t s = 0; s < ns; ++s) keyset_insert(&constrained, edge_key(segs[2 * s], segs[2 * s + 1]));
+  /* stack of (cell, slot) edges still to examine: all of them at the start */
+  int64_t cap = 3 * nc + 16, top = 0, flips = 0;
+  int64_t* stack = (int64_t*)malloc((size_t)cap * sizeof(int64_t));
+  if (!stack) { free(constrained.slot); return -1; }
+  for (int64_t c = nc - 1; c >= 0; --c) for (int k = 2; k >= 0; --k) stack[top++] = 3 * c + k;
+  while (top > 0) {
+    const int64_t e = stack[--top];
+    const int64_t f = e / 3; const int i = (int)(e % 3);
+    const int32_t n = nb[3 * f + i];
+    if (n < 0) continue;
+    const int ni = slot_of(nb, n, (int32_t)f);
+    if (ni < 0) { flips = -1; break; }
+    const int ccw_i = (i + 1) % 3, cw_i = (i + 2) % 3, ccw_ni = (ni + 1) % 3, cw_ni = (ni + 2) % 3;
+    const int32_t apex = cells[3 * f + i], a = cells[3 * f + ccw_i], b = cells[3 * f + cw_i], opp = cells[3 * (int64_t)n + ni];
+    if (keyset_has(&constrained, edge_key(a, b))) continue;
+    if (orc_incircle(xy + 2 * (int64_t)apex, xy + 2 * (int64_t)a, xy + 2 * (int64_t)b, xy + 2 * (int64_t)opp) <= 0) continue;
+    if (max_flips >= 0 && flips >= max_flips) { flips = -1; break; }
+    /* Triangulation_data_structure_2.h:885-915 */
+    const int32_t tr = nb[3 * f + ccw_i], bl = nb[3 * (int64_t)n + ccw_ni];
+    const int tri = tr >= 0 ? slot_of(nb, tr, (int32_t)f) : -1, bli = bl >= 0 ? slot_of(nb, bl, n) : -1;
+    cells[3 * f + cw_i] = opp;
+    cells[3 * (int64_t)n + cw_ni] = apex;
+    nb[3 * f + i] = bl;            if (bli >= 0) nb[3 * (int64_t)bl + bli] = (int32_t)f;
+    nb[3 * f + ccw_i] = n;         nb[3 * (int64_t)n + ccw_ni] = (int32_t)f;
+    nb[3 * (int64_t)n + ni] = tr;  if (tri >= 0) nb[3 * (int64_t)tr + tri] = n;
+    ++flips;
+    /* the four outer edges of the new pair (propagating_flip re-examines the two facing the apex; a sweep over all edges
+       needs all four) */
+    if (top + 4 > cap) {
+      cap = 2 * cap + 16;
+      int64_t* g = (int64_t*)realloc(stack, (size_t)cap * sizeof(int64_t));
+      if (!g) { flips = -1; break; }
+      stack = g;
+    }
+    stack[top++] = 3 * f + i; stack[top++] = 3 * f + cw_i; stack[top++] = 3 * (int64_t)n + ni; stack[top++] = 3 * (int64_t)n + cw_ni;
+  }
+  free(stack); free(constrained.slot);
+  return flips;
+}

@@ -197,6 +197,16 @@ int orc_ensure_interface_movement_2d(const double* x, int64_t nv, const int32_t*
 int64_t orc_component_numbers(int64_t nz, const int64_t* zone_off, const int32_t* zone_cells, int64_t component_count,
                               int32_t* zone_number, int32_t* cell_number);
 
+/* ---- Delaunay restoration by edge flips (sequential Lawson) --------------------------------------- */
+/* What CGAL does after an insertion, applied to every edge: an edge whose opposite vertex is strictly inside the circumcircle
+   (side_of_oriented_circle == ON_POSITIVE_SIDE, CGAL/Delaunay_triangulation_2.h:969,999) is flipped
+   (Triangulation_data_structure_2::flip, CGAL/Triangulation_data_structure_2.h:885-915) and its four outer edges are
+   re-examined (propagating_flip, :984-1005); interface edges (segs) are constraints and never flip.  cells [nc][3] (TDS order,
+   ccw) and nb [nc][3] (neighbour opposite vertex k, -1 = none) are updated in place.  Returns the number of flips, or -1 when
+   max_flips was exceeded. */
+int64_t orc_restore_delaunay_2d(const double* xy, int32_t* cells, int32_t* nb, int64_t nc, const int32_t* segs, int64_t ns,
+                                int64_t max_flips);
+
 #ifdef __cplusplus
 }
 #endif

@@ -412,3 +412,15 @@ def mark_interface_3d(xyz, tris, prm, maxDist):
     m = np.empty(tris.shape[0], np.int8)
     lib().orc_mark_interface_3d(_p(xyz), _p(tris), C.c_int64(tris.shape[0]), C.byref(prm), C.c_double(maxDist), _p(m))
     return m
+
+
+def restore_delaunay_2d(xy, cells, nb, segs=None, max_flips=-1):
+    """Sequential Lawson flips (CGAL/Delaunay_triangulation_2.h:936-1022, Triangulation_data_structure_2.h:885-915) with the
+    interface edges as constraints.  Returns (cells, nb, n_flips)."""
+    xy, cells, nb = _f64(xy), _i32(cells).copy(), _i32(nb).copy()
+    segs = np.zeros((0, 2), np.int32) if segs is None else _i32(segs).reshape(-1, 2)
+    lib().orc_restore_delaunay_2d.restype = C.c_int64
+    n = lib().orc_restore_delaunay_2d(_p(xy), _p(cells), _p(nb), C.c_int64(cells.shape[0]), _p(segs), C.c_int64(segs.shape[0]), C.c_int64(max_flips))
+    if n < 0:
+        raise RuntimeError("orc_restore_delaunay_2d: flip limit exceeded or inconsistent neighbour table")
+    return cells, nb, int(n)

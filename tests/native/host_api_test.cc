@@ -101,6 +101,27 @@ int main(int argc, char** argv) {
       for (uint8_t f : g2.edgeFlags()) std::printf(" %d", (int)f);
       std::printf("\n");
     }
+    {   // Delaunay restoration by device flips: the snapshot object receives the flipped topology
+      std::ifstream in3(argv[1]);
+      { std::size_t a, b, c, d; in3 >> a >> b >> c >> d; for (auto& p : s.x) in3 >> p[0] >> p[1]; }
+      MMesh<2> g3(0);
+      g3.setSnapshot(s);
+      const mmb_flip_result fr = g3.restoreDelaunay(s);
+      std::printf("flip %lld %d %d %lld\nflipcells", (long long)fr.n_flips, (int)fr.rounds, (int)fr.converged, (long long)fr.n_constrained_illegal);
+      for (auto& c : s.cells) std::printf(" %d %d %d", c[0], c[1], c[2]);
+      std::printf("\nflipedges");
+      for (auto& e : s.edges) std::printf(" %d %d %d %d", e[0], e[1], e[2], e[3]);
+      const auto legal3 = g3.edgeLegality();
+      std::size_t nill = 0; for (uint8_t f : legal3) nill += (f == 0);
+      std::printf("\nflipillegal %zu\n", nill);
+      // an inverted cell makes the flip pass refuse (GridError), like the reference refuses to move into an invalid mesh
+      Snapshot<2> bad = s;
+      const auto& c0 = bad.cells[nc / 2];
+      for (int k = 0; k < 2; ++k) bad.x[(std::size_t)c0[0]][k] = 2.0 * bad.x[(std::size_t)c0[1]][k] - bad.x[(std::size_t)c0[0]][k] + 2.0 * (bad.x[(std::size_t)c0[2]][k] - bad.x[(std::size_t)c0[1]][k]);
+      g3.setSnapshot(bad);
+      try { g3.restoreDelaunay(bad); std::printf("flipinverted missing\n"); }
+      catch (const GridError&) { std::printf("flipinverted GridError\n"); }
+    }
   } catch (const std::exception& e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

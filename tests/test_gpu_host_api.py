@@ -93,6 +93,17 @@ def test_host_class_user_loop(oracle, tmp_path):
     # after the (large) move the mesh has inverted cells => ensureInterfaceMovement's pre-check throws (mmesh.hh:926-930)
     _, _, ninv_moved = oracle.trial_validate(oracle.move(m.xy, s), None, m.cells)
     assert lines["ifmove"][0] == ("GridError" if ninv_moved > 0 else "ok")
+    # restoreDelaunay on the unmoved snapshot: the snapshot object carries the flipped topology
+    oc, onb, oflips = oracle.restore_delaunay_2d(m.xy, m.cells, m.nb, m.segs)
+    fl = [int(v) for v in lines["flip"]]
+    fc = np.array(lines["flipcells"], int).reshape(-1, 3)
+    tri = lambda c: set(map(tuple, np.sort(c, axis=1).tolist()))
+    assert fl[0] > 0 and oflips > 0 and fl[2] == 1 and tri(fc) == tri(oc)
+    fe = np.array(lines["flipedges"], int).reshape(-1, 4)
+    assert np.array_equal(fe, synth.build_edges(fc.astype(np.int32), m.nv)[0])
+    oflags, onill = oracle.legality(m.xy, None, fe.astype(np.int32))
+    assert int(lines["flipillegal"][0]) == onill == fl[3]
+    assert lines["flipinverted"] == ["GridError"]
 
 
 ADAPT_EXE = os.path.join(ROOT, "tests", "native", "_build", "adapt_handle_test")

@@ -2,6 +2,8 @@
 against the CPU oracle on the same seeded inputs.  Integer / flag / mark outputs must be bit-exact; distances are
 asserted bit-exact too (same arithmetic, conservative culling); projected DOFs within 1e-12 relative, mass 1e-13.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -732,3 +734,77 @@ def test_patch_mesh_equals_full_upload(gpu_ctx_factory, oracle):
     got2 = fields(ctx)
     for k in want2:
         assert np.array_equal(got2[k], want2[k]) if isinstance(want2[k], np.ndarray) else got2[k] == want2[k], k
+
+
+@pytest.mark.gpu
+def test_restore_delaunay_on_device(gpu_ctx_factory, oracle):
+    """mmb_restore_delaunay: after a vertex move the resident snapshot is flipped back to the (constrained)
+    Delaunay triangulation.  The device rounds are deterministic, so cells / neighbours / corner permutations equal the host
+    build of the same phase functions entry by entry (tests/native/host_flip.cc); the triangle set equals the oracle's
+    sequential Lawson iteration and, without constraints, scipy's Qhull triangulation; the rebuilt edge list equals what the
+    snapshot builder derives from the new cells, and the legality pass afterwards finds only the interface edges."""
+    from mmesh_b200 import synth
+    from test_host_flip import moved_mesh, tri_set, facet_keys, SO as FLIP_SO, ROOT as TROOT
+    import ctypes as C, subprocess
+    os.makedirs(os.path.dirname(FLIP_SO), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(TROOT, "include"),
+                           os.path.join(TROOT, "tests", "native", "host_flip.cc"), "-o", FLIP_SO])
+    L = C.CDLL(FLIP_SO)
+    P = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    t = np.linspace(0.0, 2.0 * np.pi, 800)
+    circle = (np.stack([0.5 + 0.27 * np.cos(t), 0.5 + 0.27 * np.sin(t)], 1), True)
+    for n, curves, use_vid in ((96, (), True), (160, (circle,), True), (64, (), False)):
+        m, xy = moved_mesh(oracle, n, 0.27, 11 + n, curves=curves)
+        ctx = gpu_ctx_factory(2)
+        ctx.upload_mesh(xy, m.cells, m.perm, m.edges, m.segs)
+        with pytest.raises(Exception):
+            ctx.restore_delaunay()                                     # neighbours are required
+        ctx.upload_neighbours(m.nb)
+        _, nill0 = ctx.legality()
+        res = ctx.restore_delaunay(vertex_id=m.vid if use_vid else None)
+        cells, perm, nb, edges = ctx.download_topology()
+        assert res["converged"] == 1 and res["n_illegal_left"] == 0 and 0 < res["n_flips"] and res["rounds"] < 64
+        # host build of the same phases: identical arrays
+        hc, hnb, hperm = m.cells.copy(), m.nb.copy(), m.perm.copy()
+        v_if, keys = facet_keys(m.segs.reshape(-1, 2), m.nv)
+        r = np.zeros(8, np.int64)
+        vid64 = np.ascontiguousarray(m.vid, np.int64) if use_vid else None
+        L.hf_restore(P(np.ascontiguousarray(xy)), C.c_long(m.nv), P(hc), P(hnb), P(hperm), C.c_long(m.nc), P(v_if), P(keys), C.c_int(keys.shape[0]),
+                     P(vid64), C.c_int(1000), P(r), None)
+        assert (res["n_flips"], res["rounds"], res["n_constrained_illegal"]) == (int(r[0]), int(r[1]), int(r[4]))
+        assert np.array_equal(cells, hc) and np.array_equal(nb, hnb) and np.array_equal(perm, hperm)
+        # oracle (sequential Lawson) and, unconstrained, Qhull
+        oc, _, oflips = oracle.restore_delaunay_2d(xy, m.cells, m.nb, m.segs)
+        assert oflips > 0 and tri_set(oc) == tri_set(cells)
+        if not curves:
+            from scipy.spatial import Delaunay
+            sp = Delaunay(xy).simplices
+            a = xy[sp]
+            area = np.abs((a[:, 1, 0] - a[:, 0, 0]) * (a[:, 2, 1] - a[:, 0, 1]) - (a[:, 2, 0] - a[:, 0, 0]) * (a[:, 1, 1] - a[:, 0, 1]))
+            assert tri_set(sp[area > 1e-14]) == tri_set(cells)
+        ids = m.vid if use_vid else np.arange(m.nv)
+        assert np.array_equal(perm, synth.pack_perm(ids[cells]))
+        e_ref, nb_ref, _ = synth.build_edges(cells, m.nv)
+        assert np.array_equal(edges, e_ref) and np.array_equal(nb, nb_ref)
+        # the hot path keeps working on the new topology: legality finds only the constrained edges, marks equal the oracle's
+        flags, nill = ctx.legality()
+        oflags, onill = oracle.legality(xy, None, edges)
+        assert np.array_equal(flags, oflags) and nill == onill == res["n_constrained_illegal"] and nill0 > nill
+        valid, sign, ninv = ctx.trial_move_validate(np.zeros_like(xy))
+        assert ninv == 0 and (sign > 0).all()
+        if len(m.segs):
+            prm = ctx.indicator_init()
+            d, mx = ctx.distance_update()
+            marks, le, counts = ctx.mark_elements(run_distance=False)
+            od = oracle.distance_2d(xy, m.segs)
+            prop = oracle.Params.from_buffer_copy(bytes(prm)).distProportion
+            omarks, ole, oc3 = oracle.mark(xy, od, cells, perm, oracle.Params.from_buffer_copy(bytes(prm)), prop * oracle.distance_max(od))
+            assert np.array_equal(d, od) and np.array_equal(marks, omarks) and np.array_equal(le, ole) and tuple(counts) == tuple(oc3)
+        # a second call has nothing to do; an inverted cell is refused
+        again = ctx.restore_delaunay(vertex_id=m.vid if use_vid else None)
+        assert again["n_flips"] == 0 and again["converged"] == 1 and again["rounds"] == 0
+        bad = xy.copy(); c = cells[m.nc // 2]
+        bad[c[0]] = bad[c[1]] + (bad[c[1]] - bad[c[0]]) + (bad[c[2]] - bad[c[1]]) * 2.0
+        ctx.upload_coords(bad)
+        with pytest.raises(Exception, match="positively oriented"):
+            ctx.restore_delaunay()

@@ -1,0 +1,170 @@
+"""CPU test of the PRODUCT flip logic (dune-mmesh_b200/csrc/flip.cuh, the functions the three kernels of
+mmb_restore_delaunay call) compiled for the host and run phase by phase like the kernels: Delaunay restoration by edge flips
+after a vertex move.  Checked against the oracle's sequential Lawson iteration (oracle/mmesh_oracle.c), against
+scipy.spatial.Delaunay where no constraint is present (an independent implementation: the Delaunay triangulation of points in
+general position is unique), and against the snapshot invariants (neighbour table, corner permutation, edge list)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "dune-mmesh_b200", "python"))
+from mmesh_b200 import synth  # noqa: E402
+
+SO = os.path.join(ROOT, "tests", "native", "_build", "libhost_flip.so")
+
+
+def facet_keys(segs, nv):
+    v_if = np.zeros(nv, np.uint8)
+    if len(segs):
+        v_if[np.asarray(segs).ravel()] = 1
+        a, b = np.minimum(segs[:, 0], segs[:, 1]).astype(np.uint64), np.maximum(segs[:, 0], segs[:, 1]).astype(np.uint64)
+        keys = np.sort((a << np.uint64(32)) | b)
+    else:
+        keys = np.zeros(0, np.uint64)
+    return v_if, np.ascontiguousarray(keys)
+
+
+@pytest.fixture(scope="module")
+def host_flip():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "native", "host_flip.cc"), "-o", SO])
+    L = C.CDLL(SO)
+    L.hf_edges.restype = C.c_long
+    L.hf_perm.restype = C.c_uint8
+    P = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def restore(xy, cells, nb, segs, vid=None, max_rounds=1000, perm=None):
+        xy = np.ascontiguousarray(xy, np.float64)
+        cells = np.ascontiguousarray(cells, np.int32).copy(); nb = np.ascontiguousarray(nb, np.int32).copy()
+        nc, nv = cells.shape[0], xy.shape[0]
+        v_if, keys = facet_keys(np.asarray(segs).reshape(-1, 2), nv)
+        perm = np.zeros(nc, np.uint8) if perm is None else np.ascontiguousarray(perm, np.uint8).copy()
+        res = np.zeros(8, np.int64); trace = np.zeros(max(max_rounds, 1), np.int32)
+        vid64 = None if vid is None else np.ascontiguousarray(vid, np.int64)
+        L.hf_restore(P(xy), C.c_long(nv), P(cells), P(nb), P(perm), C.c_long(nc), P(v_if), P(keys), C.c_int(keys.shape[0]), P(vid64),
+                     C.c_int(max_rounds), P(res), P(trace))
+        return dict(cells=cells, nb=nb, perm=perm, flips=int(res[0]), rounds=int(res[1]), converged=int(res[2]), illegal=int(res[3]),
+                    constrained=int(res[4]), inverted=int(res[5]), broken=int(res[6]), trace=trace[:int(res[1])])
+
+    def edges(cells, nb, cap):
+        out = np.zeros((cap, 4), np.int32)
+        n = L.hf_edges(P(np.ascontiguousarray(cells, np.int32)), P(np.ascontiguousarray(nb, np.int32)), C.c_long(cells.shape[0]), P(out), C.c_long(cap))
+        return out[:n], n
+
+    restore.edges = edges
+    restore.perm = lambda a, b, c: int(L.hf_perm(C.c_int64(a), C.c_int64(b), C.c_int64(c)))
+    return restore
+
+
+def tri_set(cells):
+    return set(map(tuple, np.sort(np.asarray(cells, np.int64), axis=1).tolist()))
+
+
+def moved_mesh(oracle, n, amp, seed, curves=()):
+    m = synth.lattice2d(n, n, jitter=0.2, seed=seed, curves=curves, hilbert=True)
+    s = synth.shifts_uniform(m, amp * m.h, seed + 100)
+    if len(m.segs):                                         # keep the interface where it is: its edges must stay edges of the mesh
+        s[np.unique(m.segs.ravel())] = 0.0
+    for _ in range(60):                                     # what ensureVertexMovement is for: no cell may invert
+        valid, _, _ = oracle.trial_validate(m.xy + s, None, m.cells)
+        if valid.all():
+            break
+        s[np.unique(m.cells[valid == 0].ravel())] *= 0.5
+    return m, m.xy + s
+
+
+def check_snapshot_invariants(host_flip, m, xy, r, oracle):
+    cells, nb = r["cells"], r["nb"]
+    # every cell counter-clockwise (exact sign)
+    pts = xy[cells].reshape(-1, 6)
+    assert (oracle.orient2d_batch(pts) > 0).all()
+    # neighbour table and edge list = what the snapshot builder derives from the cells
+    e_ref, nb_ref, _ = synth.build_edges(cells, m.nv)
+    assert np.array_equal(nb, nb_ref)
+    e, n = host_flip.edges(cells, nb, e_ref.shape[0] + 8)
+    assert n == e_ref.shape[0] == m.edges.shape[0] and np.array_equal(e, e_ref)
+    assert np.array_equal(r["perm"], synth.pack_perm(m.vid[cells]))
+
+
+@pytest.mark.parametrize("n,amp,seed", [(12, 0.2, 1), (40, 0.25, 2), (64, 0.28, 3)])
+def test_flips_restore_delaunay_unconstrained(host_flip, oracle, n, amp, seed):
+    from scipy.spatial import Delaunay
+    m, xy = moved_mesh(oracle, n, amp, seed)
+    valid, _, _ = oracle.trial_validate(xy, None, m.cells)
+    assert valid.all(), "test input must be a valid triangulation"
+    r = host_flip(xy, m.cells, m.nb, m.segs, vid=m.vid, perm=m.perm)
+    assert r["converged"] == 1 and r["illegal"] == 0 and r["flips"] > 0 and r["inverted"] == 0 and r["broken"] == 0
+    assert r["rounds"] == len(r["trace"]) and (r["trace"] > 0).all() and r["trace"].sum() == r["flips"]
+    # oracle: sequential Lawson flips reach the same triangulation
+    oc, onb, oflips = oracle.restore_delaunay_2d(xy, m.cells, m.nb)
+    assert oflips > 0 and tri_set(oc) == tri_set(r["cells"])
+    # independent implementation (Qhull); zero-area simplices along the straight domain boundary are not triangles of a mesh
+    sp = Delaunay(xy).simplices
+    a = xy[sp]
+    area = np.abs((a[:, 1, 0] - a[:, 0, 0]) * (a[:, 2, 1] - a[:, 0, 1]) - (a[:, 2, 0] - a[:, 0, 0]) * (a[:, 1, 1] - a[:, 0, 1]))
+    assert tri_set(sp[area > 1e-14]) == tri_set(r["cells"])
+    check_snapshot_invariants(host_flip, m, xy, r, oracle)
+    # a second call finds nothing to do
+    r2 = host_flip(xy, r["cells"], r["nb"], m.segs, vid=m.vid)
+    assert r2["flips"] == 0 and r2["converged"] == 1 and np.array_equal(r2["cells"], r["cells"])
+
+
+def test_flips_respect_the_interface(host_flip, oracle):
+    t = np.linspace(0.0, 2.0 * np.pi, 400)
+    circle = (np.stack([0.5 + 0.27 * np.cos(t), 0.5 + 0.27 * np.sin(t)], 1), True)
+    line = (np.stack([np.linspace(0.0, 1.0, 200), 0.13 + 0.05 * np.sin(2 * np.pi * np.linspace(0.0, 1.0, 200))], 1), False)
+    m, xy = moved_mesh(oracle, 48, 0.27, 5, curves=(circle, line))
+    assert len(m.segs) > 50
+    valid, _, _ = oracle.trial_validate(xy, None, m.cells)
+    assert valid.all()
+    r = host_flip(xy, m.cells, m.nb, m.segs, vid=m.vid, perm=m.perm)
+    assert r["converged"] == 1 and r["flips"] > 0
+    oc, onb, oflips = oracle.restore_delaunay_2d(xy, m.cells, m.nb, m.segs)
+    assert tri_set(oc) == tri_set(r["cells"])
+    check_snapshot_invariants(host_flip, m, xy, r, oracle)
+    # every interface segment is still an edge; the only edges failing the in-circle test are interface edges
+    e, _ = host_flip.edges(r["cells"], r["nb"], m.edges.shape[0])
+    ekeys = set(map(tuple, np.sort(e[:, :2], axis=1).tolist()))
+    skeys = set(map(tuple, np.sort(m.segs, axis=1).tolist()))
+    assert skeys <= ekeys
+    flags, _ = oracle.legality(xy, None, e)
+    bad = e[flags == 0]
+    assert len(bad) == r["constrained"] and all(tuple(sorted(q[:2])) in skeys for q in bad.tolist())
+    # without the constraint some of them flip: the constrained result differs from the plain Delaunay triangulation
+    if r["constrained"]:
+        r0 = host_flip(xy, m.cells, m.nb, np.zeros((0, 2), np.int32), vid=m.vid)
+        assert tri_set(r0["cells"]) != tri_set(r["cells"])
+
+
+def test_round_limit_and_invalid_input(host_flip, oracle):
+    m, xy = moved_mesh(oracle, 32, 0.25, 9)
+    full = host_flip(xy, m.cells, m.nb, m.segs)
+    assert full["rounds"] >= 2
+    part = host_flip(xy, m.cells, m.nb, m.segs, max_rounds=1)
+    assert part["rounds"] == 1 and part["converged"] == 0 and 0 < part["flips"] < full["flips"] and part["illegal"] > 0
+    # the partial result is a valid triangulation that the next call completes
+    rest = host_flip(xy, part["cells"], part["nb"], m.segs)
+    assert rest["converged"] == 1 and tri_set(rest["cells"]) == tri_set(full["cells"])
+    # an inverted cell: nothing is flipped, the count is reported
+    bad = xy.copy()
+    c = m.cells[m.nc // 2]
+    bad[c[0]] = bad[c[1]] + (bad[c[1]] - bad[c[0]]) + (bad[c[2]] - bad[c[1]]) * 2.0        # drag a corner across the opposite edge
+    valid, _, _ = oracle.trial_validate(bad, None, m.cells)
+    assert not valid.all()
+    r = host_flip(bad, m.cells, m.nb, m.segs)
+    assert r["inverted"] > 0 and r["flips"] == 0 and np.array_equal(r["cells"], m.cells)
+    # a neighbour table without mirror entries is reported
+    nb = m.nb.copy(); c0 = int(np.nonzero((nb >= 0).all(axis=1))[0][0]); nb[nb[c0, 0]][nb[nb[c0, 0]] == c0] = -1
+    assert host_flip(xy, m.cells, nb, m.segs)["broken"] > 0
+
+
+def test_corner_permutation_helper(host_flip):
+    import itertools
+    for ids in itertools.permutations((11, 42, 97)):
+        assert host_flip.perm(*ids) == int(synth.pack_perm(np.array([ids]))[0])
