@@ -756,7 +756,9 @@ def test_restore_delaunay_on_device(gpu_ctx_factory, oracle):
     for n, curves, use_vid in ((96, (), True), (160, (circle,), True), (64, (), False)):
         m, xy = moved_mesh(oracle, n, 0.27, 11 + n, curves=curves)
         ctx = gpu_ctx_factory(2)
-        ctx.upload_mesh(xy, m.cells, m.perm, m.edges, m.segs)
+        ids = m.vid if use_vid else np.arange(m.nv)                    # without vertex ids the persistent id is the index
+        perm0 = synth.pack_perm(ids[m.cells])
+        ctx.upload_mesh(xy, m.cells, perm0, m.edges, m.segs)
         with pytest.raises(Exception):
             ctx.restore_delaunay()                                     # neighbours are required
         ctx.upload_neighbours(m.nb)
@@ -765,7 +767,7 @@ def test_restore_delaunay_on_device(gpu_ctx_factory, oracle):
         cells, perm, nb, edges = ctx.download_topology()
         assert res["converged"] == 1 and res["n_illegal_left"] == 0 and 0 < res["n_flips"] and res["rounds"] < 64
         # host build of the same phases: identical arrays
-        hc, hnb, hperm = m.cells.copy(), m.nb.copy(), m.perm.copy()
+        hc, hnb, hperm = m.cells.copy(), m.nb.copy(), perm0.copy()
         v_if, keys = facet_keys(m.segs.reshape(-1, 2), m.nv)
         r = np.zeros(8, np.int64)
         vid64 = np.ascontiguousarray(m.vid, np.int64) if use_vid else None
@@ -782,7 +784,6 @@ def test_restore_delaunay_on_device(gpu_ctx_factory, oracle):
             a = xy[sp]
             area = np.abs((a[:, 1, 0] - a[:, 0, 0]) * (a[:, 2, 1] - a[:, 0, 1]) - (a[:, 2, 0] - a[:, 0, 0]) * (a[:, 1, 1] - a[:, 0, 1]))
             assert tri_set(sp[area > 1e-14]) == tri_set(cells)
-        ids = m.vid if use_vid else np.arange(m.nv)
         assert np.array_equal(perm, synth.pack_perm(ids[cells]))
         e_ref, nb_ref, _ = synth.build_edges(cells, m.nv)
         assert np.array_equal(edges, e_ref) and np.array_equal(nb, nb_ref)
