@@ -356,8 +356,10 @@ def main():
             pass
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
-                "note": "project_p1 is fp64-pipe / issue bound (ncu: fp64 pipe 46 %, issue 54 %, 22/32 active lanes, DRAM traffic = algorithmic "
-                        "bytes), not HBM bound; see DESIGN.md section 4"}
+                "note": {"project_p1": "fp64-pipe / issue bound (ncu, profiles/r02_ncu_dominant_16M_summary.txt: fp64 pipe 45 %, issue 56 %, 20/32 "
+                                       "active lanes, 31 % warps, DRAM traffic = 1.00 x algorithmic bytes), not HBM bound; see DESIGN.md section 4",
+                         "distance2d": "instruction-issue bound (ncu: issue 84 %, 27/32 lanes, 3.3 k warp instructions per warp of 32 "
+                                       "vertices for the conservative tree search), not HBM bound"}.get(dom["kernel"], "see DESIGN.md section 4")}
 
     # ---- cold distance field: first Distance::update after a snapshot upload (no hints yet), as after every TDS edit ----
     ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)

@@ -530,11 +530,14 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
   }
   const int stop = logL - DIST_GROUP_LOG;                 // level whose nodes hold DIST_GROUP leaves
   bool flat = __any_sync(0xffffffffu, live) && stop >= 1;
-  int ncur = 1, cb = 0;
+  // the walk starts with the 8 nodes of level 3 as its frontier (one test of their 16 children replaces four levels of
+  // one- to eight-node iterations; a subtree without facets has an empty box and drops out at once)
+  const int lev0 = stop > 3 ? 3 : 0;
+  int ncur = 1 << lev0, cb = 0;
   if (flat) {
-    if (lane == 0) s_front[w][0][0] = 1;
+    if (lane < ncur) s_front[w][0][lane] = ncur + lane;
     __syncwarp();
-    for (int lev = 0; lev < stop && flat; ++lev) {
+    for (int lev = lev0; lev < stop && flat; ++lev) {
       int nnext = 0;
       for (int base = 0; base < ncur; base += 16) {
         const int k = base + (lane >> 1);
