@@ -28,7 +28,9 @@ struct Counters {
   unsigned long long pad_[2];                     // pad_[0]: total of the last compaction scan; pad_[1]: predicates outside the exact stage's exponent range
   unsigned long long dbg[8];                      // development counters (MMB_DEV_VARIANTS builds only)
   unsigned long long n_invalid_global;            // what gates the fused step's move: n_invalid of ALL ranks (a sharded caller
-};                                                // all-reduces it; single GPU: a copy of n_invalid)
+                                                  // all-reduces it; single GPU: a copy of n_invalid)
+  unsigned long long wl_distance;                 // vertices handed to k_distance2d_wide (reset by k_bvh_build2d)
+};
 
 // (DevParams: geom.cuh)
 
@@ -355,10 +357,11 @@ __device__ __forceinline__ float4 box_merge(float4 a, float4 b) {
 // finishes last (atomic ticket) reduces the remaining top levels.
 __global__ void __launch_bounds__(256)
 k_bvh_build2d(const double2* __restrict__ xy, const int2* __restrict__ segs_sorted, int ns, int L,
-              SegLeaf* __restrict__ leaf, float4* __restrict__ box, unsigned* __restrict__ ticket) {
+              SegLeaf* __restrict__ leaf, float4* __restrict__ box, unsigned* __restrict__ ticket, Counters* __restrict__ cnt) {
   __shared__ float4 sb[512];
   __shared__ bool last;
   const int t = threadIdx.x;
+  if (blockIdx.x == 0 && t == 0) cnt->wl_distance = 0ull;   // cursor of the list k_distance2d fills for k_distance2d_wide
   const int W = L < 256 ? L : 256;                       // leaves per block (power of two)
   const int i = blockIdx.x * W + t;
   float4 b = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
@@ -489,7 +492,7 @@ k_distance_seeds(const SegLeaf* __restrict__ leaf, const float4* __restrict__ bo
 __global__ void __launch_bounds__(256, 5)
 k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restrict__ leaf,
              const float4* __restrict__ box, int ns, int L, int logL, double* __restrict__ dist, int32_t* __restrict__ hint,
-             const int32_t* __restrict__ seed, Counters* __restrict__ cnt) {
+             const int32_t* __restrict__ seed, int32_t* __restrict__ wide, Counters* __restrict__ cnt) {
   __shared__ int s_front[8][2][DIST_QCAP];
   __shared__ float4 s_gbox[8][DIST_QCAP];                 // boxes of the candidate groups (written by the lane that tested them)
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -529,6 +532,7 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
     bylo = fminf(bylo, __shfl_xor_sync(0xffffffffu, bylo, o)); byhi = fmaxf(byhi, __shfl_xor_sync(0xffffffffu, byhi, o));
   }
   const int stop = logL - DIST_GROUP_LOG;                 // level whose nodes hold DIST_GROUP leaves
+  bool deferred = false;
   bool flat = __any_sync(0xffffffffu, live) && stop >= 1;
   // the walk starts with the 8 nodes of level 3 as its frontier (one test of their 16 children replaces four levels of
   // one- to eight-node iterations; a subtree without facets has an empty box and drops out at once)
@@ -591,11 +595,22 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
         }
       }
     }
+  } else if (wide != nullptr && stop >= 1) {
+    // the candidate list outgrew its slots: the bounds of this warp are far larger than the facet spacing (a patch about
+    // equally far from a long stretch of interface -- the centre of a closed curve -- or no usable hint).  Its vertices go
+    // to k_distance2d_wide, one WARP per vertex; here they contribute nothing (distance, hint and maximum are written there)
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&cnt->wl_distance, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) wide[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)v;
+    q.best = 0.0;
+    deferred = true;
   } else if (live) {
     dist_lane_walk(q, leaf, box, ns, L, h);
   }
-  if (live) hint[v] = q.arg;
-  if (v < nv) dist[v] = q.best;
+  if (live && !deferred) hint[v] = q.arg;
+  if (v < nv && !deferred) dist[v] = q.best;
 #ifdef MMB_DEV_VARIANTS
   {  // per warp: [0] warps, [1] flat warps, [2] sum of candidate groups, [3] group passes (warp union), [4] leaf evals (warp union), [5] leaf evals (lanes)
     const unsigned gs = warp_sum(dbg_g), es = warp_sum(dbg_e), ls = warp_sum(dbg_l);
@@ -618,6 +633,78 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
     for (int ww = 1; ww < 8; ++ww) m = sm[ww] > m ? sm[ww] : m;
     atomicMax(&cnt->max_dist_bits, m);
   }
+}
+
+// The vertices k_distance2d could not serve from a short candidate list, one warp per vertex (grid-stride over the list):
+// the 32 lanes test the boxes of 32 leaf groups at a time against the vertex's bound, then take the passing groups four at a
+// time -- one leaf per lane, box test, exact reference arithmetic -- and tighten the common bound with a warp minimum.  The
+// work of such a vertex (every facet of a closed curve seen from its centre is about equally far) is spread over a warp and
+// the vertices over the whole grid, instead of 32 lanes walking the tree one after the other.  Same conservative culls, same
+// per-facet arithmetic: the minimum over all facets with the brute-force bits.
+__global__ void __launch_bounds__(256)
+k_distance2d_wide(const double2* __restrict__ xy, const SegLeaf* __restrict__ leaf, const float4* __restrict__ box, int ns, int L,
+                  double* __restrict__ dist, int32_t* __restrict__ hint, const int32_t* __restrict__ seed,
+                  const int32_t* __restrict__ wide, Counters* __restrict__ cnt) {
+  const unsigned long long n = cnt->wl_distance;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  const int ng = (ns + DIST_GROUP - 1) >> DIST_GROUP_LOG, G0 = L >> DIST_GROUP_LOG;
+  unsigned long long mx = 0ull;
+  for (unsigned long long i = warp0; i < n; i += nwarps) {
+    const int64_t v = wide[i];
+    DistQuery q;
+    const double2 p = ldg2(xy + v);
+    q.px = p.x; q.py = p.y;
+    q.pxlo = __double2float_rd(p.x); q.pxhi = __double2float_ru(p.x);
+    q.pylo = __double2float_rd(p.y); q.pyhi = __double2float_ru(p.y);
+    const float4 root = __ldg(box + 1);
+    q.diag = ((double)root.z - (double)root.x) + ((double)root.w - (double)root.y);
+    q.best = 1e100; q.arg = -1; q.set_threshold();
+    int h = hint[v];
+    if (h >= ns) h = -1;
+    if (h < 0) {
+      int sd = 0;
+      if (seed != nullptr) {
+        const double fx = (q.px - (double)root.x) / ((double)root.z - (double)root.x), fy = (q.py - (double)root.y) / ((double)root.w - (double)root.y);
+        const int gx = min(max((int)(fx * SEED_GX), 0), SEED_GX - 1), gy = min(max((int)(fy * SEED_GY), 0), SEED_GY - 1);
+        sd = seed[gy * SEED_GX + gx];
+      }
+      h = min(max(sd, 0), ns - 1);
+    }
+    q.eval_leaf(leaf, h);                                 // every lane holds the same bound from here on
+    for (int base = 0; base < ng; base += 32) {
+      const int g = base + lane;
+      unsigned m = __ballot_sync(0xffffffffu, g < ng && !(q.lb2(__ldg(box + G0 + g)) > q.T2f));
+      while (m) {
+        // up to four passing groups, eight lanes each
+        int gsel = -1;
+        unsigned mm = m;
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int b = mm ? __ffs(mm) - 1 : -1;
+          if (mm) mm &= mm - 1;
+          if ((lane >> DIST_GROUP_LOG) == sl) gsel = b;
+        }
+        m = mm;
+        double d = 1e300; int s = -1;
+        if (gsel >= 0) {
+          s = ((base + gsel) << DIST_GROUP_LOG) + (lane & (DIST_GROUP - 1));
+          if (s < ns && !(q.lb2(__ldg(box + L + s)) > q.T2f)) d = seg_distance(leaf[s], q.px, q.py); else s = -1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(0xffffffffu, d, o); const int os = __shfl_xor_sync(0xffffffffu, s, o);
+          if (od < d || (od == d && os >= 0 && (s < 0 || os < s))) { d = od; s = os; }
+        }
+        if (s >= 0 && d < q.best) { q.best = d; q.arg = s; q.set_threshold(); }
+      }
+    }
+    if (lane == 0) { dist[v] = q.best; hint[v] = q.arg; }
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(q.best);
+    mx = bits > mx ? bits : mx;
+  }
+  if (lane == 0 && mx) atomicMax(&cnt->max_dist_bits, mx);
 }
 
 // ------------------------------------------------------------------------------------------------------

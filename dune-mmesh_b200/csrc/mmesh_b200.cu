@@ -392,7 +392,7 @@ int mmb_upload_mesh(mmb_context* ctx, int64_t nv, const double* x_host, int64_t 
   CK(ctx->cells_aos.ensure((size_t)nc * k + 4));
   CK(ctx->perm.ensure(ctx->nc_pad + 4)); CK(ctx->valid_fp.ensure(ctx->nc_pad + 4)); CK(ctx->orient.ensure(ctx->nc_pad + 4));
   CK(ctx->mark.ensure(ctx->nc_pad + 4)); CK(ctx->longest.ensure(ctx->nc_pad + 4));
-  CK(ctx->wl.ensure(std::max(ctx->nc_pad, ne) + 4)); CK(ctx->list_out.ensure(std::max(ctx->nc_pad, ne) + 4));
+  CK(ctx->wl.ensure(std::max(std::max(ctx->nc_pad, ne), nv) + 4)); CK(ctx->list_out.ensure(std::max(ctx->nc_pad, ne) + 4));
   CK(ctx->block_count.ensure((std::max(ctx->nc_pad, ne) + COMPACT_TILE - 1) / COMPACT_TILE + 1));
   if (nc) {
     CK(cudaMemcpyAsync(ctx->cells_aos.p, cells_host, (size_t)nc * k * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -487,7 +487,7 @@ int mmb_patch_mesh(mmb_context* ctx, int64_t nv_new, int64_t n_vert, const int32
   // outputs / scratch: contents need not survive
   CK(ctx->shift.ensure((size_t)nv_new * dim + 2)); CK(ctx->dist.ensure((size_t)nv_new));
   CK(ctx->valid_fp.ensure(nc_pad_new + 4)); CK(ctx->orient.ensure(nc_pad_new + 4)); CK(ctx->mark.ensure(nc_pad_new + 4)); CK(ctx->longest.ensure(nc_pad_new + 4));
-  CK(ctx->wl.ensure(std::max(nc_pad_new, ne_new) + 4)); CK(ctx->list_out.ensure(std::max(nc_pad_new, ne_new) + 4));
+  CK(ctx->wl.ensure(std::max(std::max(nc_pad_new, ne_new), nv_new) + 4)); CK(ctx->list_out.ensure(std::max(nc_pad_new, ne_new) + 4));
   CK(ctx->block_count.ensure((std::max(nc_pad_new, ne_new) + COMPACT_TILE - 1) / COMPACT_TILE + 1));
   CK(ctx->cand_flag.ensure((size_t)std::max(nc_pad_new, std::max(ns_new, ctx->ns)) + 4));
   if (dim == 2) CK(ctx->edge_flag.ensure(ne_new + 4));
@@ -731,7 +731,7 @@ static int do_distance(mmb_context* ctx, bool reset_max = true) {
   if (ctx->dim == 2) {
     if (ns) {
       LAUNCH("bvh_build2d", k_bvh_build2d, L < 256 ? 1 : L / 256, 256, (const double2*)ctx->x.p, (const int2*)ctx->facets_sorted.p,
-             ns, L, ctx->seg_leaf.p, ctx->box2.p, ctx->ticket.p);
+             ns, L, ctx->seg_leaf.p, ctx->box2.p, ctx->ticket.p, ctx->counters.p);
     }
     int logL = 0; while ((1 << logL) < L) ++logL;
     if (ctx->hints_cold && ns) {                               // first update after an upload: no hints yet
@@ -740,7 +740,10 @@ static int do_distance(mmb_context* ctx, bool reset_max = true) {
     }
     LAUNCH("distance2d", k_distance2d, grid_for(ctx->nv, 256), 256, (const double2*)ctx->x.p, ctx->nv, ctx->seg_leaf.p,
            ctx->box2.p, ns, L, logL, ctx->dist.p, ctx->seg_hint.p, ctx->hints_cold ? (const int32_t*)ctx->seed_grid.p : (const int32_t*)nullptr,
-           ctx->counters.p);
+           ctx->wl.p, ctx->counters.p);
+    if (ns && logL > DIST_GROUP_LOG)      // warps whose candidate list overflowed: one warp per vertex (usually a handful of warps)
+      LAUNCH("distance2d_wide", k_distance2d_wide, ctx->num_sms * 2, 256, (const double2*)ctx->x.p, ctx->seg_leaf.p, ctx->box2.p, ns, L, ctx->dist.p,
+             ctx->seg_hint.p, ctx->hints_cold ? (const int32_t*)ctx->seed_grid.p : (const int32_t*)nullptr, ctx->wl.p, ctx->counters.p);
     ctx->hints_cold = false;
   } else {
     if (ns) {

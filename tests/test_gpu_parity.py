@@ -809,3 +809,38 @@ def test_restore_delaunay_on_device(gpu_ctx_factory, oracle):
         ctx.upload_coords(bad)
         with pytest.raises(Exception, match="positively oriented"):
             ctx.restore_delaunay()
+
+
+def test_distance_wide_path_equidistant_interface(gpu_ctx_factory, oracle):
+    """Vertices about equally far from a long stretch of interface (the centre of a closed curve): the warp's candidate list
+    overflows and its vertices are served by k_distance2d_wide, one warp per vertex.  The facets need not be mesh edges for the
+    distance field, so the case is built directly: 1500 segments on a circle, query vertices at the centre, on the circle,
+    and everywhere else.  Distances and Distance::maximum must carry the brute-force bits, cold, warm and after a move."""
+    rng = np.random.default_rng(23)
+    ncirc = 1500
+    t = np.linspace(0.0, 2.0 * np.pi, ncirc, endpoint=False)
+    circ = np.stack([0.5 + 0.3 * np.cos(t), 0.5 + 0.3 * np.sin(t)], 1)
+    centre = 0.5 + 1e-4 * rng.standard_normal((1024, 2))
+    ring2 = 0.5 + 0.3 * (1.0 + 1e-3 * rng.standard_normal((512, 1))) * np.stack([np.cos(rng.uniform(0, 6.3, 512)), np.sin(rng.uniform(0, 6.3, 512))], 1)
+    anywhere = rng.uniform(0.0, 1.0, (2048, 2))
+    xy = np.ascontiguousarray(np.concatenate([circ, centre, anywhere, ring2, np.full((37, 2), 0.5)]))
+    segs = np.stack([np.arange(ncirc), (np.arange(ncirc) + 1) % ncirc], 1).astype(np.int32)
+    nv = xy.shape[0]
+    cells = np.array([[0, 1, 2]], np.int32); perm = np.array([0x24], np.uint8)
+    ctx = gpu_ctx_factory(2)
+    ctx.upload_mesh(xy, cells, perm, np.zeros((0, 4), np.int32), segs)
+    ref = oracle.distance_2d(xy, segs)
+    d, mx = ctx.distance_update()                                       # cold
+    assert np.array_equal(d, ref) and mx == oracle.distance_max(ref)
+    d, mx = ctx.distance_update()                                       # warm
+    assert np.array_equal(d, ref) and mx == oracle.distance_max(ref)
+    tm_names = None
+    ctx.timing_enable(True); ctx.timing_reset(); ctx.distance_update(); tm_names = ctx.timing_get(); ctx.timing_enable(False)
+    assert "distance2d_wide" in tm_names
+    s = 0.05 * rng.standard_normal((nv, 2)); s[:ncirc] *= 0.02            # the interface wobbles, the queries move a lot
+    ctx.move_vertices(s)
+    xy2 = oracle.move(xy, s)
+    ref2 = oracle.distance_2d(xy2, segs)
+    d2, mx2 = ctx.distance_update()
+    assert np.array_equal(d2, ref2) and mx2 == oracle.distance_max(ref2)
+    assert (ref[ncirc:ncirc + 1024] > 0.29).all()                          # the centre really is equidistant

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dune-mmesh_b200
 import numpy as np
 from mmesh_b200 import capi, synth
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-m = synth.config3(nx=nx, ny=nx // 2)
+m = synth.config3(nx=nx, ny=nx // 2) if nx > 0 else synth.config2()
 s = synth.shifts_uniform(m, 0.3 * m.h, 30)
 ctx = capi.Context(2, 0)
 ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
@@ -18,8 +18,9 @@ def run(tag):
     if hasattr(L, "mmb_dev_counters"):
         L.mmb_dev_counters(ctx._h, out)
     w = max(out[0], 1)
-    print("%-28s distance2d %.4f ms  bvh %.4f ms | warps %d flat %.3f  groups/warp %.1f  group-passes/warp %.1f  evals/warp(union) %.1f  evals/lane %.2f" % (
-        tag, tm["distance2d"][0] / tm["distance2d"][1], tm["bvh_build2d"][0] / tm["bvh_build2d"][1], out[0], out[1] / w, out[2] / max(out[1], 1), out[3] / w, out[4] / w, out[5] / w / 32), flush=True)
+    wide = tm["distance2d_wide"][0] / tm["distance2d_wide"][1] if "distance2d_wide" in tm else 0.0
+    print("%-28s distance2d %.4f ms  wide %.4f ms  bvh %.4f ms | warps %d flat %.3f  groups/warp %.1f  group-passes/warp %.1f  evals/warp(union) %.1f  evals/lane %.2f" % (
+        tag, tm["distance2d"][0] / tm["distance2d"][1], wide, tm["bvh_build2d"][0] / tm["bvh_build2d"][1], out[0], out[1] / w, out[2] / max(out[1], 1), out[3] / w, out[4] / w, out[5] / w / 32), flush=True)
 run("cold (after upload)")
 run("warm, mesh unchanged")
 ctx.move_vertices(s); run("warm, after move +s")
