@@ -641,7 +641,7 @@ k_distance2d(const double2* __restrict__ xy, int64_t nv, const SegLeaf* __restri
 // work of such a vertex (every facet of a closed curve seen from its centre is about equally far) is spread over a warp and
 // the vertices over the whole grid, instead of 32 lanes walking the tree one after the other.  Same conservative culls, same
 // per-facet arithmetic: the minimum over all facets with the brute-force bits.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_distance2d_wide(const double2* __restrict__ xy, const SegLeaf* __restrict__ leaf, const float4* __restrict__ box, int ns, int L,
                   double* __restrict__ dist, int32_t* __restrict__ hint, const int32_t* __restrict__ seed,
                   const int32_t* __restrict__ wide, Counters* __restrict__ cnt) {
@@ -673,31 +673,40 @@ k_distance2d_wide(const double2* __restrict__ xy, const SegLeaf* __restrict__ le
       h = min(max(sd, 0), ns - 1);
     }
     q.eval_leaf(leaf, h);                                 // every lane holds the same bound from here on
-    for (int base = 0; base < ng; base += 32) {
-      const int g = base + lane;
-      unsigned m = __ballot_sync(0xffffffffu, g < ng && !(q.lb2(__ldg(box + G0 + g)) > q.T2f));
-      while (m) {
-        // up to four passing groups, eight lanes each
-        int gsel = -1;
-        unsigned mm = m;
+    // two levels: the boxes of 32 "super groups" (tree nodes five levels above the groups, 32 groups each) per round, then
+    // the groups of the super groups that pass.  A tree with fewer than 256 leaves has no such level: all groups then.
+    const bool two_level = G0 >= 32;
+    const int S0 = G0 >> 5, nsg = two_level ? (ng + 31) >> 5 : 1;
+    for (int sb = 0; sb < nsg; sb += 32) {
+      unsigned ms = 1u;
+      if (two_level) { const int j = sb + lane; ms = __ballot_sync(0xffffffffu, j < nsg && !(q.lb2(__ldg(box + S0 + j)) > q.T2f)); }
+      while (ms) {
+        const int sj = __ffs(ms) - 1; ms &= ms - 1;
+        const int b0 = two_level ? (sb + sj) << 5 : 0, b1 = two_level ? min(b0 + 32, ng) : ng;
+        for (int base = b0; base < b1; base += 32) {
+          const int g = base + lane;
+          unsigned m = __ballot_sync(0xffffffffu, g < b1 && !(q.lb2(__ldg(box + G0 + g)) > q.T2f));
+          while (m) {
+            int gsel = -1;                                  // up to four passing groups, eight lanes each
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-          const int b = mm ? __ffs(mm) - 1 : -1;
-          if (mm) mm &= mm - 1;
-          if ((lane >> DIST_GROUP_LOG) == sl) gsel = b;
-        }
-        m = mm;
-        double d = 1e300; int s = -1;
-        if (gsel >= 0) {
-          s = ((base + gsel) << DIST_GROUP_LOG) + (lane & (DIST_GROUP - 1));
-          if (s < ns && !(q.lb2(__ldg(box + L + s)) > q.T2f)) d = seg_distance(leaf[s], q.px, q.py); else s = -1;
-        }
+            for (int sl = 0; sl < 4; ++sl) {
+              const int b = m ? __ffs(m) - 1 : -1;
+              if (m) m &= m - 1;
+              if ((lane >> DIST_GROUP_LOG) == sl) gsel = b;
+            }
+            double d = 1e300; int s = -1;
+            if (gsel >= 0) {
+              s = ((base + gsel) << DIST_GROUP_LOG) + (lane & (DIST_GROUP - 1));
+              if (s < ns && !(q.lb2(__ldg(box + L + s)) > q.T2f)) d = seg_distance(leaf[s], q.px, q.py); else s = -1;
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double od = __shfl_xor_sync(0xffffffffu, d, o); const int os = __shfl_xor_sync(0xffffffffu, s, o);
-          if (od < d || (od == d && os >= 0 && (s < 0 || os < s))) { d = od; s = os; }
+            for (int o = 16; o > 0; o >>= 1) {              // warp minimum, lowest facet index among equal distances
+              const double od = __shfl_xor_sync(0xffffffffu, d, o); const int os = __shfl_xor_sync(0xffffffffu, s, o);
+              if (od < d || (od == d && os >= 0 && (s < 0 || os < s))) { d = od; s = os; }
+            }
+            if (s >= 0 && d < q.best) { q.best = d; q.arg = s; q.set_threshold(); }
+          }
         }
-        if (s >= 0 && d < q.best) { q.best = d; q.arg = s; q.set_threshold(); }
       }
     }
     if (lane == 0) { dist[v] = q.best; hint[v] = q.arg; }

@@ -159,6 +159,8 @@ def global_indicator_params(m):
 
 
 def bench_main(args, world, rank, local_rank, METRIC, UNIT, algorithmic_bytes, ClockSampler, make_workload, tune_params, projection_mode):
+    # NCCL writes its version / debug lines to stdout by default; the bench prints ONE JSON line there
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)

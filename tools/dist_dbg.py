@@ -26,3 +26,12 @@ run("warm, mesh unchanged")
 ctx.move_vertices(s); run("warm, after move +s")
 ctx.move_vertices(-s); run("warm, after move -s")
 ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs); run("cold again")
+if nx > 0 and len(sys.argv) > 2:                             # one shard of an 8-way partition: 1/8 of the vertices, the whole interface
+    from mmesh_b200 import partition
+    for rank in (0, 3, 5):
+        sh = partition.make_shard(m, 8, rank, all_halo_lists=False)
+        ctx = capi.Context(2, 0)
+        ctx.upload_mesh(sh.xy, sh.cells, sh.perm, sh.edges, sh.segs)
+        run("shard %d of 8 (%d vertices), cold" % (rank, sh.xy.shape[0]))
+        run("shard %d of 8, warm" % rank)
+        run("shard %d of 8, warm" % rank)
