@@ -457,4 +457,11 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line.  Whatever native libraries print to file descriptor 1 while the bench runs (NCCL's
+    # version banner at communicator creation, ...) is sent to stderr; Python's own stdout keeps the real descriptor.
+    sys.stdout.flush()
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real, "w")
     main()
+    sys.stdout.flush()

@@ -29,14 +29,15 @@ for name, (ms, cnt) in sorted(tm.items(), key=lambda kv: -kv[1][0]):
 # the oracle on the host: validity and marks over all cells, the brute-force distance estimate (distance.hh:157-173, O(Nv * Ns)) on a
 # sample of the vertices and scaled to all of them
 d_gpu, _ = ctx.distance_update()
+xyz = ctx.download_coords()                                 # the mesh where the steps above left it
 for thr in (1, os.cpu_count()):
     oracle.set_threads(thr)
-    t0 = time.perf_counter(); oracle.trial_validate(m.xyz, s, m.cells, dim=3); t1 = time.perf_counter()
+    t0 = time.perf_counter(); oracle.trial_validate(xyz, s, m.cells, dim=3); t1 = time.perf_counter()
     nsub = 4096 * thr
     vidx = np.linspace(0, m.nv - 1, nsub).astype(np.int64)
-    t2 = time.perf_counter(); od = oracle.distance_3d_subset(m.xyz, vidx, m.tris); t3 = time.perf_counter()
+    t2 = time.perf_counter(); od = oracle.distance_3d_subset(xyz, vidx, m.tris); t3 = time.perf_counter()
     oprm = oracle.Params.from_buffer_copy(bytes(ctx.get_params()))
-    t4 = time.perf_counter(); oracle.mark(m.xyz, d_gpu, m.cells, m.perm, oprm, oprm.distProportion * float(d_gpu.max()), dim=3); t5 = time.perf_counter()
+    t4 = time.perf_counter(); oracle.mark(xyz, d_gpu, m.cells, m.perm, oprm, oprm.distProportion * float(d_gpu.max()), dim=3); t5 = time.perf_counter()
     t_dist = (t3 - t2) * m.nv / nsub
     tot_cpu = (t1 - t0) + t_dist + (t5 - t4)
     print("  oracle, %2d thread(s): validity %.0f ms, marks %.0f ms, brute-force distance %.0f ms (from %d of %d vertices) -> %.3g cells/s" % (
