@@ -1,7 +1,7 @@
 """Delaunay restoration by device flips (mmb_restore_delaunay) on the config-3 mesh after one vertex move, timed beside the
 oracle's sequential Lawson iteration on the host.  usage: flip_bench.py [nx] [amp]"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dune-mmesh_b200", "python"))
 import numpy as np
 from mmesh_b200 import capi, synth

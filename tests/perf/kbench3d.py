@@ -1,6 +1,6 @@
 """Config 5 (3-D, 8 M Kuhn tets): vertex movement + orient3d validity + distance estimate + marks + P0 trace/skeleton."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dune-mmesh_b200", "python"))
 import numpy as np
 from mmesh_b200 import capi, synth

@@ -1,7 +1,7 @@
 """Config 4: near-degenerate cocircular/collinear 1025x1025 lattice perturbed by 1e-15 -- every predicate falls through the
 static filter; measures the exact-fallback kernels (interval, then expansions)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dune-mmesh_b200", "python"))
 import time
 import numpy as np
