@@ -2042,9 +2042,12 @@ k_cells_to_planes(const int32_t* __restrict__ aos, int k, int64_t nc, int64_t nc
 __global__ void __launch_bounds__(128)
 k_flip_mark(const double* __restrict__ xy, const int32_t* __restrict__ cv0, const int32_t* __restrict__ cv1, const int32_t* __restrict__ cv2,
             const int32_t* __restrict__ nb, const uint8_t* __restrict__ v_if, const unsigned long long* __restrict__ keys, int nkeys,
-            int64_t nc, unsigned* __restrict__ claim, uint8_t* __restrict__ ill, FlipCounts* __restrict__ fc) {
+            int64_t nc, const uint8_t* __restrict__ active, unsigned* __restrict__ claim, uint8_t* __restrict__ ill, FlipCounts* __restrict__ fc) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
+  // only cells whose own or neighbouring triangles changed in the last round (or whose illegal edge was deferred) can own an
+  // illegal edge: every other cell was legal when it was last tested and nothing it depends on has changed since
+  if (!active[c]) { ill[c] = 0; return; }
   unsigned cnt[5] = { 0, 0, 0, 0, 0 };
   ill[c] = (uint8_t)flip_mark_cell(c, xy, cv0, cv1, cv2, nb, v_if, keys, nkeys,
                                    [&](int64_t cell, unsigned id) { atomicMin(claim + cell, id); }, [&](int which) { cnt[which]++; });
@@ -2062,7 +2065,8 @@ k_flip_select(const int32_t* __restrict__ nb, const unsigned* __restrict__ claim
 }
 __global__ void __launch_bounds__(256)
 k_flip_apply(int32_t* cv0, int32_t* cv1, int32_t* cv2, int32_t* nb, int32_t* __restrict__ aos, const int64_t* __restrict__ vid,
-             uint8_t* perm, const uint8_t* __restrict__ sel, int64_t nc, FlipCounts* __restrict__ fc) {
+             uint8_t* perm, const uint8_t* __restrict__ sel, const uint8_t* __restrict__ ill, uint8_t* __restrict__ active_next, int64_t nc,
+             FlipCounts* __restrict__ fc) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int k1 = c < nc ? sel[c] : 0;
   if (k1) {
@@ -2070,6 +2074,16 @@ k_flip_apply(int32_t* cv0, int32_t* cv1, int32_t* cv2, int32_t* nb, int32_t* __r
     flip_apply_cell(c, k1 - 1, cv0, cv1, cv2, nb, vid, perm);
     aos[3 * c] = cv0[c]; aos[3 * c + 1] = cv1[c]; aos[3 * c + 2] = cv2[c];
     aos[3 * (int64_t)n] = cv0[n]; aos[3 * (int64_t)n + 1] = cv1[n]; aos[3 * (int64_t)n + 2] = cv2[n];
+    // next round: the two new cells and everything around them (an edge is tested by its lower cell, which may be a neighbour)
+    active_next[c] = 1; active_next[n] = 1;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int32_t a = nb[3 * c + j], b = nb[3 * (int64_t)n + j];
+      if (a >= 0) active_next[a] = 1;
+      if (b >= 0) active_next[b] = 1;
+    }
+  } else if (c < nc && ill[c]) {
+    active_next[c] = 1;                                   // an illegal edge that had to wait for a neighbouring flip
   }
   const unsigned m = __ballot_sync(0xffffffffu, k1 != 0);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fc->flips, (unsigned long long)__popc(m));

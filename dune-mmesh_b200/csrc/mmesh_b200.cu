@@ -1596,23 +1596,25 @@ int mmb_restore_delaunay(mmb_context* ctx, const int64_t* vertex_id_host, int32_
   const int64_t nc = ctx->nc, nv = ctx->nv;
   REQUIRE(3 * nc < 0xffffffffll, MMB_ERR_CAPACITY, "mmb_restore_delaunay: edge ids exceed 32 bits");
   if (nc == 0) { if (out) out->converged = 1; return MMB_OK; }
-  DBuf<unsigned> claim; DBuf<uint8_t> ill, sel; DBuf<FlipCounts> fc; DBuf<int64_t> vid;
-  auto release = [&]() { claim.release(); ill.release(); sel.release(); fc.release(); vid.release(); };
+  DBuf<unsigned> claim; DBuf<uint8_t> ill, sel, act, act_next; DBuf<FlipCounts> fc; DBuf<int64_t> vid;
+  auto release = [&]() { claim.release(); ill.release(); sel.release(); act.release(); act_next.release(); fc.release(); vid.release(); };
   auto fail = [&](cudaError_t e) { ctx->err = std::string("mmb_restore_delaunay: ") + cudaGetErrorString(e); release(); return (int)MMB_ERR_CUDA; };
   cudaError_t e;
-  if ((e = claim.ensure((size_t)nc)) || (e = ill.ensure((size_t)nc)) || (e = sel.ensure((size_t)nc)) || (e = fc.ensure(1)) ||
-      (vertex_id_host && (e = vid.ensure((size_t)nv)))) return fail(e);
+  if ((e = claim.ensure((size_t)nc)) || (e = ill.ensure((size_t)nc)) || (e = sel.ensure((size_t)nc)) || (e = act.ensure((size_t)nc)) ||
+      (e = act_next.ensure((size_t)nc)) || (e = fc.ensure(1)) || (vertex_id_host && (e = vid.ensure((size_t)nv)))) return fail(e);
   cudaStream_t S = ctx->stream;
   if (vertex_id_host && (e = cudaMemcpyAsync(vid.p, vertex_id_host, (size_t)nv * sizeof(int64_t), cudaMemcpyHostToDevice, S))) return fail(e);
   cudaMemsetAsync(fc.p, 0, sizeof(FlipCounts), S);
+  cudaMemsetAsync(act.p, 1, (size_t)nc, S);
   FlipCounts h; std::memset(&h, 0, sizeof(h));
   int rounds = 0, converged = 0;
+  bool full = true;                                           // the sweep covers every cell (first round, and the one that reports)
   for (;;) {
     // mark: counts of this sweep (flips accumulate)
     cudaMemsetAsync(fc.p, 0, offsetof(FlipCounts, flips), S);
     cudaMemsetAsync(claim.p, 0xff, (size_t)nc * sizeof(unsigned), S);
     LAUNCH("flip_mark", k_flip_mark, grid_for(nc, 128), 128, ctx->x.p, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->cell_nb.p, ctx->v_if.p,
-           ctx->facet_keys.p, (int)ctx->n_facet_keys, nc, claim.p, ill.p, fc.p);
+           ctx->facet_keys.p, (int)ctx->n_facet_keys, nc, act.p, claim.p, ill.p, fc.p);
     if ((e = cudaMemcpyAsync(&h, fc.p, sizeof(FlipCounts), cudaMemcpyDeviceToHost, S)) || (e = cudaStreamSynchronize(S))) return fail(e);
     if (h.broken) { release(); REQUIRE(false, MMB_ERR_INVALID_ARG, "mmb_restore_delaunay: the neighbour table is not symmetric"); }
     if (h.domain) { release(); REQUIRE(false, MMB_ERR_CAPACITY, "mmb_restore_delaunay: coordinates outside the exact predicates' exponent range"); }
@@ -1620,11 +1622,20 @@ int mmb_restore_delaunay(mmb_context* ctx, const int64_t* vertex_id_host, int32_
       release();
       REQUIRE(false, MMB_ERR_STATE, "mmb_restore_delaunay: " + std::to_string(h.inverted) + " cells are not positively oriented; flips need a valid triangulation (ensureVertexMovement first)");
     }
-    if (h.illegal == 0) { converged = 1; break; }
-    if (rounds >= max_rounds) break;
+    const bool done = h.illegal == 0, out_of_rounds = rounds >= max_rounds;
+    if (done || out_of_rounds) {
+      // the counts reported come from a sweep over ALL cells (a partial sweep sees every illegal edge, but not every illegal
+      // interface edge); for `done` that sweep also confirms the result independently of the bookkeeping of active cells
+      if (!full) { cudaMemsetAsync(act.p, 1, (size_t)nc, S); full = true; continue; }
+      converged = done ? 1 : 0;
+      break;
+    }
+    cudaMemsetAsync(act_next.p, 0, (size_t)nc, S);
     LAUNCH("flip_select", k_flip_select, grid_for(nc, 256), 256, ctx->cell_nb.p, claim.p, ill.p, nc, sel.p);
     LAUNCH("flip_apply", k_flip_apply, grid_for(nc, 256), 256, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->cell_nb.p, ctx->cells_aos.p,
-           vertex_id_host ? vid.p : (const int64_t*)nullptr, ctx->perm.p, sel.p, nc, fc.p);
+           vertex_id_host ? vid.p : (const int64_t*)nullptr, ctx->perm.p, sel.p, ill.p, act_next.p, nc, fc.p);
+    std::swap(act.p, act_next.p); std::swap(act.cap, act_next.cap);
+    full = false;
     ++rounds;
   }
   if (out) {

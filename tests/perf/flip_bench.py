@@ -1,5 +1,5 @@
 """Delaunay restoration by device flips (mmb_restore_delaunay) on the config-3 mesh after one vertex move, timed beside the
-oracle's sequential Lawson iteration on the host.  usage: flip_bench.py [nx] [amp]"""
+oracle's sequential Lawson iteration on the host.  usage: flip_bench.py [nx] [amp] [nooracle]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dune-mmesh_b200", "python"))
@@ -36,6 +36,8 @@ for k in sorted(tm, key=lambda k: -tm[k][0]):
 cells, perm, nb, edges = ctx.download_topology()
 flags, nill2 = ctx.legality()
 print("after: %d illegal edges (constrained %d)" % (nill2, res["n_constrained_illegal"]), flush=True)
+if len(sys.argv) > 3 and sys.argv[3] == "nooracle":
+    sys.exit(0)
 t3 = time.perf_counter()
 oc, onb, oflips = oracle.restore_delaunay_2d(xy, m.cells, m.nb, m.segs)
 t4 = time.perf_counter()

@@ -52,6 +52,21 @@ def host_flip():
         return dict(cells=cells, nb=nb, perm=perm, flips=int(res[0]), rounds=int(res[1]), converged=int(res[2]), illegal=int(res[3]),
                     constrained=int(res[4]), inverted=int(res[5]), broken=int(res[6]), trace=trace[:int(res[1])])
 
+    def restore_active(xy, cells, nb, segs, vid=None, max_rounds=1000, perm=None):
+        xy = np.ascontiguousarray(xy, np.float64)
+        cells = np.ascontiguousarray(cells, np.int32).copy(); nb = np.ascontiguousarray(nb, np.int32).copy()
+        nc, nv = cells.shape[0], xy.shape[0]
+        v_if, keys = facet_keys(np.asarray(segs).reshape(-1, 2), nv)
+        perm = np.zeros(nc, np.uint8) if perm is None else np.ascontiguousarray(perm, np.uint8).copy()
+        res = np.zeros(8, np.int64)
+        vid64 = None if vid is None else np.ascontiguousarray(vid, np.int64)
+        L.hf_restore_active(P(xy), C.c_long(nv), P(cells), P(nb), P(perm), C.c_long(nc), P(v_if), P(keys), C.c_int(keys.shape[0]), P(vid64),
+                            C.c_int(max_rounds), P(res))
+        return dict(cells=cells, nb=nb, perm=perm, flips=int(res[0]), rounds=int(res[1]), converged=int(res[2]), illegal=int(res[3]),
+                    constrained=int(res[4]), inverted=int(res[5]), broken=int(res[6]), tested=int(res[7]))
+
+    restore.active = restore_active
+
     def edges(cells, nb, cap):
         out = np.zeros((cap, 4), np.int32)
         n = L.hf_edges(P(np.ascontiguousarray(cells, np.int32)), P(np.ascontiguousarray(nb, np.int32)), C.c_long(cells.shape[0]), P(out), C.c_long(cap))
@@ -168,3 +183,21 @@ def test_corner_permutation_helper(host_flip):
     import itertools
     for ids in itertools.permutations((11, 42, 97)):
         assert host_flip.perm(*ids) == int(synth.pack_perm(np.array([ids]))[0])
+
+
+@pytest.mark.parametrize("n,curved,max_rounds", [(40, False, 1000), (64, True, 1000), (48, True, 3), (32, False, 0)])
+def test_active_cell_bookkeeping_changes_nothing(host_flip, oracle, n, curved, max_rounds):
+    """mmb_restore_delaunay re-tests only the cells around the flips of the previous round (and the cells whose illegal edge had to
+    wait).  Same flips, rounds, arrays and counts as sweeping every cell in every round -- with far fewer cells tested."""
+    curves = ()
+    if curved:
+        t = np.linspace(0.0, 2.0 * np.pi, 400)
+        curves = ((np.stack([0.5 + 0.27 * np.cos(t), 0.5 + 0.27 * np.sin(t)], 1), True),)
+    m, xy = moved_mesh(oracle, n, 0.27, 40 + n, curves=curves)
+    a = host_flip(xy, m.cells, m.nb, m.segs, vid=m.vid, perm=m.perm, max_rounds=max_rounds)
+    b = host_flip.active(xy, m.cells, m.nb, m.segs, vid=m.vid, perm=m.perm, max_rounds=max_rounds)
+    for k in ("flips", "rounds", "converged", "illegal", "constrained", "inverted", "broken"):
+        assert a[k] == b[k], k
+    assert np.array_equal(a["cells"], b["cells"]) and np.array_equal(a["nb"], b["nb"]) and np.array_equal(a["perm"], b["perm"])
+    if max_rounds >= 1000:
+        assert b["tested"] < 0.5 * (a["rounds"] + 1) * m.nc
