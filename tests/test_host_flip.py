@@ -201,3 +201,31 @@ def test_active_cell_bookkeeping_changes_nothing(host_flip, oracle, n, curved, m
     assert np.array_equal(a["cells"], b["cells"]) and np.array_equal(a["nb"], b["nb"]) and np.array_equal(a["perm"], b["perm"])
     if max_rounds >= 1000:
         assert b["tested"] < 0.5 * (a["rounds"] + 1) * m.nc
+
+
+@pytest.mark.parametrize("npts,seed", [(300, 1), (3000, 2), (20000, 3)])
+def test_flips_on_irregular_triangulations(host_flip, oracle, npts, seed):
+    """Random point clouds: the Delaunay triangulation of an affinely distorted copy (y -> 4 y + x) is a valid triangulation of the
+    original points with the same hull, but far from Delaunay -- long chains of dependent flips, vertices of every degree.
+    Restoring it must give Qhull's Delaunay triangulation of the original points, through the plain and the active-cell rounds."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    xy = rng.uniform(0.0, 1.0, (npts, 2))
+    warped = np.stack([xy[:, 0], 4.0 * xy[:, 1] + xy[:, 0]], 1)
+    cells = Delaunay(warped).simplices.astype(np.int32)
+    a = xy[cells]
+    area2 = (a[:, 1, 0] - a[:, 0, 0]) * (a[:, 2, 1] - a[:, 0, 1]) - (a[:, 2, 0] - a[:, 0, 0]) * (a[:, 1, 1] - a[:, 0, 1])
+    cells[area2 < 0] = cells[area2 < 0][:, [0, 2, 1]]                     # counter-clockwise, as a TDS stores them
+    _, nb, _ = synth.build_edges(cells, npts)
+    valid, _, _ = oracle.trial_validate(xy, None, cells)
+    assert valid.all()
+    want = tri_set(Delaunay(xy).simplices)
+    assert tri_set(cells) != want
+    r = host_flip(xy, cells, nb, np.zeros((0, 2), np.int32))
+    assert r["converged"] == 1 and r["flips"] > npts // 2 and tri_set(r["cells"]) == want
+    e_ref, nb_ref, _ = synth.build_edges(r["cells"], npts)
+    assert np.array_equal(r["nb"], nb_ref)
+    ra = host_flip.active(xy, cells, nb, np.zeros((0, 2), np.int32))
+    assert (ra["flips"], ra["rounds"]) == (r["flips"], r["rounds"]) and np.array_equal(ra["cells"], r["cells"]) and np.array_equal(ra["nb"], r["nb"])
+    oc, _, oflips = oracle.restore_delaunay_2d(xy, cells, nb)
+    assert tri_set(oc) == want
