@@ -346,11 +346,13 @@ def main():
     kern.sort(key=lambda k: -k["share"])
     dom = kern[0]
     traffic = None
+    pipes = None
     for tf in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
         try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this workload
             tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
             if tj.get("cells") == nc and dom["kernel"] in tj["kernels"]:
                 traffic = tj["kernels"][dom["kernel"]]
+                pipes = tj.get("pipes", {}).get(dom["kernel"])
                 break
         except Exception:
             pass
@@ -360,6 +362,8 @@ def main():
                                        "active lanes, 31 % warps, DRAM traffic = 1.00 x algorithmic bytes), not HBM bound; see DESIGN.md section 4",
                          "distance2d": "instruction-issue bound (ncu: issue 84 %, 27/32 lanes, 3.3 k warp instructions per warp of 32 "
                                        "vertices for the conservative tree search), not HBM bound"}.get(dom["kernel"], "see DESIGN.md section 4")}
+    if pipes:       # what actually bounds the kernel, from the committed ncu capture of this workload (not a live measurement)
+        roofline["ncu_pipes"] = pipes
 
     # ---- cold distance field: first Distance::update after a snapshot upload (no hints yet), as after every TDS edit ----
     ctx.upload_mesh(m.xy, m.cells, m.perm, m.edges, m.segs)
