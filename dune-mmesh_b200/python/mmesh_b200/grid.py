@@ -184,6 +184,19 @@ class MMesh:
         self._marks[:] = 0
         self.removed = []
 
+    def restoreDelaunay(self, max_rounds=1000):
+        """Delaunay restoration of the resident 2-D snapshot by edge flips on the device (mmb_restore_delaunay; the flips of
+        CGAL/Delaunay_triangulation_2.h:936-1022, interface edges kept).  The snapshot object receives the new cells, corner
+        permutations, neighbours and edges.  Returns the flip statistics."""
+        m = self._m
+        res = self._ctx.restore_delaunay(vertex_id=getattr(m, "vid", None), max_rounds=max_rounds)
+        if res["n_flips"]:
+            m.cells, m.perm, m.nb, edges = self._ctx.download_topology()
+            if edges is not None:
+                m.edges = edges
+            self._marks[:] = 0
+        return res
+
     def indicator(self):
         return self._indicator
 

@@ -57,3 +57,35 @@ def test_distance_integral_and_user_loop(oracle):
     assert np.array_equal(grid2.coordinates(), expect)
     with pytest.raises(AssertionError):
         grid.moveVertices(shifts[:-1])                          # wrong size, as the assert at mmesh.hh:1423
+
+
+def test_restore_delaunay_through_the_grid_class(oracle):
+    """MMesh.restoreDelaunay: the snapshot object receives the flipped topology; the same triangulation as the oracle's sequential
+    Lawson iteration; the next user loop runs on it."""
+    from mmesh_b200 import synth
+    from mmesh_b200.grid import MMesh
+    m = synth.config1(n=48)
+    s = synth.shifts_uniform(m, 0.25 * m.h, 77)
+    s[np.unique(m.segs.ravel())] = 0.0
+    for _ in range(60):
+        valid, _, ninv = oracle.trial_validate(m.xy + s, None, m.cells)
+        if ninv == 0:
+            break
+        s[np.unique(m.cells[valid == 0].ravel())] *= 0.5
+    m.xy = np.ascontiguousarray(m.xy + s)
+    cells0, nb0 = m.cells.copy(), m.nb.copy()
+    grid = MMesh(m)
+    res = grid.restoreDelaunay()
+    assert res["converged"] == 1 and res["n_flips"] > 0
+    oc, _, _ = oracle.restore_delaunay_2d(m.xy, cells0, nb0, m.segs)
+    tri = lambda c: set(map(tuple, np.sort(np.asarray(c, np.int64), axis=1).tolist()))
+    assert tri(m.cells) == tri(oc) and tri(m.cells) != tri(cells0)
+    e_ref, nb_ref, _ = synth.build_edges(m.cells, m.nv)
+    assert np.array_equal(m.edges, e_ref) and np.array_equal(m.nb, nb_ref) and np.array_equal(m.perm, synth.pack_perm(m.vid[m.cells]))
+    grid.indicator().init()
+    grid.markElements()
+    d = oracle.distance_2d(m.xy, m.segs)
+    prm = oracle.Params.from_buffer_copy(bytes(grid._ctx.get_params()))
+    rm, _, _ = oracle.mark(m.xy, d, m.cells, m.perm, prm, oracle.distance_max(d))
+    assert [grid.getMark(c) for c in range(m.nc)] == [int(v) for v in rm]
+    assert grid.restoreDelaunay()["n_flips"] == 0
