@@ -229,3 +229,34 @@ def test_flips_on_irregular_triangulations(host_flip, oracle, npts, seed):
     assert (ra["flips"], ra["rounds"]) == (r["flips"], r["rounds"]) and np.array_equal(ra["cells"], r["cells"]) and np.array_equal(ra["nb"], r["nb"])
     oc, _, oflips = oracle.restore_delaunay_2d(xy, cells, nb)
     assert tri_set(oc) == want
+
+
+def test_flips_on_irregular_triangulations_with_constraints(host_flip, oracle):
+    """The same distorted triangulations with a random tenth of their interior edges declared interface: the constrained edges stay,
+    the result equals the oracle's sequential iteration with the same constraints, every edge still failing the in-circle test is a
+    constraint, and the count of those is what the pass reports."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(8)
+    npts = 4000
+    xy = rng.uniform(0.0, 1.0, (npts, 2))
+    warped = np.stack([xy[:, 0], 4.0 * xy[:, 1] + xy[:, 0]], 1)
+    cells = Delaunay(warped).simplices.astype(np.int32)
+    a = xy[cells]
+    area2 = (a[:, 1, 0] - a[:, 0, 0]) * (a[:, 2, 1] - a[:, 0, 1]) - (a[:, 2, 0] - a[:, 0, 0]) * (a[:, 1, 1] - a[:, 0, 1])
+    cells[area2 < 0] = cells[area2 < 0][:, [0, 2, 1]]
+    edges, nb, _ = synth.build_edges(cells, npts)
+    inner = np.nonzero(edges[:, 3] >= 0)[0]
+    segs = np.ascontiguousarray(edges[rng.choice(inner, len(inner) // 10, replace=False), :2])
+    r = host_flip(xy, cells, nb, segs)
+    ra = host_flip.active(xy, cells, nb, segs)
+    assert r["converged"] == 1 and r["flips"] > 0 and r["constrained"] > 0
+    assert (ra["flips"], ra["rounds"], ra["constrained"]) == (r["flips"], r["rounds"], r["constrained"]) and np.array_equal(ra["cells"], r["cells"])
+    oc, _, _ = oracle.restore_delaunay_2d(xy, cells, nb, segs)
+    assert tri_set(oc) == tri_set(r["cells"])
+    e, _, _ = synth.build_edges(r["cells"], npts)
+    ekeys = set(map(tuple, np.sort(e[:, :2], axis=1).tolist()))
+    skeys = set(map(tuple, np.sort(segs, axis=1).tolist()))
+    assert skeys <= ekeys
+    flags, nill = oracle.legality(xy, None, e)
+    bad = e[flags == 0]
+    assert nill == r["constrained"] and all(tuple(sorted(q[:2])) in skeys for q in bad.tolist())
