@@ -2066,7 +2066,7 @@ k_flip_select(const int32_t* __restrict__ nb, const unsigned* __restrict__ claim
 __global__ void __launch_bounds__(256)
 k_flip_apply(int32_t* cv0, int32_t* cv1, int32_t* cv2, int32_t* nb, int32_t* __restrict__ aos, const int64_t* __restrict__ vid,
              uint8_t* perm, const uint8_t* __restrict__ sel, const uint8_t* __restrict__ ill, uint8_t* __restrict__ active_next, int64_t nc,
-             FlipCounts* __restrict__ fc) {
+             FlipCounts* __restrict__ fc, uint32_t* __restrict__ log, unsigned long long log_cap) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int k1 = c < nc ? sel[c] : 0;
   if (k1) {
@@ -2085,8 +2085,15 @@ k_flip_apply(int32_t* cv0, int32_t* cv1, int32_t* cv2, int32_t* nb, int32_t* __r
   } else if (c < nc && ill[c]) {
     active_next[c] = 1;                                   // an illegal edge that had to wait for a neighbouring flip
   }
+  // flip counter + log of (cell, slot) = the arguments of TDS::flip(f, i), one atomic per warp
   const unsigned m = __ballot_sync(0xffffffffu, k1 != 0);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fc->flips, (unsigned long long)__popc(m));
+  unsigned long long base = 0;
+  if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&fc->flips, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (k1) {
+    const unsigned long long pos = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+    if (pos < log_cap) log[pos] = 3u * (uint32_t)c + (uint32_t)(k1 - 1);
+  }
 }
 // edge list from cells + neighbours: per-block counts (COMPACT_TILE cells per block), k_compact_scan, emission
 __global__ void __launch_bounds__(256)

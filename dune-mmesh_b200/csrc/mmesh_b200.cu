@@ -81,6 +81,7 @@ struct mmb_context {
   DBuf<int32_t> wl, list_out;
   DBuf<uint32_t> block_count;
   DBuf<int32_t> tile_lo_cells, tile_lo_edges;
+  DBuf<uint32_t> flip_log; std::vector<int64_t> flip_round_off; int64_t flip_log_total = 0;   // last mmb_restore_delaunay
   DBuf<int32_t> cell_nb; bool have_nb = false; DBuf<uint8_t> v_if, cand_flag; DBuf<unsigned long long> facet_keys; int64_t n_facet_keys = 0;
   DBuf<unsigned long long> ht_key; DBuf<int32_t> ht_val, ht_slot;   // inserted_ of the 3-D candidate loop
   DBuf<uint8_t> v_bnd; DBuf<int32_t> v_ifcount, v_level, first_claim, first_seg, chosen; bool cand_ready = false, have_levels = false;
@@ -204,7 +205,7 @@ int mmb_destroy(mmb_context* ctx) {
   ctx->orient.release(); ctx->mark.release(); ctx->imark.release(); ctx->edges.release();
   ctx->wl.release(); ctx->list_out.release(); ctx->block_count.release(); ctx->counters.release();
   ctx->tile_lo_cells.release(); ctx->tile_lo_edges.release();
-  ctx->cell_nb.release(); ctx->v_if.release(); ctx->cand_flag.release(); ctx->facet_keys.release(); ctx->ht_key.release(); ctx->ht_val.release(); ctx->ht_slot.release();
+  ctx->flip_log.release(); ctx->cell_nb.release(); ctx->v_if.release(); ctx->cand_flag.release(); ctx->facet_keys.release(); ctx->ht_key.release(); ctx->ht_val.release(); ctx->ht_slot.release();
   ctx->v_bnd.release(); ctx->v_ifcount.release(); ctx->v_level.release(); ctx->first_claim.release(); ctx->first_seg.release(); ctx->chosen.release();
   ctx->seg_leaf.release(); ctx->box2.release(); ctx->seg_hint.release(); ctx->ticket.release(); ctx->tri_leaf.release(); ctx->box3.release(); ctx->seed_grid.release();
   ctx->new_off.release(); ctx->new_cell.release(); ctx->old_idx.release(); ctx->old_xy.release();
@@ -1606,6 +1607,8 @@ int mmb_restore_delaunay(mmb_context* ctx, const int64_t* vertex_id_host, int32_
   if (vertex_id_host && (e = cudaMemcpyAsync(vid.p, vertex_id_host, (size_t)nv * sizeof(int64_t), cudaMemcpyHostToDevice, S))) return fail(e);
   cudaMemsetAsync(fc.p, 0, sizeof(FlipCounts), S);
   cudaMemsetAsync(act.p, 1, (size_t)nc, S);
+  if ((e = ctx->flip_log.ensure((size_t)nc))) return fail(e);      // room for nc flips; beyond that only the count is kept
+  ctx->flip_round_off.clear(); ctx->flip_log_total = 0;
   FlipCounts h; std::memset(&h, 0, sizeof(h));
   int rounds = 0, converged = 0;
   bool full = true;                                           // the sweep covers every cell (first round, and the one that reports)
@@ -1630,14 +1633,17 @@ int mmb_restore_delaunay(mmb_context* ctx, const int64_t* vertex_id_host, int32_
       converged = done ? 1 : 0;
       break;
     }
+    ctx->flip_round_off.push_back((int64_t)h.flips);          // flips of the earlier rounds: where this round's log entries start
     cudaMemsetAsync(act_next.p, 0, (size_t)nc, S);
     LAUNCH("flip_select", k_flip_select, grid_for(nc, 256), 256, ctx->cell_nb.p, claim.p, ill.p, nc, sel.p);
     LAUNCH("flip_apply", k_flip_apply, grid_for(nc, 256), 256, ctx->cv[0].p, ctx->cv[1].p, ctx->cv[2].p, ctx->cell_nb.p, ctx->cells_aos.p,
-           vertex_id_host ? vid.p : (const int64_t*)nullptr, ctx->perm.p, sel.p, ill.p, act_next.p, nc, fc.p);
+           vertex_id_host ? vid.p : (const int64_t*)nullptr, ctx->perm.p, sel.p, ill.p, act_next.p, nc, fc.p, ctx->flip_log.p,
+           (unsigned long long)nc);
     std::swap(act.p, act_next.p); std::swap(act.cap, act_next.cap);
     full = false;
     ++rounds;
   }
+  ctx->flip_round_off.push_back((int64_t)h.flips); ctx->flip_log_total = (int64_t)h.flips;
   if (out) {
     out->n_flips = (int64_t)h.flips; out->n_illegal_left = (int64_t)h.illegal; out->n_constrained_illegal = (int64_t)h.constrained;
     out->rounds = rounds; out->converged = converged;
@@ -1665,6 +1671,21 @@ int mmb_restore_delaunay(mmb_context* ctx, const int64_t* vertex_id_host, int32_
   }
   if ((e = cudaStreamSynchronize(S))) return fail(e);
   release();
+  return MMB_OK;
+}
+int mmb_flip_log(mmb_context* ctx, uint32_t* edge_id_host, int64_t cap, int64_t* n_total, int64_t* round_off_host, int32_t round_cap,
+                 int32_t* n_rounds) {
+  if (!ctx) return MMB_ERR_INVALID_ARG;
+  REQUIRE(cap >= 0 && round_cap >= 0 && (cap == 0 || edge_id_host) && (round_cap == 0 || round_off_host), MMB_ERR_INVALID_ARG, "mmb_flip_log: bad arguments");
+  const int64_t rounds = ctx->flip_round_off.empty() ? 0 : (int64_t)ctx->flip_round_off.size() - 1;
+  if (n_total) *n_total = ctx->flip_log_total;
+  if (n_rounds) *n_rounds = (int32_t)rounds;
+  for (int64_t r = 0; r <= rounds && r < round_cap && !ctx->flip_round_off.empty(); ++r) round_off_host[r] = ctx->flip_round_off[(size_t)r];
+  const int64_t n = std::min<int64_t>(std::min<int64_t>(cap, ctx->flip_log_total), (int64_t)ctx->flip_log.cap);
+  if (n > 0) {
+    CK(cudaMemcpyAsync(edge_id_host, ctx->flip_log.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   return MMB_OK;
 }
 int mmb_download_topology(mmb_context* ctx, int32_t* cells_host, uint8_t* perm_host, int32_t* cell_nb_host, int32_t* edges_host) {

@@ -257,6 +257,22 @@ class MMesh {
     return r;
   }
 
+  //! The flips of the last restoreDelaunay as (cell, slot) = the arguments of Triangulation_data_structure_2::flip(f, i), round after
+  //! round (roundOffsets delimits the rounds; flips of one round touch disjoint cells).  An adapter that prefers replaying to copying
+  //! the tables calls tds().flip(faceOfIndex[cell], slot) for every entry, in this order.
+  struct FlipLog { std::vector<std::pair<int32_t, int>> flips; std::vector<int64_t> roundOffsets; int64_t total = 0; };
+  FlipLog lastFlips() const {
+    FlipLog log;
+    int32_t rounds = 0;
+    check(mmb_flip_log(ctx_, nullptr, 0, &log.total, nullptr, 0, &rounds));
+    std::vector<uint32_t> ids((std::size_t)std::max<int64_t>(log.total, 1));
+    log.roundOffsets.assign((std::size_t)rounds + 1, 0);
+    check(mmb_flip_log(ctx_, ids.data(), log.total, &log.total, log.roundOffsets.data(), rounds + 1, &rounds));
+    log.flips.reserve((std::size_t)log.total);
+    for (int64_t i = 0; i < log.total; ++i) log.flips.push_back({ (int32_t)(ids[(std::size_t)i] / 3u), (int)(ids[(std::size_t)i] % 3u) });
+    return log;
+  }
+
   //! mmesh.hh:1421-1430
   void moveVertices(const std::vector<Coordinate>& shifts) {
     requireSize(shifts);

@@ -21,7 +21,7 @@ EXPORTS = [
     "mmb_upload_pairs", "mmb_project", "mmb_intersection_volumes", "mmb_adapt_step", "mmb_adapt_step_host", "mmb_trace_skeleton_p0",
     "mmb_step_host_begin", "mmb_step_host_marks", "mmb_step_host_finish", "mmb_upload_neighbours", "mmb_refinement_candidates", "mmb_upload_vertex_levels", "mmb_coarsening_candidates", "mmb_interface_candidates", "mmb_project_interface_p0", "mmb_project_interface_p1", "mmb_refinement_points", "mmb_upload_dofs", "mmb_download_fields", "mmb_set_owned_cells", "mmb_halo_setup", "mmb_halo_pack_shifts", "mmb_halo_unpack_shifts", "mmb_device_buffer",
     "mmb_component_numbers", "mmb_host_register", "mmb_host_unregister", "mmb_comm_unique_id", "mmb_comm_init", "mmb_comm_destroy", "mmb_halo_counts", "mmb_adapt_step_sharded", "mmb_step_phase_distance", "mmb_step_phase_rest", "mmb_step_phase", "mmb_timing_enable", "mmb_timing_reset", "mmb_timing_get", "mmb_launch_count", "mmb_predicate_batch",
-    "mmb_restore_delaunay", "mmb_download_topology",
+    "mmb_restore_delaunay", "mmb_download_topology", "mmb_flip_log",
 ]
 
 
@@ -159,6 +159,14 @@ class Context:
         vid = None if vertex_id is None else np.ascontiguousarray(vertex_id, np.int64)
         self._ck(lib().mmb_restore_delaunay(self._h, _p(vid), C.c_int32(max_rounds), C.byref(r)))
         return {k: int(getattr(r, k)) for k, _ in FlipResult._fields_}
+
+    def flip_log(self):
+        """flips of the last restore_delaunay: (edge ids 3 * cell + slot in round order, round offsets [rounds + 1], total flips)"""
+        tot, nr = C.c_int64(), C.c_int32()
+        self._ck(lib().mmb_flip_log(self._h, None, C.c_int64(0), C.byref(tot), None, C.c_int32(0), C.byref(nr)))
+        ids = np.zeros(max(tot.value, 1), np.uint32); off = np.zeros(nr.value + 1, np.int64)
+        self._ck(lib().mmb_flip_log(self._h, _p(ids), C.c_int64(tot.value), C.byref(tot), _p(off), C.c_int32(nr.value + 1), C.byref(nr)))
+        return ids[:tot.value], off, int(tot.value)
 
     def download_topology(self, neighbours=True, edges=True):
         """resident cells [nc][dim+1], perm [nc], neighbours [nc][3] and edges [ne][4] (2-D)"""

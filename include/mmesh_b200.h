@@ -122,6 +122,12 @@ int mmb_patch_mesh(mmb_context* ctx, int64_t nv_new, int64_t n_vert, const int32
    (mmb_download_topology reads them back); marks, flags, candidates and projection pairs of the old topology are void.
    The result is the constrained Delaunay triangulation: unique for points in general position, so it equals CGAL's. */
 int mmb_restore_delaunay(mmb_context* ctx, const int64_t* vertex_id_host, int32_t max_rounds, mmb_flip_result* out);
+/* The flips of the last mmb_restore_delaunay, round after round: edge_id = 3 * cell + slot with cell and slot as they were when the
+   flip was applied, i.e. the arguments f, i of Triangulation_data_structure_2::flip(f, i); round_off [rounds + 1] delimits the rounds.
+   The flips of one round touch disjoint cells, so a host TDS that replays them round by round (any order inside a round) ends up
+   slot for slot in the state mmb_download_topology returns.  At most nc flips are logged (n_total reports all of them). */
+int mmb_flip_log(mmb_context* ctx, uint32_t* edge_id_host, int64_t cap, int64_t* n_total, int64_t* round_off_host, int32_t round_cap,
+                 int32_t* n_rounds);
 /* resident topology -> host: cells [nc][dim+1] (TDS order), perm [nc], neighbours [nc][3] (2-D, if uploaded), edges [ne][4]
    (2-D); NULL skips an array */
 int mmb_download_topology(mmb_context* ctx, int32_t* cells_host, uint8_t* perm_host, int32_t* cell_nb_host, int32_t* edges_host);

@@ -107,6 +107,8 @@ int main(int argc, char** argv) {
       MMesh<2> g3(0);
       g3.setSnapshot(s);
       const mmb_flip_result fr = g3.restoreDelaunay(s);
+      const auto flog = g3.lastFlips();
+      std::printf("fliplog %lld %zu %zu\n", (long long)flog.total, flog.flips.size(), flog.roundOffsets.size());
       std::printf("flip %lld %d %d %lld\nflipcells", (long long)fr.n_flips, (int)fr.rounds, (int)fr.converged, (long long)fr.n_constrained_illegal);
       for (auto& c : s.cells) std::printf(" %d %d %d", c[0], c[1], c[2]);
       std::printf("\nflipedges");

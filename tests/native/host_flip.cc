@@ -12,6 +12,18 @@ extern "C" {
 // cells / nb [nc][3] in/out; perm [nc] out (may be null); keys = sorted (min << 32 | max) interface edges; vid may be null.
 // result: [0] flips, [1] rounds, [2] converged, [3] illegal left, [4] constrained illegal, [5] inverted, [6] broken
 // trace (may be null): number of flips per round, up to max_rounds entries
+static uint32_t* g_log = nullptr; static long g_log_cap = 0, g_log_n = 0;
+// as hf_restore, additionally logging the flips as edge ids 3 * cell + slot (the arguments of TDS::flip) in application order
+int hf_restore(const double* xy, long nv, int32_t* cells, int32_t* nb, uint8_t* perm, long nc, const uint8_t* v_if,
+               const unsigned long long* keys, int nkeys, const int64_t* vid, int max_rounds, long long* result, int32_t* trace);
+long hf_restore_log(const double* xy, long nv, int32_t* cells, int32_t* nb, uint8_t* perm, long nc, const uint8_t* v_if,
+                    const unsigned long long* keys, int nkeys, const int64_t* vid, int max_rounds, long long* result, int32_t* trace,
+                    uint32_t* log, long log_cap) {
+  g_log = log; g_log_cap = log_cap; g_log_n = 0;
+  hf_restore(xy, nv, cells, nb, perm, nc, v_if, keys, nkeys, vid, max_rounds, result, trace);
+  g_log = nullptr;
+  return g_log_n;
+}
 int hf_restore(const double* xy, long nv, int32_t* cells, int32_t* nb, uint8_t* perm, long nc, const uint8_t* v_if,
                const unsigned long long* keys, int nkeys, const int64_t* vid, int max_rounds, long long* result, int32_t* trace) {
   (void)nv;
@@ -34,7 +46,11 @@ int hf_restore(const double* xy, long nv, int32_t* cells, int32_t* nb, uint8_t* 
     for (long c = 0; c < nc; ++c) sel[c] = (uint8_t)flip_select_cell(c, ill[c], nb, claim.data());
     const unsigned long long before = fc.flips;
     for (long c = 0; c < nc; ++c)
-      if (sel[c]) { flip_apply_cell(c, sel[c] - 1, cv0.data(), cv1.data(), cv2.data(), nb, vid, perm); ++fc.flips; }
+      if (sel[c]) {
+        if (g_log && g_log_n < g_log_cap) g_log[g_log_n] = 3u * (uint32_t)c + (uint32_t)(sel[c] - 1);
+        if (g_log) ++g_log_n;
+        flip_apply_cell(c, sel[c] - 1, cv0.data(), cv1.data(), cv2.data(), nb, vid, perm); ++fc.flips;
+      }
     if (trace) trace[rounds] = (int32_t)(fc.flips - before);
     ++rounds;
   }

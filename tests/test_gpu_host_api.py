@@ -104,6 +104,7 @@ def test_host_class_user_loop(oracle, tmp_path):
     oflags, onill = oracle.legality(m.xy, None, fe.astype(np.int32))
     assert int(lines["flipillegal"][0]) == onill == fl[3]
     assert lines["flipinverted"] == ["GridError"]
+    assert [int(v) for v in lines["fliplog"]] == [fl[0], fl[0], fl[1] + 1]            # total, logged entries, rounds + 1 offsets
 
 
 ADAPT_EXE = os.path.join(ROOT, "tests", "native", "_build", "adapt_handle_test")

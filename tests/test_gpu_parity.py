@@ -775,6 +775,23 @@ def test_restore_delaunay_on_device(gpu_ctx_factory, oracle):
                      P(vid64), C.c_int(1000), P(r), None)
         assert (res["n_flips"], res["rounds"], res["n_constrained_illegal"]) == (int(r[0]), int(r[1]), int(r[4]))
         assert np.array_equal(cells, hc) and np.array_equal(nb, hnb) and np.array_equal(perm, hperm)
+        # the flip log: per round the same set of (cell, slot) as the host build, and replaying it with TDS::flip semantics on
+        # the original tables gives the device's tables slot for slot
+        from test_host_flip import replay_flips
+        fids, off, tot = ctx.flip_log()
+        assert tot == res["n_flips"] == len(fids) and len(off) == res["rounds"] + 1 and off[0] == 0 and off[-1] == tot
+        hlog = np.zeros(4 * m.nc + 16, np.uint32); htrace = np.zeros(1000, np.int32); hr = np.zeros(8, np.int64)
+        lc, lnb, lperm = m.cells.copy(), m.nb.copy(), perm0.copy()
+        L.hf_restore_log.restype = C.c_long
+        hn = L.hf_restore_log(P(np.ascontiguousarray(xy)), C.c_long(m.nv), P(lc), P(lnb), P(lperm), C.c_long(m.nc), P(v_if), P(keys), C.c_int(keys.shape[0]),
+                              P(vid64), C.c_int(1000), P(hr), P(htrace), P(hlog), C.c_long(hlog.shape[0]))
+        hoff = np.concatenate([[0], np.cumsum(htrace[:int(hr[1])])])
+        assert hn == tot and np.array_equal(hoff, off)
+        for r_ in range(len(off) - 1):
+            assert np.array_equal(np.sort(fids[off[r_]:off[r_ + 1]]), np.sort(hlog[off[r_]:off[r_ + 1]]))
+        if m.nc <= 30000:
+            rc_, rnb_ = replay_flips(m.cells, m.nb, fids)
+            assert np.array_equal(rc_, cells) and np.array_equal(rnb_, nb)
         # oracle (sequential Lawson) and, unconstrained, Qhull
         oc, _, oflips = oracle.restore_delaunay_2d(xy, m.cells, m.nb, m.segs)
         assert oflips > 0 and tri_set(oc) == tri_set(cells)

@@ -67,6 +67,22 @@ def host_flip():
 
     restore.active = restore_active
 
+    def restore_log(xy, cells, nb, segs):
+        """(final cells, final nb, edge ids in application order, round offsets)"""
+        xy = np.ascontiguousarray(xy, np.float64)
+        cells = np.ascontiguousarray(cells, np.int32).copy(); nb = np.ascontiguousarray(nb, np.int32).copy()
+        nc, nv = cells.shape[0], xy.shape[0]
+        v_if, keys = facet_keys(np.asarray(segs).reshape(-1, 2), nv)
+        res = np.zeros(8, np.int64); trace = np.zeros(1000, np.int32); log = np.zeros(4 * nc + 16, np.uint32)
+        L.hf_restore_log.restype = C.c_long
+        n = L.hf_restore_log(P(xy), C.c_long(nv), P(cells), P(nb), None, C.c_long(nc), P(v_if), P(keys), C.c_int(keys.shape[0]), None,
+                             C.c_int(1000), P(res), P(trace), P(log), C.c_long(log.shape[0]))
+        off = np.concatenate([[0], np.cumsum(trace[:int(res[1])])]).astype(np.int64)
+        assert n == int(res[0]) == off[-1]
+        return cells, nb, log[:n], off
+
+    restore.log = restore_log
+
     def edges(cells, nb, cap):
         out = np.zeros((cap, 4), np.int32)
         n = L.hf_edges(P(np.ascontiguousarray(cells, np.int32)), P(np.ascontiguousarray(nb, np.int32)), C.c_long(cells.shape[0]), P(out), C.c_long(cap))
@@ -75,6 +91,28 @@ def host_flip():
     restore.edges = edges
     restore.perm = lambda a, b, c: int(L.hf_perm(C.c_int64(a), C.c_int64(b), C.c_int64(c)))
     return restore
+
+
+def replay_flips(cells, nb, ids):
+    """Triangulation_data_structure_2::flip(f, i) (CGAL/Triangulation_data_structure_2.h:885-915) applied to index tables, one flip
+    after the other -- what a host TDS does with the log of mmb_flip_log."""
+    cells = np.array(cells, np.int32); nb = np.array(nb, np.int32)
+    for e in np.asarray(ids, np.int64).tolist():
+        f, i = e // 3, e % 3
+        n = int(nb[f, i]); ni = int(np.nonzero(nb[n] == f)[0][0])
+        ccw, cw = (i + 1) % 3, (i + 2) % 3
+        nccw, ncw = (ni + 1) % 3, (ni + 2) % 3
+        tr, bl = int(nb[f, ccw]), int(nb[n, nccw])
+        tri = int(np.nonzero(nb[tr] == f)[0][0]) if tr >= 0 else -1
+        bli = int(np.nonzero(nb[bl] == n)[0][0]) if bl >= 0 else -1
+        apex, opp = cells[f, i], cells[n, ni]
+        cells[f, cw] = opp; cells[n, ncw] = apex
+        nb[f, i] = bl
+        if bl >= 0: nb[bl, bli] = f
+        nb[f, ccw] = n; nb[n, nccw] = f
+        nb[n, ni] = tr
+        if tr >= 0: nb[tr, tri] = n
+    return cells, nb
 
 
 def tri_set(cells):
@@ -260,3 +298,18 @@ def test_flips_on_irregular_triangulations_with_constraints(host_flip, oracle):
     flags, nill = oracle.legality(xy, None, e)
     bad = e[flags == 0]
     assert nill == r["constrained"] and all(tuple(sorted(q[:2])) in skeys for q in bad.tolist())
+
+
+def test_flip_log_replays_to_the_same_tables(host_flip, oracle):
+    """The log of flips (cell, slot) in round order -- what mmb_flip_log hands to the host -- replayed with TDS::flip semantics on the
+    original tables gives the restored tables slot for slot; shuffling the flips INSIDE a round changes nothing (they touch disjoint
+    cells), which is what allows the device to log them in any order."""
+    rng = np.random.default_rng(4)
+    m, xy = moved_mesh(oracle, 40, 0.27, 90)
+    cells, nb, ids, off = host_flip.log(xy, m.cells, m.nb, m.segs)
+    assert len(ids) > 100 and len(off) > 3
+    rc, rnb = replay_flips(m.cells, m.nb, ids)
+    assert np.array_equal(rc, cells) and np.array_equal(rnb, nb)
+    shuffled = np.concatenate([rng.permutation(ids[off[r]:off[r + 1]]) for r in range(len(off) - 1)])
+    rc2, rnb2 = replay_flips(m.cells, m.nb, shuffled)
+    assert np.array_equal(rc2, cells) and np.array_equal(rnb2, nb)
